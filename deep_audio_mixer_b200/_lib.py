@@ -1,0 +1,66 @@
+"""ctypes binding of libdam_b200.so (include/dam_b200.h).  There is no CPU fallback: if the
+library is missing or a call fails, this module raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdam_b200.so')
+
+DAM_I16, DAM_F32, DAM_F64 = 0, 1, 2
+
+_lib = None
+
+_c = ctypes
+_vp, _i, _i64, _d = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double
+
+# name -> (restype, argtypes); must list every symbol include/dam_b200.h declares
+SIGNATURES = {
+    'dam_version': (_c.c_char_p, []),
+    'dam_last_error': (_c.c_char_p, []),
+    'dam_stft_num_frames': (_i64, [_i64, _i]),
+    'dam_stft_db': (_i, [_vp, _i, _i, _i64, _i64, _i64, _i64, _i64, _d, _vp, _vp, _i, _i, _d, _d, _i,
+                         _vp, _i, _vp, _vp]),
+}
+
+
+class DamError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DamError('%s not found: build it with `python -m deep_audio_mixer_b200.build` '
+                           '(there is no CPU fallback)' % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = lib().dam_last_error().decode('utf-8', 'replace')
+        raise DamError('%s failed with status %d: %s' % (what, status, msg))
+
+
+def dtype_code(torch_dtype):
+    import torch
+    table = {torch.int16: DAM_I16, torch.float32: DAM_F32, torch.float64: DAM_F64}
+    if torch_dtype not in table:
+        raise TypeError('unsupported dtype %s (int16, float32, float64)' % torch_dtype)
+    return table[torch_dtype]
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return ctypes.c_void_p(s.cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
