@@ -32,8 +32,11 @@ constexpr int kRow = 34;          // complex elements per k' row in the exchange
 constexpr int kKp = 33;           // stage-2 tasks per frame
 
 template <typename R> struct Cx;
-template <> struct Cx<float>  { using type = float2;  static constexpr int kXch = 32 * kRow + 2; };  // /2 odd
-template <> struct Cx<double> { using type = double2; static constexpr int kXch = 32 * kRow + 1; };  // odd
+// Exchange buffer: per frame 33 rows (k' = 0..32) of kRow complex values.  The per-frame stride is
+// chosen so the 128-bit stage-2 loads (lane = frame + 8*(k' mod 4)) are bank-conflict free:
+// float: stride/2 odd (two complex per load); double: stride odd (one complex per load).
+template <> struct Cx<float>  { using type = float2;  static constexpr int kXch = 33 * kRow; };      // 1122
+template <> struct Cx<double> { using type = double2; static constexpr int kXch = 33 * kRow + 1; };  // 1123
 
 struct StftParams {
     const void* audio;
@@ -47,37 +50,163 @@ struct StftParams {
     int hop;
     long long T;                  // frames per row
     long long tiles_per_row, n_tiles;
-    float amin2;                  // amin^2 (power floor)
-    float log_scale;              // multiplier/2 * log10(2)
-    double log_scale_d;
+    float log_scale;              // multiplier/2 * log10(2): dB = log_scale * log2(|X|^2)
+    float floor_db;               // multiplier * log10(amin), the clamp applied in the dB domain
+    double log_scale_d, floor_db_d;
     void* out;
     double* stats;
 };
 
-template <typename P>
-__device__ __forceinline__ P load_sample(const void* base, int dtype, long long idx) {
-    if (dtype == DAM_F32) return (P)__ldg(reinterpret_cast<const float*>(base) + idx);
-    if (dtype == DAM_I16) return (P)__ldg(reinterpret_cast<const short*>(base) + idx);
-    return (P)__ldg(reinterpret_cast<const double*>(base) + idx);
+// ---- staging --------------------------------------------------------------------------------
+// Samples [g0, g0 + span) of one row go to shared memory as the compute type R after the
+// prologue the reference performs in numpy, in the SOURCE precision P (float for int16/float32
+// sources, double for float64): x*input_scale, channel mean (sum in channel order, then a
+// division by C -- a multiply by 1/C when C is a power of two, which is bit-identical), row gain.
+// Loads are issued in batches so every thread keeps several global requests in flight; interior,
+// unit-stride, 16-byte-aligned tiles use 128-bit loads and vector shared-memory stores.
+template <typename SRC> struct VecOf { static constexpr int kN = 16 / sizeof(SRC); };
+
+template <typename P, typename SRC>
+__device__ __forceinline__ void unpack16(const uint4& raw, P (&v)[VecOf<SRC>::kN]) {
+    const SRC* e = reinterpret_cast<const SRC*>(&raw);
+#pragma unroll
+    for (int j = 0; j < VecOf<SRC>::kN; ++j) v[j] = (P)e[j];
 }
 
-// One staged sample: scale, channel mean and row gain in the source precision P (what numpy
-// does on the reference path), then converted to the compute type.
-template <typename P>
-__device__ __forceinline__ P staged_value(const StftParams& p, long long row_off, long long g, P gain,
-                                          bool has_gain) {
-    const long long off = row_off + g * p.samp_stride;
-    P acc = load_sample<P>(p.audio, p.audio_dtype, off) * (P)p.input_scale;
-    if (p.channels > 1) {
-        for (int c = 1; c < p.channels; ++c)
-            acc += load_sample<P>(p.audio, p.audio_dtype, off + c * p.chan_stride) * (P)p.input_scale;
-        acc = acc / (P)p.channels;
+template <typename R, int V>
+__device__ __forceinline__ void store_vec(R* dst, const R (&v)[V]) {
+    constexpr int kBytes = V * (int)sizeof(R);
+    if (kBytes == 8) {
+        *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(v);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kBytes / 16; ++k)
+            reinterpret_cast<uint4*>(dst)[k] = reinterpret_cast<const uint4*>(v)[k];
     }
-    if (has_gain) acc = gain * acc;
-    return acc;
 }
 
-template <typename R, typename OUT>
+template <typename P>
+struct Prologue {
+    P scale, gain, inv_c, f_c;
+    int C;
+    __device__ __forceinline__ P finish(P acc) const {
+        if (C > 1) acc = (inv_c != (P)0) ? acc * inv_c : acc / f_c;
+        return gain * acc;
+    }
+};
+
+template <typename R, typename P, typename SRC>
+__device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ s_stage, long long row,
+                                           long long g0, int span, int tid) {
+    constexpr int V = VecOf<SRC>::kN;
+    constexpr int U = 4;                         // vector loads in flight per thread and channel
+    const SRC* __restrict__ base = reinterpret_cast<const SRC*>(p.audio) + row * p.row_stride;
+    const long long n = p.n_samples;
+    const int C = p.channels;
+    Prologue<P> pro;
+    pro.C = C;
+    pro.scale = (P)p.input_scale;
+    pro.gain = p.row_gain != nullptr ? (P)p.row_gain[row] : (P)1;
+    pro.f_c = (P)C;
+    pro.inv_c = ((C & (C - 1)) == 0) ? (P)1 / (P)C : (P)0;
+
+    int done = 0;
+    const bool interior = g0 >= 0 && g0 + span <= n && p.samp_stride == 1;
+    if (interior) {
+        const SRC* src = base + g0;
+        const bool aligned = ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0) &&
+                             (C == 1 || ((p.chan_stride * (long long)sizeof(SRC)) & 15ll) == 0);
+        if (aligned) {
+            const int nvec = span / V;
+            for (int v0 = tid; v0 < nvec; v0 += kThreads * U) {
+                P acc[U][V];
+                uint4 raw[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int v = v0 + u * kThreads;
+                    raw[u] = v < nvec ? __ldg(reinterpret_cast<const uint4*>(src) + v) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    unpack16<P, SRC>(raw[u], acc[u]);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[u][j] *= pro.scale;
+                }
+                for (int c = 1; c < C; ++c) {
+                    const uint4* sc = reinterpret_cast<const uint4*>(src + c * p.chan_stride);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int v = v0 + u * kThreads;
+                        raw[u] = v < nvec ? __ldg(sc + v) : make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        P t[V];
+                        unpack16<P, SRC>(raw[u], t);
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[u][j] += t[j] * pro.scale;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int v = v0 + u * kThreads;
+                    if (v < nvec) {
+                        R r[V];
+#pragma unroll
+                        for (int j = 0; j < V; ++j) r[j] = (R)pro.finish(acc[u][j]);
+                        store_vec<R, V>(s_stage + v * V, r);
+                    }
+                }
+            }
+            done = nvec * V;
+        }
+    }
+    // general path: edges (reflection), strided or unaligned sources, vector tail
+    constexpr int UG = 8;
+    for (int i0 = done + tid; i0 < span; i0 += kThreads * UG) {
+        P acc[UG];
+        long long off[UG];
+#pragma unroll
+        for (int u = 0; u < UG; ++u) {
+            const int i = i0 + u * kThreads;
+            long long g = g0 + i;
+            g = g < 0 ? -g : g;
+            g = g >= n ? 2 * (n - 1) - g : g;
+            g = i < span ? g : 0;
+            off[u] = g * p.samp_stride;
+            acc[u] = (P)__ldg(base + off[u]) * pro.scale;
+        }
+        for (int c = 1; c < C; ++c) {
+            P t[UG];
+#pragma unroll
+            for (int u = 0; u < UG; ++u) t[u] = (P)__ldg(base + off[u] + c * p.chan_stride);
+#pragma unroll
+            for (int u = 0; u < UG; ++u) acc[u] += t[u] * pro.scale;
+        }
+#pragma unroll
+        for (int u = 0; u < UG; ++u) {
+            const int i = i0 + u * kThreads;
+            if (i < span) s_stage[i] = (R)pro.finish(acc[u]);
+        }
+    }
+}
+
+// L2 prefetch of the samples the NEXT tile of this CTA will stage (no registers, no smem).
+__device__ __forceinline__ void prefetch_tile(const StftParams& p, long long row, long long g0, int span,
+                                              int elem_bytes, int tid) {
+    if (p.samp_stride != 1) return;
+    long long lo = g0 < 0 ? 0 : g0;
+    long long hi = g0 + span > p.n_samples ? p.n_samples : g0 + span;
+    const char* base = reinterpret_cast<const char*>(p.audio) + row * p.row_stride * elem_bytes;
+    const long long bytes = (hi - lo) * elem_bytes;
+    for (int c = 0; c < p.channels; ++c) {
+        const char* q = base + (c * p.chan_stride + lo) * elem_bytes;
+        for (long long o = (long long)tid * 128; o < bytes; o += (long long)kThreads * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(q + o));
+    }
+}
+
+template <typename R, typename OUT, bool kStats>
 __global__ void __launch_bounds__(kThreads, sizeof(R) == 4 ? 2 : 1)
 stft_db_kernel(const StftParams p) {
     using C = typename Cx<R>::type;
@@ -100,7 +229,9 @@ stft_db_kernel(const StftParams p) {
 
     const int hop = p.hop;
     const long long T = p.T;
-    double st_sum = 0.0, st_sq = 0.0, st_cnt = 0.0;
+    const int elem_bytes = p.audio_dtype == DAM_I16 ? 2 : (p.audio_dtype == DAM_F32 ? 4 : 8);
+    float st_sum = 0.f, st_sq = 0.f;
+    double st_sum_d = 0.0, st_sq_d = 0.0, st_cnt = 0.0;
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const long long row = tile / p.tiles_per_row;
@@ -111,30 +242,24 @@ stft_db_kernel(const StftParams p) {
 
         // ---- staging: samples [t0*hop - 1024, (t0+nf-1)*hop + 1024) with reflection at the row ends
         {
-            const long long row_off = row * p.row_stride;
             const long long g0 = t0 * hop - kNfft / 2;
             const int span = (nf - 1) * hop + kNfft;
-            const long long n = p.n_samples;
-            const bool has_gain = p.row_gain != nullptr;
-            const double gain_d = has_gain ? p.row_gain[row] : 1.0;
-            if (p.audio_dtype == DAM_F64) {
-                for (int i = tid; i < span; i += kThreads) {
-                    long long g = g0 + i;
-                    g = g < 0 ? -g : g;
-                    g = g >= n ? 2 * (n - 1) - g : g;
-                    s_stage[i] = (R)staged_value<double>(p, row_off, g, gain_d, has_gain);
-                }
-            } else {
-                const float gain_f = (float)gain_d;
-                for (int i = tid; i < span; i += kThreads) {
-                    long long g = g0 + i;
-                    g = g < 0 ? -g : g;
-                    g = g >= n ? 2 * (n - 1) - g : g;
-                    s_stage[i] = (R)staged_value<float>(p, row_off, g, gain_f, has_gain);
-                }
-            }
+            if (p.audio_dtype == DAM_F32)      stage_tile<R, float, float>(p, s_stage, row, g0, span, tid);
+            else if (p.audio_dtype == DAM_I16) stage_tile<R, float, short>(p, s_stage, row, g0, span, tid);
+            else                               stage_tile<R, double, double>(p, s_stage, row, g0, span, tid);
         }
         __syncthreads();
+
+        // pull the next tile's samples towards L2 while this one is transformed
+        {
+            const long long nt = tile + gridDim.x;
+            if (nt < p.n_tiles) {
+                const long long nrow = nt / p.tiles_per_row;
+                const long long nt0 = (nt - nrow * p.tiles_per_row) * kFT;
+                const int nnf = (int)((T - nt0) < kFT ? (T - nt0) : kFT);
+                prefetch_tile(p, nrow, nt0 * hop - kNfft / 2, (nnf - 1) * hop + kNfft, elem_bytes, tid);
+            }
+        }
 
         // ---- stage 1: warp = frame, lane = b
         R sr[32], si[32];
@@ -149,8 +274,14 @@ stft_db_kernel(const StftParams p) {
             if (warp < nf) {
                 dam_rfft64_packed<R>(x, sr, si);
                 C* dst = s_xch + warp * kXch + lane;
+                {
+                    C v; v.x = sr[0]; v.y = R(0);
+                    dst[0] = v;                        // row 0:  Y[0]  (real)
+                    v.x = si[0];
+                    dst[32 * kRow] = v;                // row 32: Y[32] (real)
+                }
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
+                for (int k = 1; k < 32; ++k) {
                     C v; v.x = sr[k]; v.y = si[k];
                     dst[k * kRow] = v;
                 }
@@ -163,57 +294,71 @@ stft_db_kernel(const StftParams p) {
         for (int task = tid; task < kKp * kFT; task += kThreads) {
             const int kp = task >> 3, t = task & 7;
             if (t >= nf) continue;
-            const C* src = s_xch + t * kXch + (kp == 32 ? 0 : kp) * kRow;
+            const C* src = s_xch + t * kXch + kp * kRow;
             const C* tw = s_tw + kp * kRow;
-            const bool real_lo = (kp == 0), real_hi = (kp == 32);
+            if (sizeof(R) == 4) {
+                // two complex values per 128-bit load (rows are 16-byte aligned by construction)
+                const float4* s4 = reinterpret_cast<const float4*>(src);
+                const float4* w4 = reinterpret_cast<const float4*>(tw);
 #pragma unroll
-            for (int b = 0; b < 32; ++b) {
-                const C v = src[b];
-                const C w = tw[b];
-                const R vr = real_hi ? v.y : v.x;
-                const R vi = (real_lo || real_hi) ? R(0) : v.y;
-                sr[b] = vr * w.x - vi * w.y;
-                si[b] = vr * w.y + vi * w.x;
+                for (int b2 = 0; b2 < 16; ++b2) {
+                    const float4 v = s4[b2];
+                    const float4 w = w4[b2];
+                    sr[2 * b2] = v.x * w.x - v.y * w.y;
+                    si[2 * b2] = v.x * w.y + v.y * w.x;
+                    sr[2 * b2 + 1] = v.z * w.z - v.w * w.w;
+                    si[2 * b2 + 1] = v.z * w.w + v.w * w.z;
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < 32; ++b) {
+                    const C v = src[b];
+                    const C w = tw[b];
+                    sr[b] = v.x * w.x - v.y * w.y;
+                    si[b] = v.x * w.y + v.y * w.x;
+                }
             }
             dam_cfft32<R>(sr, si);
 
-            OUT* o = reinterpret_cast<OUT*>(p.out) + (row * kBins) * T + t0 + t;
-            const bool mirror_ok = !(real_lo || real_hi);
+            // bins k'+64q (q < 16) walk up from row k'; mirrors 2048-k'-64q (q >= 16) walk down from
+            // row 1024-k'.  k' = 0 and 32 own only 17 / 16 distinct bins.
+            const long long stride = 64 * T;
+            OUT* o_lo = reinterpret_cast<OUT*>(p.out) + (row * kBins + kp) * T + t0 + t;
+            OUT* o_hi = reinterpret_cast<OUT*>(p.out) + (row * kBins + (kNfft / 2 - kp)) * T + t0 + t;
+            const bool mirror_ok = (kp != 0) && (kp != 32);
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
-                const int f = q < 16 ? kp + 64 * q : kNfft - kp - 64 * q;
-                const bool valid = q < 16 ? true : (q == 16 ? (mirror_ok || real_lo) : mirror_ok);
+                const bool valid = q < 16 ? true : (q == 16 ? (kp != 32) : mirror_ok);
+                OUT* o = q < 16 ? o_lo + q * stride : o_hi - (q - 16) * stride;
                 float db;
                 if (sizeof(R) == 4) {
-                    float pw = fmaf((float)sr[q], (float)sr[q], (float)si[q] * (float)si[q]);
-                    pw = fmaxf(pw, p.amin2);
-                    db = p.log_scale * __log2f(pw);
-                    if (valid) o[(long long)f * T] = (OUT)db;
+                    const float pw = fmaf((float)sr[q], (float)sr[q], (float)si[q] * (float)si[q]);
+                    db = fmaxf(p.log_scale * __log2f(pw), p.floor_db);
+                    if (valid) *o = (OUT)db;
                 } else {
                     // |X|^2 in double, log2 split into exponent + mantissa so the only fp32 error is
-                    // lg2.approx on [1, 2) (2^-22 absolute); recombined in double.
-                    float pw = (float)(sr[q] * sr[q] + si[q] * si[q]);
-                    pw = fmaxf(pw, p.amin2);
+                    // lg2.approx on [1, 2) (2^-22 absolute); recombined and clamped in double.
+                    const float pw = (float)(sr[q] * sr[q] + si[q] * si[q]);
                     const int bits = __float_as_int(pw);
                     const int e = (bits >> 23) - 127;
                     const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
-                    const double l2 = (double)e + (double)__log2f(m);
-                    const double dbd = p.log_scale_d * l2;
+                    double dbd = p.log_scale_d * ((double)e + (double)__log2f(m));
+                    dbd = (pw >= 1.17549435e-38f) ? dbd : -INFINITY;
+                    dbd = fmax(dbd, p.floor_db_d);
                     db = (float)dbd;
-                    if (valid) o[(long long)f * T] = (OUT)dbd;
+                    if (valid) *o = (OUT)dbd;
                 }
-                if (p.stats != nullptr && valid) {
-                    st_sum += db; st_sq += (double)db * db; st_cnt += 1.0;
-                }
+                if (kStats && valid) { st_sum += db; st_sq = fmaf(db, db, st_sq); st_cnt += 1.0; }
             }
+            if (kStats) { st_sum_d += st_sum; st_sq_d += st_sq; st_sum = 0.f; st_sq = 0.f; }
         }
     }
 
-    if (p.stats != nullptr) {
-        st_sum = dam_warp_sum(st_sum); st_sq = dam_warp_sum(st_sq); st_cnt = dam_warp_sum(st_cnt);
+    if (kStats) {
+        st_sum_d = dam_warp_sum(st_sum_d); st_sq_d = dam_warp_sum(st_sq_d); st_cnt = dam_warp_sum(st_cnt);
         if (lane == 0 && st_cnt > 0.0) {
-            atomicAdd(p.stats + 0, st_sum);
-            atomicAdd(p.stats + 1, st_sq);
+            atomicAdd(p.stats + 0, st_sum_d);
+            atomicAdd(p.stats + 1, st_sq_d);
             atomicAdd(p.stats + 2, st_cnt);
         }
     }
@@ -279,10 +424,10 @@ size_t smem_bytes(int hop) {
     return kNfft * sizeof(R) + (size_t)kKp * kRow * sizeof(C) + (xch > stage ? xch : stage);
 }
 
-template <typename R, typename OUT>
+template <typename R, typename OUT, bool kStats>
 int launch(const StftParams& p, cudaStream_t stream) {
     const size_t smem = smem_bytes<R>(p.hop);
-    auto kern = stft_db_kernel<R, OUT>;
+    auto kern = stft_db_kernel<R, OUT, kStats>;
     static std::mutex mu;
     static bool configured[64] = {};
     static int blocks_per_sm[64] = {};
@@ -347,16 +492,18 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     p.hop = hop; p.T = 1 + n_samples / hop;
     p.tiles_per_row = (p.T + kFT - 1) / kFT;
     p.n_tiles = p.tiles_per_row * n_rows;
-    p.amin2 = (float)(amin * amin);
     p.log_scale_d = multiplier * 0.5 * 0.30102999566398119521373889472449302676819;
     p.log_scale = (float)p.log_scale_d;
+    p.floor_db_d = amin > 0.0 ? multiplier * log10(amin) : -INFINITY;
+    p.floor_db = (float)p.floor_db_d;
     p.out = out; p.stats = stats;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const bool st = stats != nullptr;
     if (compute_dtype == DAM_F32) {
         p.twiddle = tw->f32;
-        return launch<float, float>(p, s);
+        return st ? launch<float, float, true>(p, s) : launch<float, float, false>(p, s);
     }
     p.twiddle = tw->f64;
-    if (out_dtype == DAM_F32) return launch<double, float>(p, s);
-    return launch<double, double>(p, s);
+    if (out_dtype == DAM_F32) return st ? launch<double, float, true>(p, s) : launch<double, float, false>(p, s);
+    return st ? launch<double, double, true>(p, s) : launch<double, double, false>(p, s);
 }
