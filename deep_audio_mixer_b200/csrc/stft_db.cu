@@ -32,11 +32,11 @@ constexpr int kRow = 34;          // complex elements per k' row in the exchange
 constexpr int kKp = 33;           // stage-2 tasks per frame
 
 template <typename R> struct Cx;
-// Exchange buffer: per frame 33 rows (k' = 0..32) of kRow complex values.  The per-frame stride is
+// Exchange buffer: per frame 32 rows (k' = 0..31) of kRow complex values (k' = 32 never leaves stage 1).  The per-frame stride is
 // chosen so the 128-bit stage-2 loads (lane = frame + 8*(k' mod 4)) are bank-conflict free:
 // float: stride/2 odd (two complex per load); double: stride odd (one complex per load).
-template <> struct Cx<float>  { using type = float2;  static constexpr int kXch = 33 * kRow; };      // 1122
-template <> struct Cx<double> { using type = double2; static constexpr int kXch = 33 * kRow + 1; };  // 1123
+template <> struct Cx<float>  { using type = float2;  static constexpr int kXch = 32 * kRow + 2; };  // 1090
+template <> struct Cx<double> { using type = double2; static constexpr int kXch = 32 * kRow + 1; };  // 1089
 
 struct StftParams {
     const void* audio;
@@ -89,11 +89,21 @@ template <typename P>
 struct Prologue {
     P scale, gain, inv_c, f_c;
     int C;
+    bool unit_scale, has_gain;
+    __device__ __forceinline__ P load(P raw) const { return unit_scale ? raw : raw * scale; }
     __device__ __forceinline__ P finish(P acc) const {
         if (C > 1) acc = (inv_c != (P)0) ? acc * inv_c : acc / f_c;
-        return gain * acc;
+        return has_gain ? gain * acc : acc;
     }
 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
 
 template <typename R, typename P, typename SRC>
 __device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ s_stage, long long row,
@@ -106,7 +116,9 @@ __device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ 
     Prologue<P> pro;
     pro.C = C;
     pro.scale = (P)p.input_scale;
-    pro.gain = p.row_gain != nullptr ? (P)p.row_gain[row] : (P)1;
+    pro.has_gain = p.row_gain != nullptr;
+    pro.gain = pro.has_gain ? (P)p.row_gain[row] : (P)1;
+    pro.unit_scale = p.input_scale == 1.0;
     pro.f_c = (P)C;
     pro.inv_c = ((C & (C - 1)) == 0) ? (P)1 / (P)C : (P)0;
 
@@ -118,6 +130,11 @@ __device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ 
                              (C == 1 || ((p.chan_stride * (long long)sizeof(SRC)) & 15ll) == 0);
         if (aligned) {
             const int nvec = span / V;
+            if (sizeof(R) == sizeof(SRC) && sizeof(P) == sizeof(SRC) && C == 1 && pro.unit_scale && !pro.has_gain) {
+                // plain copy (same type, mono, no scaling): asynchronous 16-byte global->shared copies
+                for (int v = tid; v < nvec; v += kThreads) cp_async16(s_stage + v * V, src + v * V);
+                cp_async_wait_all();
+            } else
             for (int v0 = tid; v0 < nvec; v0 += kThreads * U) {
                 P acc[U][V];
                 uint4 raw[U];
@@ -130,7 +147,7 @@ __device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ 
                 for (int u = 0; u < U; ++u) {
                     unpack16<P, SRC>(raw[u], acc[u]);
 #pragma unroll
-                    for (int j = 0; j < V; ++j) acc[u][j] *= pro.scale;
+                    for (int j = 0; j < V; ++j) acc[u][j] = pro.load(acc[u][j]);
                 }
                 for (int c = 1; c < C; ++c) {
                     const uint4* sc = reinterpret_cast<const uint4*>(src + c * p.chan_stride);
@@ -144,7 +161,7 @@ __device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ 
                         P t[V];
                         unpack16<P, SRC>(raw[u], t);
 #pragma unroll
-                        for (int j = 0; j < V; ++j) acc[u][j] += t[j] * pro.scale;
+                        for (int j = 0; j < V; ++j) acc[u][j] += pro.load(t[j]);
                     }
                 }
 #pragma unroll
@@ -174,14 +191,14 @@ __device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ 
             g = g >= n ? 2 * (n - 1) - g : g;
             g = i < span ? g : 0;
             off[u] = g * p.samp_stride;
-            acc[u] = (P)__ldg(base + off[u]) * pro.scale;
+            acc[u] = pro.load((P)__ldg(base + off[u]));
         }
         for (int c = 1; c < C; ++c) {
             P t[UG];
 #pragma unroll
             for (int u = 0; u < UG; ++u) t[u] = (P)__ldg(base + off[u] + c * p.chan_stride);
 #pragma unroll
-            for (int u = 0; u < UG; ++u) acc[u] += t[u] * pro.scale;
+            for (int u = 0; u < UG; ++u) acc[u] += pro.load(t[u]);
         }
 #pragma unroll
         for (int u = 0; u < UG; ++u) {
@@ -206,6 +223,44 @@ __device__ __forceinline__ void prefetch_tile(const StftParams& p, long long row
     }
 }
 
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// dB of one bin from its complex value.  float path: 10*log10(|X|^2) through MUFU.LG2, clamped in
+// the dB domain (so the floor is exactly multiplier*log10(amin)).  double path: |X|^2 in double,
+// log2 split into exponent + mantissa so the only fp32 error is lg2.approx on [1, 2) (2^-22
+// absolute), recombined and clamped in double.
+template <typename R>
+struct DbOut;
+template <>
+struct DbOut<float> {
+    using type = float;
+    static __device__ __forceinline__ float eval(float re, float im, const StftParams& p) {
+        const float pw = fmaf(re, re, im * im);
+        return fmaxf(p.log_scale * lg2_approx(pw), p.floor_db);
+    }
+};
+template <>
+struct DbOut<double> {
+    using type = double;
+    static __device__ __forceinline__ double eval(double re, double im, const StftParams& p) {
+        const float pw = (float)(re * re + im * im);
+        const int bits = __float_as_int(pw);
+        const int e = (bits >> 23) - 127;
+        const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+        double db = p.log_scale_d * ((double)e + (double)lg2_approx(m));
+        db = (pw >= 1.17549435e-38f) ? db : -INFINITY;
+        return fmax(db, p.floor_db_d);
+    }
+};
+
+template <typename R> __device__ __forceinline__ R shfl_xor_r(R v, int m);
+template <> __device__ __forceinline__ float shfl_xor_r<float>(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <> __device__ __forceinline__ double shfl_xor_r<double>(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+
 template <typename R, typename OUT, bool kStats>
 __global__ void __launch_bounds__(kThreads, sizeof(R) == 4 ? 2 : 1)
 stft_db_kernel(const StftParams p) {
@@ -227,15 +282,35 @@ stft_db_kernel(const StftParams p) {
         for (int i = tid; i < kKp * kRow; i += kThreads) s_tw[i] = tw[i];
     }
 
+    // Per-lane constants of the cross-lane 32-point DFT that turns Y_b[32] into bins 32 + 64 q:
+    // pre-twiddle W_64^lane and the decimation-in-frequency twiddles of the distance-16/8/4 stages
+    // (1 for the lower lane of a pair).
+    R nq_pre_r, nq_pre_i, nq_wr[3], nq_wi[3];
+    {
+        double sn, cs;
+        sincospi(-(double)lane / 32.0, &sn, &cs);
+        nq_pre_r = (R)cs; nq_pre_i = (R)sn;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int dist = 16 >> i;
+            const bool upper = (lane & dist) != 0;
+            sincospi(upper ? -(double)((lane & (dist - 1)) * (16 / dist)) / 16.0 : 0.0, &sn, &cs);
+            nq_wr[i] = (R)cs; nq_wi[i] = (R)sn;
+        }
+    }
+    const int nq_bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);     // lane r ends up holding q = bitrev5(r)
+
     const int hop = p.hop;
     const long long T = p.T;
     const int elem_bytes = p.audio_dtype == DAM_I16 ? 2 : (p.audio_dtype == DAM_F32 ? 4 : 8);
+    const unsigned tiles_per_row = (unsigned)p.tiles_per_row, n_tiles = (unsigned)p.n_tiles;
     float st_sum = 0.f, st_sq = 0.f;
     double st_sum_d = 0.0, st_sq_d = 0.0, st_cnt = 0.0;
 
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const long long row = tile / p.tiles_per_row;
-        const long long t0 = (tile - row * p.tiles_per_row) * kFT;
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned urow = tile / tiles_per_row;
+        const long long row = urow;
+        const long long t0 = (long long)(tile - urow * tiles_per_row) * kFT;
         const int nf = (int)((T - t0) < kFT ? (T - t0) : kFT);
 
         __syncthreads();     // previous tile's stage 2 has finished reading s_xch (and tables are loaded)
@@ -252,10 +327,10 @@ stft_db_kernel(const StftParams p) {
 
         // pull the next tile's samples towards L2 while this one is transformed
         {
-            const long long nt = tile + gridDim.x;
-            if (nt < p.n_tiles) {
-                const long long nrow = nt / p.tiles_per_row;
-                const long long nt0 = (nt - nrow * p.tiles_per_row) * kFT;
+            const unsigned nt = tile + gridDim.x;
+            if (nt < n_tiles) {
+                const unsigned nrow = nt / tiles_per_row;
+                const long long nt0 = (long long)(nt - nrow * tiles_per_row) * kFT;
                 const int nnf = (int)((T - nt0) < kFT ? (T - nt0) : kFT);
                 prefetch_tile(p, nrow, nt0 * hop - kNfft / 2, (nnf - 1) * hop + kNfft, elem_bytes, tid);
             }
@@ -276,81 +351,90 @@ stft_db_kernel(const StftParams p) {
                 C* dst = s_xch + warp * kXch + lane;
                 {
                     C v; v.x = sr[0]; v.y = R(0);
-                    dst[0] = v;                        // row 0:  Y[0]  (real)
-                    v.x = si[0];
-                    dst[32 * kRow] = v;                // row 32: Y[32] (real)
+                    dst[0] = v;                        // row 0: Y[0] (real)
                 }
 #pragma unroll
                 for (int k = 1; k < 32; ++k) {
                     C v; v.x = sr[k]; v.y = si[k];
                     dst[k * kRow] = v;
                 }
+                // k' = 32: Y_b[32] = si[0] is real; bins 32 + 64 q = sum_b Y_b[32] W_64^b W_32^(bq) are a
+                // 32-point DFT ACROSS the lanes of this warp (radix-2 DIF over shuffles, output lane r
+                // holds q = bitrev5(r); q < 16 are the distinct bins).
+                R vr = si[0] * nq_pre_r, vi = si[0] * nq_pre_i;
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    const int dist = 16 >> i;
+                    const R pr = shfl_xor_r<R>(vr, dist), pi = shfl_xor_r<R>(vi, dist);
+                    const bool upper = (lane & dist) != 0;
+                    const R tr = upper ? pr - vr : vr + pr;
+                    const R ti = upper ? pi - vi : vi + pi;
+                    if (i < 3) {
+                        vr = tr * nq_wr[i] - ti * nq_wi[i];
+                        vi = tr * nq_wi[i] + ti * nq_wr[i];
+                    } else if (i == 3) {                 // W_4^j: j = 1 on the upper lane of odd pairs -> -i
+                        const bool rot = upper && (lane & 1);
+                        vr = rot ? ti : tr;
+                        vi = rot ? -tr : ti;
+                    } else {
+                        vr = tr; vi = ti;
+                    }
+                }
+                const typename DbOut<R>::type db = DbOut<R>::eval(vr, vi, p);
+                if ((lane & 1) == 0) {
+                    reinterpret_cast<OUT*>(p.out)[(row * kBins + nq_bin) * T + t0 + warp] = (OUT)db;
+                    if (kStats) { st_sum_d += (double)db; st_sq_d += (double)db * (double)db; st_cnt += 1.0; }
+                }
             }
         }
         __syncthreads();
 
-        // ---- stage 2: task = (k' = task / 8, frame = task % 8); tasks 256..263 (k' = 32) take a
-        //      second round on the first 8 threads
-        for (int task = tid; task < kKp * kFT; task += kThreads) {
-            const int kp = task >> 3, t = task & 7;
-            if (t >= nf) continue;
-            const C* src = s_xch + t * kXch + kp * kRow;
-            const C* tw = s_tw + kp * kRow;
-            if (sizeof(R) == 4) {
-                // two complex values per 128-bit load (rows are 16-byte aligned by construction)
-                const float4* s4 = reinterpret_cast<const float4*>(src);
-                const float4* w4 = reinterpret_cast<const float4*>(tw);
-#pragma unroll
-                for (int b2 = 0; b2 < 16; ++b2) {
-                    const float4 v = s4[b2];
-                    const float4 w = w4[b2];
-                    sr[2 * b2] = v.x * w.x - v.y * w.y;
-                    si[2 * b2] = v.x * w.y + v.y * w.x;
-                    sr[2 * b2 + 1] = v.z * w.z - v.w * w.w;
-                    si[2 * b2 + 1] = v.z * w.w + v.w * w.z;
-                }
-            } else {
-#pragma unroll
-                for (int b = 0; b < 32; ++b) {
-                    const C v = src[b];
-                    const C w = tw[b];
-                    sr[b] = v.x * w.x - v.y * w.y;
-                    si[b] = v.x * w.y + v.y * w.x;
-                }
-            }
-            dam_cfft32<R>(sr, si);
-
-            // bins k'+64q (q < 16) walk up from row k'; mirrors 2048-k'-64q (q >= 16) walk down from
-            // row 1024-k'.  k' = 0 and 32 own only 17 / 16 distinct bins.
-            const long long stride = 64 * T;
-            OUT* o_lo = reinterpret_cast<OUT*>(p.out) + (row * kBins + kp) * T + t0 + t;
-            OUT* o_hi = reinterpret_cast<OUT*>(p.out) + (row * kBins + (kNfft / 2 - kp)) * T + t0 + t;
-            const bool mirror_ok = (kp != 0) && (kp != 32);
-#pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                const bool valid = q < 16 ? true : (q == 16 ? (kp != 32) : mirror_ok);
-                OUT* o = q < 16 ? o_lo + q * stride : o_hi - (q - 16) * stride;
-                float db;
+        // ---- stage 2: thread = (k' = tid / 8 in 0..31, frame = tid % 8)
+        {
+            const int kp = tid >> 3, t = tid & 7;
+            if (t < nf) {
+                const C* src = s_xch + t * kXch + kp * kRow;
+                const C* tw = s_tw + kp * kRow;
                 if (sizeof(R) == 4) {
-                    const float pw = fmaf((float)sr[q], (float)sr[q], (float)si[q] * (float)si[q]);
-                    db = fmaxf(p.log_scale * __log2f(pw), p.floor_db);
-                    if (valid) *o = (OUT)db;
+                    // two complex values per 128-bit load (rows are 16-byte aligned by construction)
+                    const float4* s4 = reinterpret_cast<const float4*>(src);
+                    const float4* w4 = reinterpret_cast<const float4*>(tw);
+#pragma unroll
+                    for (int b2 = 0; b2 < 16; ++b2) {
+                        const float4 v = s4[b2];
+                        const float4 w = w4[b2];
+                        sr[2 * b2] = v.x * w.x - v.y * w.y;
+                        si[2 * b2] = v.x * w.y + v.y * w.x;
+                        sr[2 * b2 + 1] = v.z * w.z - v.w * w.w;
+                        si[2 * b2 + 1] = v.z * w.w + v.w * w.z;
+                    }
                 } else {
-                    // |X|^2 in double, log2 split into exponent + mantissa so the only fp32 error is
-                    // lg2.approx on [1, 2) (2^-22 absolute); recombined and clamped in double.
-                    const float pw = (float)(sr[q] * sr[q] + si[q] * si[q]);
-                    const int bits = __float_as_int(pw);
-                    const int e = (bits >> 23) - 127;
-                    const float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);
-                    double dbd = p.log_scale_d * ((double)e + (double)__log2f(m));
-                    dbd = (pw >= 1.17549435e-38f) ? dbd : -INFINITY;
-                    dbd = fmax(dbd, p.floor_db_d);
-                    db = (float)dbd;
-                    if (valid) *o = (OUT)dbd;
+#pragma unroll
+                    for (int b = 0; b < 32; ++b) {
+                        const C v = src[b];
+                        const C w = tw[b];
+                        sr[b] = v.x * w.x - v.y * w.y;
+                        si[b] = v.x * w.y + v.y * w.x;
+                    }
                 }
-                if (kStats && valid) { st_sum += db; st_sq = fmaf(db, db, st_sq); st_cnt += 1.0; }
+                dam_cfft32<R>(sr, si);
+
+                // bins k'+64q (q < 16) walk up from row k'; mirrors 2048-k'-64q (q >= 16) walk down
+                // from row 1024-k'.  k' = 0 owns only q <= 16 (bins 0, 64, ..., 1024).
+                const long long stride = 64 * T;
+                OUT* o_lo = reinterpret_cast<OUT*>(p.out) + (row * kBins + kp) * T + t0 + t;
+                OUT* o_hi = reinterpret_cast<OUT*>(p.out) + (row * kBins + (kNfft / 2 - kp)) * T + t0 + t;
+                const bool mirror_ok = kp != 0;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const bool valid = q <= 16 ? true : mirror_ok;
+                    OUT* o = q < 16 ? o_lo + q * stride : o_hi - (q - 16) * stride;
+                    const typename DbOut<R>::type db = DbOut<R>::eval(sr[q], si[q], p);
+                    if (valid) *o = (OUT)db;
+                    if (kStats && valid) { st_sum += (float)db; st_sq = fmaf((float)db, (float)db, st_sq); st_cnt += 1.0; }
+                }
+                if (kStats) { st_sum_d += st_sum; st_sq_d += st_sq; st_sum = 0.f; st_sq = 0.f; }
             }
-            if (kStats) { st_sum_d += st_sum; st_sq_d += st_sq; st_sum = 0.f; st_sq = 0.f; }
         }
     }
 
@@ -492,6 +576,8 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     p.hop = hop; p.T = 1 + n_samples / hop;
     p.tiles_per_row = (p.T + kFT - 1) / kFT;
     p.n_tiles = p.tiles_per_row * n_rows;
+    DAM_CHECK_ARG(p.n_tiles < 0x7fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
+                  (long long)p.n_tiles);
     p.log_scale_d = multiplier * 0.5 * 0.30102999566398119521373889472449302676819;
     p.log_scale = (float)p.log_scale_d;
     p.floor_db_d = amin > 0.0 ? multiplier * log10(amin) : -INFINITY;
