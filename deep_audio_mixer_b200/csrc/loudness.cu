@@ -1,0 +1,331 @@
+// K4: ITU-R BS.1770 K-weighting (two cascaded biquads, float64) and mean-square partial sums over
+// caller-defined sample segments, for many signals at once.
+//
+// Replaces the inside of pyloudnorm.Meter.integrated_loudness as the reference calls it
+// (data/dataset.py:118,126; evaluation.py:32,40,63; models/baselines/mean_loudness_model.py:7,14;
+// data/listening_test_data_preparation.py:16,23): scipy.signal.lfilter x2 per channel followed by a
+// Python loop over 400 ms blocks.  Gating and the final log are done by the caller on the tiny
+// per-segment array.
+//
+// The IIR recurrence is serial in time, so the signal is cut into chunks of kChunk samples:
+//   pass A  (parallel)  zero-state end state of every chunk = sum_i G[:, i] * x[i]  (a dot product
+//                       with the precomputed decaying response table G; no serial dependency)
+//   scan    (tiny)      true start state of every chunk: s_{c+1} = M^L s_c + z_c, two-level
+//   pass C  (parallel)  every chunk re-runs the exact DF2T recurrence from its true start state,
+//                       squares the output and adds it to the segment sums
+// This is the exact state hand-off (no warm-up approximation); all filter arithmetic is float64.
+#include "dam_common.cuh"
+
+#include <math.h>
+#include <mutex>
+#include <string.h>
+#include <vector>
+
+namespace {
+
+constexpr int kChunk = 256;        // samples per chunk (L)
+constexpr int kSuper = 256;        // chunks per super-chunk in the two-level scan
+constexpr int kBlock = 128;
+
+struct Coeffs { double b0[2], b1[2], b2[2], a1[2], a2[2]; };
+
+struct KwTables {                  // device-resident, per coefficient set
+    Coeffs c;
+    double* G = nullptr;           // [kChunk][4]
+    double ML[16];                 // M^L   (row-major 4x4)
+    double MS[16];                 // M^(L*kSuper)
+};
+
+__host__ __device__ inline void step(const Coeffs& c, double x, double s[4], double* y_out) {
+    const double y1 = fma(c.b0[0], x, s[0]);
+    s[0] = fma(-c.a1[0], y1, fma(c.b1[0], x, s[1]));
+    s[1] = fma(-c.a2[0], y1, c.b2[0] * x);
+    const double y2 = fma(c.b0[1], y1, s[2]);
+    s[2] = fma(-c.a1[1], y2, fma(c.b1[1], y1, s[3]));
+    s[3] = fma(-c.a2[1], y2, c.b2[1] * y1);
+    if (y_out) *y_out = y2;
+}
+
+void matmul4(const double* a, const double* b, double* out) {
+    double t[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double acc = 0;
+            for (int k = 0; k < 4; ++k) acc += a[i * 4 + k] * b[k * 4 + j];
+            t[i * 4 + j] = acc;
+        }
+    memcpy(out, t, sizeof(t));
+}
+
+int get_tables(const Coeffs& c, KwTables** out) {
+    static std::mutex mu;
+    static std::vector<KwTables*> cache[64];
+    int dev = 0;
+    DAM_CHECK_CUDA(cudaGetDevice(&dev));
+    DAM_CHECK_ARG(dev >= 0 && dev < 64, "device index out of range");
+    std::lock_guard<std::mutex> lock(mu);
+    for (KwTables* t : cache[dev])
+        if (memcmp(&t->c, &c, sizeof(Coeffs)) == 0) { *out = t; return DAM_OK; }
+    KwTables* t = new KwTables();
+    t->c = c;
+    // one-step zero-input matrix M (columns = images of unit states)
+    double M[16];
+    for (int j = 0; j < 4; ++j) {
+        double s[4] = {0, 0, 0, 0};
+        s[j] = 1.0;
+        step(c, 0.0, s, nullptr);
+        for (int i = 0; i < 4; ++i) M[i * 4 + j] = s[i];
+    }
+    // G[:, L-1-k] = M^k * B, B = state after a unit impulse from rest
+    std::vector<double> G(kChunk * 4);
+    {
+        double v[4] = {0, 0, 0, 0};
+        step(c, 1.0, v, nullptr);
+        for (int k = 0; k < kChunk; ++k) {
+            for (int i = 0; i < 4; ++i) G[(kChunk - 1 - k) * 4 + i] = v[i];
+            step(c, 0.0, v, nullptr);
+        }
+    }
+    // M^L by running L zero-input steps on unit states; M^(L*kSuper) by repeated squaring
+    for (int j = 0; j < 4; ++j) {
+        double s[4] = {0, 0, 0, 0};
+        s[j] = 1.0;
+        for (int k = 0; k < kChunk; ++k) step(c, 0.0, s, nullptr);
+        for (int i = 0; i < 4; ++i) t->ML[i * 4 + j] = s[i];
+    }
+    memcpy(t->MS, t->ML, sizeof(t->ML));
+    for (int sq = 1; sq < kSuper; sq <<= 1) matmul4(t->MS, t->MS, t->MS);
+    (void)M;
+    DAM_CHECK_CUDA(cudaMalloc(&t->G, G.size() * sizeof(double)));
+    DAM_CHECK_CUDA(cudaMemcpy(t->G, G.data(), G.size() * sizeof(double), cudaMemcpyHostToDevice));
+    cache[dev].push_back(t);
+    *out = t;
+    return DAM_OK;
+}
+
+struct KwParams {
+    const void* x;
+    long long n_rows, n, row_stride, samp_stride;
+    long long n_chunks;            // ceil(n / kChunk)
+    Coeffs c;
+    const double* G;
+    double ML[16], MS[16];
+    const long long* seg_bounds;   // [n_seg + 1]
+    long long n_seg;
+    double* seg_sumsq;             // [n_rows][n_seg]
+    double* states;                // workspace [n_rows][n_chunks][4]
+};
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, long long stride, double (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, long long stride, double (&v)[8]) {
+    if (stride == 1 && ((reinterpret_cast<unsigned long long>(p) & 15ull) == 0)) {
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        const float4 b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = p[j * stride];
+    }
+}
+template <>
+__device__ __forceinline__ void load8<double>(const double* p, long long stride, double (&v)[8]) {
+    if (stride == 1 && ((reinterpret_cast<unsigned long long>(p) & 15ull) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double2 a = *reinterpret_cast<const double2*>(p + 2 * j);
+            v[2 * j] = a.x; v[2 * j + 1] = a.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = p[j * stride];
+    }
+}
+
+// pass A: zero-state end state of each full chunk (the last chunk's end state is never needed)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) kw_chunk_state_kernel(const KwParams p) {
+    __shared__ double s_G[kChunk * 4];
+    for (int i = threadIdx.x; i < kChunk * 4; i += kBlock) s_G[i] = p.G[i];
+    __syncthreads();
+    const long long row = blockIdx.y;
+    const long long chunk = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (chunk >= p.n_chunks - 1) {
+        if (chunk == p.n_chunks - 1) {
+            double* st = p.states + (row * p.n_chunks + chunk) * 4;
+            st[0] = st[1] = st[2] = st[3] = 0.0;
+        }
+        return;
+    }
+    const T* x = reinterpret_cast<const T*>(p.x) + row * p.row_stride + chunk * kChunk * p.samp_stride;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int i = 0; i < kChunk; i += 8) {
+        double v[8];
+        load8<T>(x + (long long)i * p.samp_stride, p.samp_stride, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double* g = s_G + (i + j) * 4;
+            a0 = fma(g[0], v[j], a0); a1 = fma(g[1], v[j], a1);
+            a2 = fma(g[2], v[j], a2); a3 = fma(g[3], v[j], a3);
+        }
+    }
+    double* st = p.states + (row * p.n_chunks + chunk) * 4;
+    *reinterpret_cast<double2*>(st) = make_double2(a0, a1);
+    *reinterpret_cast<double2*>(st + 2) = make_double2(a2, a3);
+}
+
+__device__ __forceinline__ void matvec_add(const double* M, const double s[4], const double z[4], double out[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        out[i] = fma(M[i * 4 + 0], s[0], fma(M[i * 4 + 1], s[1], fma(M[i * 4 + 2], s[2], fma(M[i * 4 + 3], s[3], z[i]))));
+}
+
+// scan: turn zero-state end states into true start states, in place.  One CTA per row.
+__global__ void __launch_bounds__(1024) kw_scan_kernel(const KwParams p) {
+    __shared__ double s_end[1024][4];
+    __shared__ double s_carry[4];
+    const long long row = blockIdx.x;
+    double* st = p.states + row * p.n_chunks * 4;
+    const long long n_super = (p.n_chunks + kSuper - 1) / kSuper;
+    if (threadIdx.x == 0) s_carry[0] = s_carry[1] = s_carry[2] = s_carry[3] = 0.0;
+    for (long long base = 0; base < n_super; base += 1024) {
+        const long long u = base + threadIdx.x;
+        const long long c0 = u * kSuper;
+        const long long c1 = c0 + kSuper < p.n_chunks ? c0 + kSuper : p.n_chunks;
+        double s[4] = {0, 0, 0, 0};
+        if (u < n_super) {
+            for (long long c = c0; c < c1; ++c) {
+                double z[4] = {st[c * 4], st[c * 4 + 1], st[c * 4 + 2], st[c * 4 + 3]}, o[4];
+                matvec_add(p.ML, s, z, o);
+                s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+            }
+        }
+        s_end[threadIdx.x][0] = s[0]; s_end[threadIdx.x][1] = s[1];
+        s_end[threadIdx.x][2] = s[2]; s_end[threadIdx.x][3] = s[3];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // serial over the super-chunks of this round; s_end[i] becomes the START state of super-chunk i
+            double cur[4] = {s_carry[0], s_carry[1], s_carry[2], s_carry[3]};
+            const long long cnt = n_super - base < 1024 ? n_super - base : 1024;
+            for (long long i = 0; i < cnt; ++i) {
+                double e[4] = {s_end[i][0], s_end[i][1], s_end[i][2], s_end[i][3]}, o[4];
+                s_end[i][0] = cur[0]; s_end[i][1] = cur[1]; s_end[i][2] = cur[2]; s_end[i][3] = cur[3];
+                matvec_add(p.MS, cur, e, o);      // only exact for full super-chunks; a partial one is last
+                cur[0] = o[0]; cur[1] = o[1]; cur[2] = o[2]; cur[3] = o[3];
+            }
+            s_carry[0] = cur[0]; s_carry[1] = cur[1]; s_carry[2] = cur[2]; s_carry[3] = cur[3];
+        }
+        __syncthreads();
+        if (u < n_super) {
+            s[0] = s_end[threadIdx.x][0]; s[1] = s_end[threadIdx.x][1];
+            s[2] = s_end[threadIdx.x][2]; s[3] = s_end[threadIdx.x][3];
+            for (long long c = c0; c < c1; ++c) {
+                double z[4] = {st[c * 4], st[c * 4 + 1], st[c * 4 + 2], st[c * 4 + 3]}, o[4];
+                st[c * 4] = s[0]; st[c * 4 + 1] = s[1]; st[c * 4 + 2] = s[2]; st[c * 4 + 3] = s[3];
+                matvec_add(p.ML, s, z, o);
+                s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// pass C: exact recurrence per chunk from its true start state; squared output -> segment sums
+template <typename T>
+__global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
+    const long long row = blockIdx.y;
+    const long long chunk = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (chunk >= p.n_chunks) return;
+    const long long i0 = chunk * kChunk;
+    const long long len = p.n - i0 < kChunk ? p.n - i0 : kChunk;
+    const T* x = reinterpret_cast<const T*>(p.x) + row * p.row_stride + i0 * p.samp_stride;
+    const double* st = p.states + (row * p.n_chunks + chunk) * 4;
+    double s[4] = {st[0], st[1], st[2], st[3]};
+    const Coeffs c = p.c;
+
+    // segment containing sample i0: largest k with bounds[k] <= i0 (k = -1 before the first bound)
+    long long lo = 0, hi = p.n_seg + 1;              // search in bounds[0 .. n_seg]
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (p.seg_bounds[mid] <= i0) lo = mid + 1; else hi = mid;
+    }
+    long long seg = lo - 1;                           // -1: before first bound; n_seg: after last
+    long long next = seg + 1 <= p.n_seg ? p.seg_bounds[seg + 1] : (long long)0x7fffffffffffffffLL;
+    double* out = p.seg_sumsq + row * p.n_seg;
+    double acc = 0.0;
+
+    for (long long i = 0; i < len; i += 8) {
+        double v[8];
+        if (i + 8 <= len) {
+            load8<T>(x + i * p.samp_stride, p.samp_stride, v);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = i + j < len ? (double)x[(i + j) * p.samp_stride] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (i + j < len) {
+                const long long gi = i0 + i + j;
+                while (gi >= next) {                  // crossed a segment boundary: flush
+                    if (seg >= 0 && seg < p.n_seg && acc != 0.0) atomicAdd(out + seg, acc);
+                    acc = 0.0;
+                    ++seg;
+                    next = seg + 1 <= p.n_seg ? p.seg_bounds[seg + 1] : (long long)0x7fffffffffffffffLL;
+                }
+                double y;
+                step(c, v[j], s, &y);
+                acc = fma(y, y, acc);
+            }
+        }
+    }
+    if (seg >= 0 && seg < p.n_seg && acc != 0.0) atomicAdd(out + seg, acc);
+}
+
+}  // namespace
+
+extern "C" size_t dam_kweight_workspace_bytes(int64_t n_rows, int64_t n_samples) {
+    if (n_rows <= 0 || n_samples <= 0) return 0;
+    const int64_t n_chunks = (n_samples + kChunk - 1) / kChunk;
+    return (size_t)n_rows * (size_t)n_chunks * 4 * sizeof(double);
+}
+
+extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, int64_t n_samples,
+                                    int64_t row_stride, int64_t samp_stride,
+                                    const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,
+                                    double* seg_sumsq, void* workspace, size_t workspace_bytes, void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(x && coeffs_host && seg_bounds && seg_sumsq && workspace, "null pointer argument");
+    DAM_CHECK_ARG(dtype == DAM_F32 || dtype == DAM_F64, "dtype must be F32 or F64");
+    DAM_CHECK_ARG(n_rows >= 1 && n_rows <= 65535 && n_samples >= 1 && n_seg >= 1, "bad sizes");
+    DAM_CHECK_ARG(workspace_bytes >= dam_kweight_workspace_bytes(n_rows, n_samples),
+                  "workspace too small: need %zu bytes", dam_kweight_workspace_bytes(n_rows, n_samples));
+    DAM_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
+    Coeffs c;
+    for (int s = 0; s < 2; ++s) {
+        c.b0[s] = coeffs_host[s * 5 + 0]; c.b1[s] = coeffs_host[s * 5 + 1]; c.b2[s] = coeffs_host[s * 5 + 2];
+        c.a1[s] = coeffs_host[s * 5 + 3]; c.a2[s] = coeffs_host[s * 5 + 4];
+    }
+    KwTables* t = nullptr;
+    int rc = get_tables(c, &t);
+    if (rc != DAM_OK) return rc;
+    KwParams p;
+    p.x = x; p.n_rows = n_rows; p.n = n_samples; p.row_stride = row_stride; p.samp_stride = samp_stride;
+    p.n_chunks = (n_samples + kChunk - 1) / kChunk;
+    p.c = c; p.G = t->G;
+    memcpy(p.ML, t->ML, sizeof(p.ML));
+    memcpy(p.MS, t->MS, sizeof(p.MS));
+    p.seg_bounds = reinterpret_cast<const long long*>(seg_bounds); p.n_seg = n_seg;
+    p.seg_sumsq = seg_sumsq; p.states = reinterpret_cast<double*>(workspace);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    dim3 grid((unsigned)((p.n_chunks + kBlock - 1) / kBlock), (unsigned)n_rows);
+    if (dtype == DAM_F32) kw_chunk_state_kernel<float><<<grid, kBlock, 0, st>>>(p);
+    else kw_chunk_state_kernel<double><<<grid, kBlock, 0, st>>>(p);
+    DAM_CHECK_CUDA(cudaGetLastError());
+    kw_scan_kernel<<<(unsigned)n_rows, 1024, 0, st>>>(p);
+    DAM_CHECK_CUDA(cudaGetLastError());
+    if (dtype == DAM_F32) kw_apply_kernel<float><<<grid, kBlock, 0, st>>>(p);
+    else kw_apply_kernel<double><<<grid, kBlock, 0, st>>>(p);
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}

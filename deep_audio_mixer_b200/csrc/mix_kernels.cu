@@ -1,0 +1,545 @@
+// K2 / K3 / K5 / K6 / N2: the bandwidth-bound elementwise and reduction kernels of the mix path.
+// All of them stream their operands once with 128-bit accesses; grids are sized in multiples of
+// the SM count and grid-stride over the data.
+#include "dam_common.cuh"
+
+#include <math.h>
+
+namespace {
+
+constexpr int kBlock = 256;
+
+inline int grid_for(long long work_items, int per_sm = 8) {
+    long long blocks = (work_items + kBlock - 1) / kBlock;
+    long long cap = (long long)dam_sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* s_buf) {
+    v = dam_warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_buf[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < (blockDim.x >> 5) ? s_buf[lane] : T(0);
+        v = dam_warp_sum(v);
+    }
+    __syncthreads();
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T block_max(T v, T* s_buf) {
+    v = dam_warp_max(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_buf[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < (blockDim.x >> 5) ? s_buf[lane] : T(0);
+        v = dam_warp_max(v);
+    }
+    __syncthreads();
+    return v;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+    // valid for non-negative doubles: their bit patterns order like signed integers
+    atomicMax(reinterpret_cast<long long*>(addr), __double_as_longlong(v));
+}
+
+template <typename T, int V> struct Vec { T v[V]; };
+template <typename T, int V>
+__device__ __forceinline__ Vec<T, V> load_vec(const T* p) {
+    Vec<T, V> r;
+    if (V == 1) { r.v[0] = __ldg(p); return r; }
+    constexpr int kBytes = V * (int)sizeof(T);
+    if (kBytes == 16) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+        r = *reinterpret_cast<const Vec<T, V>*>(&raw);
+    } else {      // 32 bytes
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+        reinterpret_cast<uint4*>(&r)[0] = a;
+        reinterpret_cast<uint4*>(&r)[1] = b;
+    }
+    return r;
+}
+template <typename T, int V>
+__device__ __forceinline__ void store_vec(T* p, const Vec<T, V>& r) {
+    if (V == 1) { *p = r.v[0]; return; }
+    constexpr int kBytes = V * (int)sizeof(T);
+    if (kBytes == 16) {
+        *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&r);
+    } else {
+        reinterpret_cast<uint4*>(p)[0] = reinterpret_cast<const uint4*>(&r)[0];
+        reinterpret_cast<uint4*>(p)[1] = reinterpret_cast<const uint4*>(&r)[1];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 gain-mask apply + stem sum
+struct GainMixParams {
+    const void* stems;
+    long long n_stems, n_channels, n_samples, stem_stride, chan_stride;
+    const double* gains;
+    long long n_gains, interp_coef;
+    int zero_mask;                 // n_gains == 1 without hold_single: mask is all zeros
+    void* mix_out;
+    void* stems_out;
+    double* peak;
+    double* sumsq;
+};
+
+template <typename TS, typename TC, typename TO, int V>
+__global__ void __launch_bounds__(kBlock) gain_mix_kernel(const GainMixParams p) {
+    __shared__ double s_red[kBlock / 32];
+    const long long c = blockIdx.y;
+    const long long n = p.n_samples;
+    const long long nvec = (n + V - 1) / V;
+    const TS* base = reinterpret_cast<const TS*>(p.stems) + c * p.chan_stride;
+    TO* mix = p.mix_out ? reinterpret_cast<TO*>(p.mix_out) + c * n : nullptr;
+    double loc_peak = 0.0, loc_sq = 0.0;
+    const long long K = p.n_gains, coef = p.interp_coef;
+
+    for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
+        const long long i0 = v * V;
+        long long kidx[V];
+        {
+            long long k0 = coef > 0 ? i0 / coef : K - 1;
+            if (k0 > K - 1) k0 = K - 1;
+            const long long next = (k0 + 1) * coef;          // first sample of gain k0+1
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                long long k = k0;
+                if (k0 < K - 1 && i0 + j >= next) {
+                    k = (i0 + j) / coef;                      // coef < V is legal: recompute
+                    if (k > K - 1) k = K - 1;
+                }
+                kidx[j] = k;
+            }
+        }
+        TC acc[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = TC(0);
+        for (long long s = 0; s < p.n_stems; ++s) {
+            const Vec<TS, V> x = load_vec<TS, V>(base + s * p.stem_stride + i0);
+            Vec<TO, V> y;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const TC g = p.zero_mask ? TC(0) : (TC)__ldg(p.gains + s * K + kidx[j]);
+                const TC prod = (TC)x.v[j] * g;
+                acc[j] = s == 0 ? prod : acc[j] + prod;
+                y.v[j] = (TO)prod;
+            }
+            if (p.stems_out)
+                store_vec<TO, V>(reinterpret_cast<TO*>(p.stems_out) + (s * p.n_channels + c) * n + i0, y);
+        }
+        Vec<TO, V> o;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            o.v[j] = (TO)acc[j];
+            const double a = fabs((double)acc[j]);
+            loc_peak = fmax(loc_peak, a);
+            loc_sq += a * a;
+        }
+        if (mix) store_vec<TO, V>(mix + i0, o);
+    }
+    if (p.peak) {
+        const double m = block_max(loc_peak, s_red);
+        if (threadIdx.x == 0) atomic_max_nonneg(p.peak + c, m);
+    }
+    if (p.sumsq) {
+        const double m = block_sum(loc_sq, s_red);
+        if (threadIdx.x == 0) atomicAdd(p.sumsq + c, m);
+    }
+}
+
+template <typename TS, typename TC, typename TO>
+int launch_gain_mix(const GainMixParams& p, bool vec_ok, cudaStream_t st) {
+    constexpr int V = 4;
+    if (vec_ok) {
+        const long long nvec = (p.n_samples + V - 1) / V;
+        dim3 grid(grid_for(nvec, 8 / (int)(p.n_channels > 4 ? 4 : p.n_channels) + 1), (unsigned)p.n_channels);
+        gain_mix_kernel<TS, TC, TO, V><<<grid, kBlock, 0, st>>>(p);
+    } else {
+        dim3 grid(grid_for(p.n_samples, 8), (unsigned)p.n_channels);
+        gain_mix_kernel<TS, TC, TO, 1><<<grid, kBlock, 0, st>>>(p);
+    }
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// N2 bus sum
+struct BusParams {
+    const void* stems;
+    long long n_stems, n_elems, stem_stride;
+    int n_bus;
+    void* out;
+    int group[64];
+};
+
+template <typename T, int V>
+__global__ void __launch_bounds__(kBlock) bus_sum_kernel(const BusParams p) {
+    const long long nvec = (p.n_elems + V - 1) / V;
+    for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
+        const long long i0 = v * V;
+        for (int g = 0; g < p.n_bus; ++g) {
+            Vec<T, V> acc;
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc.v[j] = T(0);
+            for (long long s = 0; s < p.n_stems; ++s) {
+                if (p.group[s] != g) continue;
+                const Vec<T, V> x = load_vec<T, V>(reinterpret_cast<const T*>(p.stems) + s * p.stem_stride + i0);
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc.v[j] += x.v[j];
+            }
+            store_vec<T, V>(reinterpret_cast<T*>(p.out) + (long long)g * p.n_elems + i0, acc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 feature-domain gain-weighted sum and gradients (float32)
+constexpr int kMaxS = 8;
+
+template <int V>
+__global__ void __launch_bounds__(kBlock) feature_mix_fwd_kernel(const float* __restrict__ x, const float* __restrict__ m,
+                                                                 long long S, long long P, float* __restrict__ out) {
+    const long long b = blockIdx.y;
+    const float* xb = x + b * S * P;
+    float mb[kMaxS];
+#pragma unroll
+    for (int i = 0; i < kMaxS; ++i) mb[i] = i < S ? __ldg(m + b * S + i) : 0.f;
+    const long long nvec = (P + V - 1) / V;
+    for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
+        const long long i0 = v * V;
+        Vec<float, V> acc;
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc.v[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxS; ++i) {
+            if (i < S) {
+                const Vec<float, V> xv = load_vec<float, V>(xb + i * P + i0);
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc.v[j] = __fadd_rn(acc.v[j], __fmul_rn(mb[i], xv.v[j]));
+            }
+        }
+        store_vec<float, V>(out + b * P + i0, acc);
+    }
+}
+
+template <int V>
+__global__ void __launch_bounds__(kBlock) feature_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ m,
+                                                                 const float* __restrict__ go, long long S, long long P,
+                                                                 float* __restrict__ grad_m, float* __restrict__ grad_x) {
+    __shared__ double s_red[kBlock / 32];
+    const long long b = blockIdx.y;
+    const float* xb = x + b * S * P;
+    float mb[kMaxS];
+    float part[kMaxS];
+#pragma unroll
+    for (int i = 0; i < kMaxS; ++i) { mb[i] = i < S ? __ldg(m + b * S + i) : 0.f; part[i] = 0.f; }
+    double tot[kMaxS];
+#pragma unroll
+    for (int i = 0; i < kMaxS; ++i) tot[i] = 0.0;
+    const long long nvec = (P + V - 1) / V;
+    int since = 0;
+    for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
+        const long long i0 = v * V;
+        const Vec<float, V> g = load_vec<float, V>(go + b * P + i0);
+#pragma unroll
+        for (int i = 0; i < kMaxS; ++i) {
+            if (i < S) {
+                const Vec<float, V> xv = load_vec<float, V>(xb + i * P + i0);
+                if (grad_x) {
+                    Vec<float, V> gx;
+#pragma unroll
+                    for (int j = 0; j < V; ++j) gx.v[j] = mb[i] * g.v[j];
+                    store_vec<float, V>(grad_x + (b * S + i) * P + i0, gx);
+                }
+#pragma unroll
+                for (int j = 0; j < V; ++j) part[i] = fmaf(g.v[j], xv.v[j], part[i]);
+            }
+        }
+        if (++since == 16) {       // flush fp32 partials into fp64 before they lose bits
+#pragma unroll
+            for (int i = 0; i < kMaxS; ++i) { tot[i] += part[i]; part[i] = 0.f; }
+            since = 0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxS; ++i) {
+        if (i < S) {
+            const double t = block_sum(tot[i] + (double)part[i], s_red);
+            if (threadIdx.x == 0) atomicAdd(grad_m + b * S + i, (float)t);
+        }
+    }
+}
+
+// K6 DummyModel: 20*log10(sum_i 10^(0.5 x_i))
+template <int V>
+__global__ void __launch_bounds__(kBlock) db_sum_kernel(const float* __restrict__ x, long long S, long long P,
+                                                        float* __restrict__ out) {
+    const long long b = blockIdx.y;
+    const float* xb = x + b * S * P;
+    const long long nvec = (P + V - 1) / V;
+    for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
+        const long long i0 = v * V;
+        Vec<float, V> acc;
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc.v[j] = 0.f;
+        for (long long i = 0; i < S; ++i) {
+            const Vec<float, V> xv = load_vec<float, V>(xb + i * P + i0);
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc.v[j] = __fadd_rn(acc.v[j], powf(10.0f, __fmul_rn(0.5f, xv.v[j])));
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc.v[j] = __fmul_rn(20.0f, log10f(acc.v[j]));
+        store_vec<float, V>(out + b * P + i0, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5 row scale and row reductions
+template <typename TI, typename TO, int V>
+__global__ void __launch_bounds__(kBlock) scale_rows_kernel(const TI* __restrict__ x, long long n, long long row_stride,
+                                                            const double* __restrict__ factor, int divide,
+                                                            TO* __restrict__ out) {
+    const long long r = blockIdx.y;
+    const double f = __ldg(factor + r);
+    const TI* xr = x + r * row_stride;
+    TO* o = out + r * n;
+    const long long nvec = (n + V - 1) / V;
+    for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
+        const Vec<TI, V> xv = load_vec<TI, V>(xr + v * V);
+        Vec<TO, V> y;
+#pragma unroll
+        for (int j = 0; j < V; ++j) y.v[j] = (TO)(divide ? (double)xv.v[j] / f : (double)xv.v[j] * f);
+        store_vec<TO, V>(o + v * V, y);
+    }
+}
+
+template <typename TI, int V>
+__global__ void __launch_bounds__(kBlock) row_reduce_kernel(const TI* __restrict__ x, long long n, long long row_stride,
+                                                            double* absmax, double* sumsq) {
+    __shared__ double s_red[kBlock / 32];
+    const long long r = blockIdx.y;
+    const TI* xr = x + r * row_stride;
+    double mx = 0.0, sq = 0.0;
+    const long long nvec = n / V;
+    for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
+        const Vec<TI, V> xv = load_vec<TI, V>(xr + v * V);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const double a = fabs((double)xv.v[j]);
+            mx = fmax(mx, a);
+            sq += a * a;
+        }
+    }
+    for (long long i = nvec * V + (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+        const double a = fabs((double)__ldg(xr + i));
+        mx = fmax(mx, a);
+        sq += a * a;
+    }
+    if (absmax) {
+        const double m = block_max(mx, s_red);
+        if (threadIdx.x == 0) atomic_max_nonneg(absmax + r, m);
+    }
+    if (sumsq) {
+        const double s = block_sum(sq, s_red);
+        if (threadIdx.x == 0) atomicAdd(sumsq + r, s);
+    }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+// ==========================================================================================
+extern "C" int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_stems, int64_t n_channels,
+                            int64_t n_samples, int64_t stem_stride, int64_t chan_stride,
+                            const double* gains, int64_t n_gains, int64_t interp_coef, int hold_single,
+                            int compute_dtype, void* mix_out, void* stems_out, int out_dtype,
+                            double* peak, double* sumsq, void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(stems && gains, "null pointer argument");
+    DAM_CHECK_ARG(mix_out || stems_out || peak || sumsq, "no output requested");
+    DAM_CHECK_ARG(stems_dtype == DAM_F32 || stems_dtype == DAM_F64, "stems_dtype must be F32 or F64");
+    DAM_CHECK_ARG(compute_dtype == DAM_F32 || compute_dtype == DAM_F64, "compute_dtype must be F32 or F64");
+    DAM_CHECK_ARG(out_dtype == DAM_F32 || out_dtype == DAM_F64, "out_dtype must be F32 or F64");
+    DAM_CHECK_ARG(!(stems_dtype == DAM_F64 && compute_dtype == DAM_F32), "F64 stems need F64 compute");
+    DAM_CHECK_ARG(n_stems >= 1 && n_channels >= 1 && n_channels <= 65535 && n_samples >= 0, "bad sizes");
+    DAM_CHECK_ARG(n_gains >= 1, "need at least one gain per stem");
+    DAM_CHECK_ARG(n_gains <= n_samples || n_samples == 0, "Target mask should be longer than the initial one");
+    DAM_CHECK_ARG(interp_coef >= 0, "interp_coef must be non-negative");
+    if (n_samples == 0) return DAM_OK;
+    GainMixParams p;
+    p.stems = stems; p.n_stems = n_stems; p.n_channels = n_channels; p.n_samples = n_samples;
+    p.stem_stride = stem_stride; p.chan_stride = chan_stride;
+    p.gains = gains; p.n_gains = n_gains; p.interp_coef = interp_coef;
+    p.zero_mask = (n_gains == 1 && !hold_single) ? 1 : 0;
+    p.mix_out = mix_out; p.stems_out = stems_out; p.peak = peak; p.sumsq = sumsq;
+    const size_t es = stems_dtype == DAM_F32 ? 4 : 8;
+    bool vec_ok = (n_samples % 4 == 0) && (stem_stride % 4 == 0) && (chan_stride % 4 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(stems) % (4 * es)) == 0) &&
+                  (!mix_out || (reinterpret_cast<uintptr_t>(mix_out) % 32) == 0) &&
+                  (!stems_out || (reinterpret_cast<uintptr_t>(stems_out) % 32) == 0);
+    if (stems_dtype == DAM_F64) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(stems) % 32 == 0);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (stems_dtype == DAM_F32) {
+        if (compute_dtype == DAM_F64)
+            return out_dtype == DAM_F64 ? launch_gain_mix<float, double, double>(p, vec_ok, st)
+                                        : launch_gain_mix<float, double, float>(p, vec_ok, st);
+        return out_dtype == DAM_F64 ? launch_gain_mix<float, float, double>(p, vec_ok, st)
+                                    : launch_gain_mix<float, float, float>(p, vec_ok, st);
+    }
+    return out_dtype == DAM_F64 ? launch_gain_mix<double, double, double>(p, vec_ok, st)
+                                : launch_gain_mix<double, double, float>(p, vec_ok, st);
+}
+
+extern "C" int dam_bus_sum(const void* stems, int dtype, int64_t n_stems, int64_t n_elems, int64_t stem_stride,
+                           const int32_t* group_host, int n_bus, void* out, void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(stems && group_host && out, "null pointer argument");
+    DAM_CHECK_ARG(dtype == DAM_F32 || dtype == DAM_F64, "dtype must be F32 or F64");
+    DAM_CHECK_ARG(n_stems >= 1 && n_stems <= 64, "n_stems must be in [1, 64]");
+    DAM_CHECK_ARG(n_bus >= 1 && n_bus <= 64 && n_elems >= 0, "bad sizes");
+    if (n_elems == 0) return DAM_OK;
+    BusParams p;
+    p.stems = stems; p.n_stems = n_stems; p.n_elems = n_elems; p.stem_stride = stem_stride;
+    p.n_bus = n_bus; p.out = out;
+    for (int i = 0; i < 64; ++i) p.group[i] = -1;
+    for (int64_t s = 0; s < n_stems; ++s) {
+        DAM_CHECK_ARG(group_host[s] >= -1 && group_host[s] < n_bus, "group[%lld]=%d out of range", (long long)s, group_host[s]);
+        p.group[s] = group_host[s];
+    }
+    const size_t es = dtype == DAM_F32 ? 4 : 8;
+    const bool vec_ok = (n_elems % 4 == 0) && (stem_stride % 4 == 0) &&
+                        (reinterpret_cast<uintptr_t>(stems) % (4 * es) == 0) &&
+                        (reinterpret_cast<uintptr_t>(out) % (4 * es) == 0);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == DAM_F32) {
+        if (vec_ok) bus_sum_kernel<float, 4><<<grid_for((n_elems + 3) / 4), kBlock, 0, st>>>(p);
+        else bus_sum_kernel<float, 1><<<grid_for(n_elems), kBlock, 0, st>>>(p);
+    } else {
+        if (vec_ok) bus_sum_kernel<double, 4><<<grid_for((n_elems + 3) / 4), kBlock, 0, st>>>(p);
+        else bus_sum_kernel<double, 1><<<grid_for(n_elems), kBlock, 0, st>>>(p);
+    }
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
+
+static int check_bsp(int64_t B, int64_t S, int64_t P) {
+    DAM_CHECK_ARG(B >= 0 && B <= 65535 && P >= 0, "bad sizes");
+    DAM_CHECK_ARG(S >= 1 && S <= kMaxS, "S must be in [1, %d]", kMaxS);
+    return DAM_OK;
+}
+
+extern "C" int dam_feature_mix_fwd(const float* x, const float* m, int64_t B, int64_t S, int64_t P,
+                                   float* out, void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(x && m && out, "null pointer argument");
+    int rc = check_bsp(B, S, P);
+    if (rc != DAM_OK) return rc;
+    if (B == 0 || P == 0) return DAM_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool vec_ok = (P % 4 == 0) && aligned16(x) && aligned16(out);
+    if (vec_ok) {
+        dim3 grid(grid_for((P + 3) / 4, 2), (unsigned)B);
+        feature_mix_fwd_kernel<4><<<grid, kBlock, 0, st>>>(x, m, S, P, out);
+    } else {
+        dim3 grid(grid_for(P, 2), (unsigned)B);
+        feature_mix_fwd_kernel<1><<<grid, kBlock, 0, st>>>(x, m, S, P, out);
+    }
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
+
+extern "C" int dam_feature_mix_bwd(const float* x, const float* m, const float* grad_out,
+                                   int64_t B, int64_t S, int64_t P,
+                                   float* grad_m, float* grad_x, void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(x && m && grad_out && grad_m, "null pointer argument");
+    int rc = check_bsp(B, S, P);
+    if (rc != DAM_OK) return rc;
+    if (B == 0 || P == 0) return DAM_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool vec_ok = (P % 4 == 0) && aligned16(x) && aligned16(grad_out) && (!grad_x || aligned16(grad_x));
+    if (vec_ok) {
+        dim3 grid(grid_for((P + 3) / 4, 2) > 64 ? 64 : grid_for((P + 3) / 4, 2), (unsigned)B);
+        feature_mix_bwd_kernel<4><<<grid, kBlock, 0, st>>>(x, m, grad_out, S, P, grad_m, grad_x);
+    } else {
+        dim3 grid(grid_for(P, 2) > 64 ? 64 : grid_for(P, 2), (unsigned)B);
+        feature_mix_bwd_kernel<1><<<grid, kBlock, 0, st>>>(x, m, grad_out, S, P, grad_m, grad_x);
+    }
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
+
+extern "C" int dam_db_sum(const float* x, int64_t B, int64_t S, int64_t P, float* out, void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(x && out, "null pointer argument");
+    DAM_CHECK_ARG(B >= 0 && B <= 65535 && P >= 0 && S >= 1, "bad sizes");
+    if (B == 0 || P == 0) return DAM_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool vec_ok = (P % 4 == 0) && aligned16(x) && aligned16(out);
+    if (vec_ok) {
+        dim3 grid(grid_for((P + 3) / 4, 2), (unsigned)B);
+        db_sum_kernel<4><<<grid, kBlock, 0, st>>>(x, S, P, out);
+    } else {
+        dim3 grid(grid_for(P, 2), (unsigned)B);
+        db_sum_kernel<1><<<grid, kBlock, 0, st>>>(x, S, P, out);
+    }
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
+
+extern "C" int dam_scale_rows(const void* x, int dtype, int64_t n_rows, int64_t n, int64_t row_stride,
+                              const double* factor, int divide, void* out, int out_dtype, void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(x && factor && out, "null pointer argument");
+    DAM_CHECK_ARG((dtype == DAM_F32 || dtype == DAM_F64) && (out_dtype == DAM_F32 || out_dtype == DAM_F64),
+                  "dtypes must be F32 or F64");
+    DAM_CHECK_ARG(n_rows >= 0 && n_rows <= 65535 && n >= 0, "bad sizes");
+    if (n_rows == 0 || n == 0) return DAM_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool vec_ok = (n % 4 == 0) && (row_stride % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 32 == 0) &&
+                        (reinterpret_cast<uintptr_t>(out) % 32 == 0);
+    dim3 grid(grid_for(vec_ok ? (n + 3) / 4 : n, 4), (unsigned)n_rows);
+#define DAM_SCALE(TI, TO)                                                                                         \
+    do {                                                                                                          \
+        if (vec_ok) scale_rows_kernel<TI, TO, 4><<<grid, kBlock, 0, st>>>((const TI*)x, n, row_stride, factor, divide, (TO*)out); \
+        else scale_rows_kernel<TI, TO, 1><<<grid, kBlock, 0, st>>>((const TI*)x, n, row_stride, factor, divide, (TO*)out);        \
+    } while (0)
+    if (dtype == DAM_F32 && out_dtype == DAM_F32) DAM_SCALE(float, float);
+    else if (dtype == DAM_F32) DAM_SCALE(float, double);
+    else if (out_dtype == DAM_F32) DAM_SCALE(double, float);
+    else DAM_SCALE(double, double);
+#undef DAM_SCALE
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
+
+extern "C" int dam_row_reduce(const void* x, int dtype, int64_t n_rows, int64_t n, int64_t row_stride,
+                              double* absmax, double* sumsq, void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(x && (absmax || sumsq), "null pointer argument");
+    DAM_CHECK_ARG(dtype == DAM_F32 || dtype == DAM_F64, "dtype must be F32 or F64");
+    DAM_CHECK_ARG(n_rows >= 0 && n_rows <= 65535 && n >= 0, "bad sizes");
+    if (n_rows == 0 || n == 0) return DAM_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool vec_ok = (row_stride % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 32 == 0);
+    dim3 grid(grid_for(vec_ok ? (n + 3) / 4 : n, 4), (unsigned)n_rows);
+    if (dtype == DAM_F32) {
+        if (vec_ok) row_reduce_kernel<float, 4><<<grid, kBlock, 0, st>>>((const float*)x, n, row_stride, absmax, sumsq);
+        else row_reduce_kernel<float, 1><<<grid, kBlock, 0, st>>>((const float*)x, n, row_stride, absmax, sumsq);
+    } else {
+        if (vec_ok) row_reduce_kernel<double, 4><<<grid, kBlock, 0, st>>>((const double*)x, n, row_stride, absmax, sumsq);
+        else row_reduce_kernel<double, 1><<<grid, kBlock, 0, st>>>((const double*)x, n, row_stride, absmax, sumsq);
+    }
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}

@@ -54,6 +54,7 @@ struct StftParams {
     float floor_db;               // multiplier * log10(amin), the clamp applied in the dB domain
     double log_scale_d, floor_db_d;
     void* out;
+    long long out_row_stride;
     double* stats;
 };
 
@@ -382,7 +383,7 @@ stft_db_kernel(const StftParams p) {
                 }
                 const typename DbOut<R>::type db = DbOut<R>::eval(vr, vi, p);
                 if ((lane & 1) == 0) {
-                    reinterpret_cast<OUT*>(p.out)[(row * kBins + nq_bin) * T + t0 + warp] = (OUT)db;
+                    reinterpret_cast<OUT*>(p.out)[row * p.out_row_stride + nq_bin * T + t0 + warp] = (OUT)db;
                     if (kStats) { st_sum_d += (double)db; st_sq_d += (double)db * (double)db; st_cnt += 1.0; }
                 }
             }
@@ -422,8 +423,8 @@ stft_db_kernel(const StftParams p) {
                 // bins k'+64q (q < 16) walk up from row k'; mirrors 2048-k'-64q (q >= 16) walk down
                 // from row 1024-k'.  k' = 0 owns only q <= 16 (bins 0, 64, ..., 1024).
                 const long long stride = 64 * T;
-                OUT* o_lo = reinterpret_cast<OUT*>(p.out) + (row * kBins + kp) * T + t0 + t;
-                OUT* o_hi = reinterpret_cast<OUT*>(p.out) + (row * kBins + (kNfft / 2 - kp)) * T + t0 + t;
+                OUT* o_lo = reinterpret_cast<OUT*>(p.out) + row * p.out_row_stride + kp * T + t0 + t;
+                OUT* o_hi = reinterpret_cast<OUT*>(p.out) + row * p.out_row_stride + (kNfft / 2 - kp) * T + t0 + t;
                 const bool mirror_ok = kp != 0;
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
@@ -543,7 +544,7 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
                            double input_scale, const double* row_gain,
                            const float* window, int n_fft, int hop,
                            double amin, double multiplier, int compute_dtype,
-                           void* out, int out_dtype, double* stats, void* stream) {
+                           void* out, int out_dtype, int64_t out_row_stride, double* stats, void* stream) {
     dam_clear_error();
     DAM_CHECK_ARG(audio != nullptr && window != nullptr && out != nullptr, "null pointer argument");
     DAM_CHECK_ARG(audio_dtype == DAM_I16 || audio_dtype == DAM_F32 || audio_dtype == DAM_F64,
@@ -560,6 +561,7 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     }
     DAM_CHECK_ARG(hop >= 1 && hop <= n_fft, "hop=%d must be in [1, n_fft]", hop);
     DAM_CHECK_ARG(amin >= 0.0, "amin must be non-negative");
+    DAM_CHECK_ARG(out_row_stride >= 0, "out_row_stride must be non-negative");
     if (n_rows == 0) return DAM_OK;
     DAM_CHECK_ARG(n_samples > n_fft / 2,
                   "reflect padding needs n_samples > n_fft/2 (got %lld)", (long long)n_samples);
@@ -583,6 +585,7 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     p.floor_db_d = amin > 0.0 ? multiplier * log10(amin) : -INFINITY;
     p.floor_db = (float)p.floor_db_d;
     p.out = out; p.stats = stats;
+    p.out_row_stride = out_row_stride > 0 ? out_row_stride : (long long)kBins * p.T;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const bool st = stats != nullptr;
     if (compute_dtype == DAM_F32) {

@@ -30,7 +30,8 @@ def stft_db(audio: torch.Tensor, n_fft: int = 2048, hop: int = 1024, window: tor
             channel_axis=None, amin: float = 1e-5, multiplier: float = 20.0,
             compute_dtype: torch.dtype = None, out_dtype: torch.dtype = None,
             input_scale: float = None, row_gain: torch.Tensor = None,
-            out: torch.Tensor = None, stats: torch.Tensor = None, stream=None) -> torch.Tensor:
+            out: torch.Tensor = None, out_row_stride: int = 0, stats: torch.Tensor = None,
+            stream=None) -> torch.Tensor:
     """20*log10(max(|STFT(audio)|, amin)) for every row of a CUDA tensor.
 
     audio        [..., n] (mono rows), or with ``channel_axis`` = -2 ([..., C, n], planar) or -1
@@ -38,6 +39,9 @@ def stft_db(audio: torch.Tensor, n_fft: int = 2048, hop: int = 1024, window: tor
                  dtype int16 / float32 / float64.
     compute_dtype  float32 or float64; default follows the input like the reference (float64 for
                  float64 input, float32 otherwise).  out_dtype defaults to compute_dtype.
+    out / out_row_stride  optional preallocated destination; plane r is written at
+                 out.data_ptr() + r*out_row_stride elements (0 = dense), which lets one call per stem
+                 fill a [chunks, S, F, T] model input in place.  Then ``out`` itself is returned.
     Returns      [..., n_fft/2+1, T] contiguous (T innermost), T = 1 + n // hop.
     """
     if not audio.is_cuda:
@@ -79,6 +83,9 @@ def stft_db(audio: torch.Tensor, n_fft: int = 2048, hop: int = 1024, window: tor
     F = n_fft // 2 + 1
     if out is None:
         out = torch.empty((rows, F, T), dtype=out_dtype, device=dev)
+    elif out_row_stride:
+        if out.dtype != out_dtype or not out.is_cuda or out_row_stride < F * T:
+            raise ValueError('strided out must be a CUDA %s tensor with out_row_stride >= F*T' % out_dtype)
     else:
         if out.dtype != out_dtype or not out.is_contiguous() or out.numel() != rows * F * T:
             raise ValueError('out must be a contiguous %s tensor of %d elements' % (out_dtype, rows * F * T))
@@ -93,9 +100,11 @@ def stft_db(audio: torch.Tensor, n_fft: int = 2048, hop: int = 1024, window: tor
             _lib.ptr(a), _lib.dtype_code(audio.dtype), C, rows, n,
             row_stride, chan_stride, samp_stride, float(input_scale), _lib.ptr(row_gain),
             _lib.ptr(window), n_fft, hop, float(amin), float(multiplier),
-            _lib.dtype_code(compute_dtype), _lib.ptr(out), _lib.dtype_code(out_dtype),
+            _lib.dtype_code(compute_dtype), _lib.ptr(out), _lib.dtype_code(out_dtype), int(out_row_stride),
             _lib.ptr(stats), _lib.stream_ptr(stream))
     _lib.check(rc, 'dam_stft_db')
+    if out_row_stride:
+        return out
     return out.reshape(tuple(lead) + (F, T))
 
 

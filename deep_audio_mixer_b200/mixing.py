@@ -1,0 +1,181 @@
+"""Time-domain mix kernels (K2, N2, K5) and feature-domain ops (K3, K6) behind the C ABI."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _check_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError('%s must be a CUDA tensor' % name)
+
+
+def gain_mix(stems: torch.Tensor, gains, interp_coef: int = None, hold_single: bool = False,
+             compute_dtype: torch.dtype = torch.float64, out_dtype: torch.dtype = None,
+             want_mix: bool = True, want_stems: bool = False, want_stats: bool = False, stream=None):
+    """Zero-order-hold gain masks x stems, summed over stems (kernel K2).
+
+    stems [S, C, N] CUDA float32/float64 (planar); gains [S, K] (array-like or tensor), amplitude
+    gains.  mask_s[i] = gains[s][min(i // interp_coef, K-1)], interp_coef = int(N / K) by default
+    (inference_utils.py:26); K == 1 gives an all-zero mask unless hold_single (the reference quirk).
+    Returns dict(mix=[C, N], stems=[S, C, N], peak=[C], sumsq=[C]) for the requested outputs.
+    """
+    _check_cuda(stems, 'stems')
+    if stems.dim() != 3:
+        raise ValueError('stems must be [S, C, N]')
+    if stems.stride(-1) != 1:
+        stems = stems.contiguous()
+    S, C, N = stems.shape
+    dev = stems.device
+    g = torch.as_tensor(np.asarray(gains, dtype=np.float64) if not isinstance(gains, torch.Tensor) else gains)
+    g = g.to(device=dev, dtype=torch.float64).reshape(S, -1).contiguous()
+    K = g.shape[1]
+    assert K <= N or N == 0, "Target mask should be longer than the initial one"
+    if interp_coef is None:
+        interp_coef = int(N / K)
+    if out_dtype is None:
+        out_dtype = compute_dtype
+    mix = torch.empty((C, N), dtype=out_dtype, device=dev) if want_mix else None
+    st_out = torch.empty((S, C, N), dtype=out_dtype, device=dev) if want_stems else None
+    peak = torch.zeros(C, dtype=torch.float64, device=dev) if want_stats else None
+    sumsq = torch.zeros(C, dtype=torch.float64, device=dev) if want_stats else None
+    with torch.cuda.device(dev):
+        rc = _lib.lib().dam_gain_mix(
+            _lib.ptr(stems), _lib.dtype_code(stems.dtype), S, C, N, stems.stride(0), stems.stride(1),
+            _lib.ptr(g), K, int(interp_coef), int(bool(hold_single)), _lib.dtype_code(compute_dtype),
+            _lib.ptr(mix), _lib.ptr(st_out), _lib.dtype_code(out_dtype),
+            _lib.ptr(peak), _lib.ptr(sumsq), _lib.stream_ptr(stream))
+    _lib.check(rc, 'dam_gain_mix')
+    return dict(mix=mix, stems=st_out, peak=peak, sumsq=sumsq)
+
+
+def stem_sum(stems: torch.Tensor, out_dtype=None) -> torch.Tensor:
+    """np.sum(np.array(list(d.values())), axis=0) (evaluation.py:59-60) for stems [S, C, N]."""
+    ones = torch.ones((stems.shape[0], 1), dtype=torch.float64, device=stems.device)
+    return gain_mix(stems, ones, hold_single=True, compute_dtype=stems.dtype,
+                    out_dtype=out_dtype or stems.dtype)['mix']
+
+
+def bus_sum(stems: torch.Tensor, group, n_bus: int = 4) -> torch.Tensor:
+    """S raw stems -> n_bus buses, summed in stem order in the audio dtype (kernel N2;
+    data/medleydb_data_surgery.ipynb:305-332).  stems [S, ...]; group[s] in [0, n_bus) or -1."""
+    _check_cuda(stems, 'stems')
+    S = stems.shape[0]
+    flat = stems.reshape(S, -1)
+    if flat.stride(1) != 1:
+        flat = flat.contiguous()
+    out = torch.empty((n_bus,) + tuple(stems.shape[1:]), dtype=stems.dtype, device=stems.device)
+    grp = (ctypes.c_int32 * S)(*[int(v) for v in group])
+    with torch.cuda.device(stems.device):
+        rc = _lib.lib().dam_bus_sum(_lib.ptr(flat), _lib.dtype_code(stems.dtype), S, flat.shape[1],
+                                    flat.stride(0), grp, n_bus, _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, 'dam_bus_sum')
+    return out
+
+
+def row_reduce(x: torch.Tensor, want_absmax=True, want_sumsq=True):
+    """Per-row max|x| and sum x^2 (float64) of a [R, n] CUDA tensor."""
+    _check_cuda(x, 'x')
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    R, n = x2.shape
+    absmax = torch.zeros(R, dtype=torch.float64, device=x.device) if want_absmax else None
+    sumsq = torch.zeros(R, dtype=torch.float64, device=x.device) if want_sumsq else None
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().dam_row_reduce(_lib.ptr(x2), _lib.dtype_code(x.dtype), R, n, x2.stride(0),
+                                       _lib.ptr(absmax), _lib.ptr(sumsq), _lib.stream_ptr())
+    _lib.check(rc, 'dam_row_reduce')
+    return absmax, sumsq
+
+
+def scale_rows(x: torch.Tensor, factor, divide: bool = False, out_dtype=None) -> torch.Tensor:
+    """x[r, :] * factor[r] (or / factor[r]) in float64, rounded to out_dtype (kernel K5)."""
+    _check_cuda(x, 'x')
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    R, n = x2.shape
+    f = torch.as_tensor(factor, dtype=torch.float64).reshape(-1).to(x.device)
+    if f.numel() == 1 and R > 1:
+        f = f.expand(R)
+    f = f.contiguous()
+    out_dtype = out_dtype or x.dtype
+    out = torch.empty((R, n), dtype=out_dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().dam_scale_rows(_lib.ptr(x2), _lib.dtype_code(x.dtype), R, n, x2.stride(0),
+                                       _lib.ptr(f), int(bool(divide)), _lib.ptr(out),
+                                       _lib.dtype_code(out_dtype), _lib.stream_ptr())
+    _lib.check(rc, 'dam_scale_rows')
+    return out.reshape(x.shape)
+
+
+def normalize_loudness(data: torch.Tensor, input_loudness: float, target_loudness: float,
+                       out_dtype=None) -> torch.Tensor:
+    """pyloudnorm.normalize.loudness: data * 10**((target - input)/20) (evaluation.py:64)."""
+    gain = float(np.power(10.0, (target_loudness - input_loudness) / 20.0))
+    flat = data.reshape(1, -1) if data.is_contiguous() else data.contiguous().reshape(1, -1)
+    return scale_rows(flat, [gain], out_dtype=out_dtype or data.dtype).reshape(data.shape)
+
+
+def peak_normalize(x: torch.Tensor) -> torch.Tensor:
+    """librosa.util.normalize(x, axis=1) for [R, n]: each row divided by its max |x|
+    (inference.ipynb:219); rows with a peak below the dtype's tiny are left unscaled."""
+    absmax, _ = row_reduce(x, True, False)
+    tiny = torch.finfo(x.dtype).tiny
+    absmax = torch.where(absmax < tiny, torch.ones_like(absmax), absmax)
+    return scale_rows(x, absmax, divide=True)
+
+
+class _FeatureMix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, m):
+        B, S = x.shape[0], x.shape[1]
+        P = x[0, 0].numel()
+        xc = x.contiguous()
+        mc = m.contiguous()
+        out = torch.empty((B,) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().dam_feature_mix_fwd(_lib.ptr(xc), _lib.ptr(mc), B, S, P, _lib.ptr(out),
+                                                _lib.stream_ptr())
+        _lib.check(rc, 'dam_feature_mix_fwd')
+        ctx.save_for_backward(xc, mc)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xc, mc = ctx.saved_tensors
+        B, S = xc.shape[0], xc.shape[1]
+        P = xc[0, 0].numel()
+        go = grad_out.contiguous()
+        grad_m = torch.zeros_like(mc)
+        grad_x = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(xc.device):
+            rc = _lib.lib().dam_feature_mix_bwd(_lib.ptr(xc), _lib.ptr(mc), _lib.ptr(go), B, S, P,
+                                                _lib.ptr(grad_m), _lib.ptr(grad_x), _lib.stream_ptr())
+        _lib.check(rc, 'dam_feature_mix_bwd')
+        return grad_x, grad_m
+
+
+def feature_mix(x: torch.Tensor, m: torch.Tensor) -> torch.Tensor:
+    """masked[b] = sum_i m[b, i] * x[b, i] with autograd (kernel K3; model_scalar_1s.py:260-275).
+    x [B, S, F, T] float32 CUDA, m [B, S] float32."""
+    _check_cuda(x, 'x')
+    if x.dtype != torch.float32 or m.dtype != torch.float32:
+        raise TypeError('feature_mix is float32 (the reference raises on float64 input too)')
+    return _FeatureMix.apply(x, m)
+
+
+def db_sum(x: torch.Tensor) -> torch.Tensor:
+    """DummyModel.forward: 20*log10(sum_i 10**(0.5*x_i)) (kernel K6; dummy_model.py:23-34)."""
+    _check_cuda(x, 'x')
+    xc = x.contiguous().float()
+    B, S = xc.shape[0], xc.shape[1]
+    P = xc[0, 0].numel()
+    out = torch.empty((B,) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().dam_db_sum(_lib.ptr(xc), B, S, P, _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, 'dam_db_sum')
+    return out

@@ -20,6 +20,7 @@
 #ifndef DAM_B200_H
 #define DAM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -67,8 +68,10 @@ const char* dam_last_error(void);
  *   amin, multiplier   dB = multiplier * log10(max(|X|, amin))   (1e-5 and 20 in the reference).
  *   compute_dtype  DAM_F32 or DAM_F64 arithmetic for the FFT (the reference's dtype follows its
  *                input: float32 on the inference path, float64 on the training path).
- *   out          [n_rows, n_fft/2+1, T] contiguous, T innermost, dtype out_dtype (F32 or F64;
- *                F64 output requires compute_dtype F64).
+ *   out          n_rows planes [n_fft/2+1, T], T innermost, dtype out_dtype (F32 or F64; F64
+ *                output requires compute_dtype F64); plane r starts at out + r*out_row_stride
+ *                elements (0 = densely packed, (n_fft/2+1)*T).  A stride of S*F*T lets one call
+ *                per stem fill a [chunks, S, F, T] model input in place.
  *   stats        optional device double[3]: sum, sum of squares and count of the dB values
  *                written are ATOMICALLY ADDED (caller zeroes it); NULL = skip.
  */
@@ -78,7 +81,107 @@ int dam_stft_db(const void* audio, int audio_dtype, int channels,
                 double input_scale, const double* row_gain,
                 const float* window, int n_fft, int hop,
                 double amin, double multiplier, int compute_dtype,
-                void* out, int out_dtype, double* stats, void* stream);
+                void* out, int out_dtype, int64_t out_row_stride, double* stats, void* stream);
+
+/*
+ * K2: zero-order-hold gain masks applied to stems + stem sum (time domain).
+ * Replaces  interpolate_mask                     inference_utils.py:12-41
+ *           mixed_tracks[t] = track * mask       inference_utils.py:143
+ *           np.sum(np.array(list(d.values())),0) evaluation.py:59-60,
+ *                                                data/listening_test_data_preparation.py:20-21
+ *           RandomModel.forward (scalar gains)   models/baselines/random_model.py:11
+ *
+ *   stems        [n_stems, n_channels, n_samples] planar, dtype stems_dtype (F32 or F64);
+ *                stem_stride / chan_stride in elements, samples contiguous.
+ *   gains        [n_stems, n_gains] float64 amplitude gains.
+ *   interp_coef  samples held per gain = int(n_samples / n_gains) as Python computes it.
+ *                mask_s[i] = gains[s][min(i / interp_coef, n_gains-1)]; with n_gains == 1 and
+ *                hold_single == 0 the mask is all zeros (the reference quirk);
+ *                hold_single != 0 treats a single gain as a constant gain (RandomModel).
+ *   compute_dtype  F64: product and sum in float64 (float64 mask path, outputs are float64 in
+ *                the reference); F32: gain cast to float32, product and sum in float32
+ *                (python-float x float32-array path of RandomModel).
+ *   mix_out      optional [n_channels, n_samples], dtype out_dtype: sum over stems in stem order.
+ *   stems_out    optional [n_stems, n_channels, n_samples] contiguous, dtype out_dtype.
+ *   peak, sumsq  optional device double[n_channels]: max |mix| (atomic max) and sum mix^2
+ *                (atomic add) per channel; caller zeroes them.
+ */
+int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_stems, int64_t n_channels,
+                 int64_t n_samples, int64_t stem_stride, int64_t chan_stride,
+                 const double* gains, int64_t n_gains, int64_t interp_coef, int hold_single,
+                 int compute_dtype, void* mix_out, void* stems_out, int out_dtype,
+                 double* peak, double* sumsq, void* stream);
+
+/*
+ * N2: S raw stems -> n_bus bus sums (summed_track += track in stem order, in the audio dtype).
+ * Replaces  sum_stems  data/medleydb_data_surgery.ipynb:305-332.
+ *   stems [n_stems, n_elems] (rows stem_stride apart), group[n_stems] (host pointer; bus index,
+ *   or -1 to drop a stem), out [n_bus, n_elems] contiguous, same dtype (F32 or F64).
+ */
+int dam_bus_sum(const void* stems, int dtype, int64_t n_stems, int64_t n_elems, int64_t stem_stride,
+                const int32_t* group_host, int n_bus, void* out, void* stream);
+
+/*
+ * K3: the models' tail  masked[b] = sum_i m[b,i] * x[b,i]  (dB maps times raw head outputs) and
+ * its gradients.  Replaces model_scalar_1s.py:260-275, model_scalar_2s.py:117-132,
+ * model_resnet.py:120-126 (8 elementwise launches in the reference).  float32; products are
+ * rounded before each add, in stem order, exactly like the reference's mul/add sequence.
+ *   x [B, S, P] (P = F*T contiguous), m [B, S], out [B, P].
+ * Backward: grad_m[b,i] = sum_p grad_out[b,p] * x[b,i,p] (ADDED atomically to grad_m; caller
+ * zeroes it); grad_x[b,i,p] = m[b,i] * grad_out[b,p] if grad_x != NULL.
+ */
+int dam_feature_mix_fwd(const float* x, const float* m, int64_t B, int64_t S, int64_t P,
+                        float* out, void* stream);
+int dam_feature_mix_bwd(const float* x, const float* m, const float* grad_out,
+                        int64_t B, int64_t S, int64_t P,
+                        float* grad_m, float* grad_x, void* stream);
+
+/*
+ * K6: DummyModel.forward  y = 20*log10(sum_i 10**(0.5*x_i))  (models/baselines/dummy_model.py:23-34)
+ *   x [B, S, P] float32 -> out [B, P] float32.
+ */
+int dam_db_sum(const float* x, int64_t B, int64_t S, int64_t P, float* out, void* stream);
+
+/*
+ * K5: per-row scalar scale.  Replaces pyln.normalize.loudness (x * 10**((target-L)/20),
+ * evaluation.py:64) and librosa.util.normalize (x / max|x|, inference.ipynb:219).
+ *   x [n_rows, n] (row_stride apart), factor[n_rows] device float64; divide != 0 divides instead
+ *   of multiplying.  Arithmetic in float64, rounded to out_dtype.
+ */
+int dam_scale_rows(const void* x, int dtype, int64_t n_rows, int64_t n, int64_t row_stride,
+                   const double* factor, int divide, void* out, int out_dtype, void* stream);
+
+/*
+ * Row reductions used by the normalisations: absmax[r] = max |x[r,:]| and sumsq[r] = sum x[r,:]^2
+ * in float64 (either pointer may be NULL).  Results are ACCUMULATED (atomic max / add); caller
+ * zeroes them.
+ */
+int dam_row_reduce(const void* x, int dtype, int64_t n_rows, int64_t n, int64_t row_stride,
+                   double* absmax, double* sumsq, void* stream);
+
+/*
+ * K4: BS.1770 K-weighting (two cascaded biquads, float64 state) + sums of squares of the
+ * weighted signal over caller-defined sample segments, for n_rows signals in one call.
+ * Replaces the body of pyloudnorm.Meter.integrated_loudness as the reference calls it
+ * (data/dataset.py:118,126; evaluation.py:32,40,63; models/baselines/mean_loudness_model.py:7,14;
+ * data/listening_test_data_preparation.py:16,23): scipy.signal.lfilter twice per channel and the
+ * Python loop over 400 ms gating blocks.  Gating / LUFS are computed by the caller from the
+ * small seg_sumsq array.
+ *
+ *   x            [n_rows] signals of n_samples; sample i of row r at x[r*row_stride + i*samp_stride].
+ *   coeffs_host  HOST double[10]: b0,b1,b2,a1,a2 of stage 1 (high shelf) then stage 2 (high pass),
+ *                already divided by a0 (what IIRfilter.generate_coefficients returns).
+ *   seg_bounds   DEVICE int64[n_seg+1], ascending sample indices in [0, n_samples]; segment k is
+ *                [seg_bounds[k], seg_bounds[k+1]).  A gating block is a run of segments.
+ *   seg_sumsq    DEVICE double[n_rows, n_seg]; sums are ADDED (caller zeroes).
+ *   workspace    DEVICE scratch of dam_kweight_workspace_bytes(n_rows, n_samples) bytes,
+ *                16-byte aligned.
+ */
+size_t dam_kweight_workspace_bytes(int64_t n_rows, int64_t n_samples);
+int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, int64_t n_samples,
+                         int64_t row_stride, int64_t samp_stride,
+                         const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,
+                         double* seg_sumsq, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Number of frames dam_stft_db produces for n_samples (1 + n_samples / hop). */
 int64_t dam_stft_num_frames(int64_t n_samples, int hop);

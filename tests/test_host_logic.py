@@ -1,0 +1,135 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every symbol the header
+declares, WAV I/O, sharding (incl. a world_size-2 gloo all-reduce), dataset indexing."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from deep_audio_mixer_b200 import _lib, build
+    build.build_library()
+    header = open(os.path.join(ROOT, 'include', 'dam_b200.h')).read()
+    declared = set(re.findall(r'\b(dam_[a-z0-9_]+)\s*\(', header))
+    declared -= {'dam_status', 'dam_dtype'}
+    assert len(declared) >= 12
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(handle, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.lib()
+    assert lib.dam_version().decode().count('.') == 2
+    assert lib.dam_stft_num_frames(88200, 1024) == 87
+    assert lib.dam_kweight_workspace_bytes(2, 1000) == 2 * 4 * 4 * 8
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'deep_audio_mixer_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), fn
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from deep_audio_mixer_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libdam_b200.so')
+    with pytest.raises(_lib.DamError):
+        _lib.lib()
+
+
+def test_cpu_tensor_is_rejected_not_computed_on_cpu():
+    from deep_audio_mixer_b200 import features, mixing
+    with pytest.raises(ValueError):
+        features.stft_db(torch.zeros(1, 4096))
+    with pytest.raises(ValueError):
+        mixing.gain_mix(torch.zeros(4, 2, 100), [[1.0]] * 4)
+
+
+def test_wavio_roundtrip(tmp_path):
+    from deep_audio_mixer_b200 import wavio
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-0.9, 0.9, size=(5000, 2))
+    p = str(tmp_path / 'a.wav')
+    wavio.write(p, x, 44100)
+    wi = wavio.info(p)
+    assert (wi.samplerate, wi.channels, wi.frames) == (44100, 2, 5000) and abs(wi.duration - 5000 / 44100) < 1e-12
+    y, sr = wavio.read(p)
+    assert y.dtype == np.float64 and y.shape == (5000, 2) and sr == 44100
+    assert np.max(np.abs(y - np.round(x * 32768) / 32768)) == 0
+    part, _ = wavio.read(p, start=100, stop=300)
+    assert np.array_equal(part, y[100:300])
+    raw, _ = wavio.read_raw(p)
+    assert raw.dtype == np.int16
+    wavio.write(str(tmp_path / 'f.wav'), x.astype(np.float32), 48000, subtype='FLOAT')
+    z, sr = wavio.read(str(tmp_path / 'f.wav'), dtype='float32')
+    assert sr == 48000 and np.array_equal(z, x.astype(np.float32))
+
+
+def test_lpt_and_ranges():
+    from deep_audio_mixer_b200 import sharding
+    costs = [600, 20, 240, 240, 240, 30, 500, 100, 90]
+    parts = sharding.assign_lpt(costs, 4)
+    assert sorted(i for p in parts for i in p) == list(range(len(costs)))
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert max(loads) <= 600 and max(loads) - min(loads) <= 240
+    assert [sharding.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    # 122 equal songs on 8 ranks: 16 vs 15
+    assert sorted(len(p) for p in sharding.assign_lpt([1] * 122, 8)) == [15] * 6 + [16] * 2
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from deep_audio_mixer_b200 import sharding
+    sums = np.array([1.0, 2.0, 3.0, 4.0, 5.0]) * (rank + 1)
+    counts = np.full(5, rank + 2.0)
+    s, c = sharding.allreduce_sum_count(sums, counts)
+    stats = torch.tensor([10.0 * (rank + 1), 1000.0 * (rank + 1), 5.0], dtype=torch.float64)
+    mean, std = sharding.feature_mean_std(stats)
+    q.put((rank, s.tolist(), c.tolist(), mean, std))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_statistics_allreduce():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, s, c, mean, std in res:
+        assert s == [3.0, 6.0, 9.0, 12.0, 15.0] and c == [5.0] * 5
+        assert abs(mean - 3.0) < 1e-12 and abs(std - np.sqrt(300.0 - 9.0)) < 1e-9
+
+
+def test_dataset_indexing_without_gpu(tmp_path):
+    from deep_audio_mixer_b200 import dataset as D, wavio
+    sr = 8000
+    for name, secs in (('A', 7.3), ('B', 4.0), ('C', 11.9)):
+        os.makedirs(str(tmp_path / name / (name + '_STEMS_JOINED')))
+        wavio.write(str(tmp_path / name / (name + '_MIX.wav')), np.zeros((int(secs * sr), 2)), sr)
+    ds = D.MultitrackAudioDataset(str(tmp_path), songlist=['A', 'B', 'C'], chunk_length=2, sr=sr, seed=7)
+    # reference semantics (data/dataset.py:56-113): durations trimmed to a multiple of the chunk length
+    durs = dict(zip(ds.songlist, ds.get_song_durations()))
+    assert durs == {'A': 6, 'B': 4, 'C': 10}
+    assert len(ds) == 3 + 2 + 5
+    seen = [ds._calculate_song_index(i) for i in range(len(ds))]
+    per_song = [int(d / 2) for d in ds.get_song_durations()]
+    expect = [(s, c) for s, n in enumerate(per_song) for c in range(n)]
+    assert seen == expect

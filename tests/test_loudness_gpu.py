@@ -1,0 +1,60 @@
+"""K4 (dam_kweight_segments + host gating) against the oracle's pyloudnorm restatement.  GPU only.
+Tolerance: 1e-8 LU on integrated loudness, 1e-9 relative on block energies (float64 filters with
+an exact chunked state hand-off; only the summation order differs from scipy.lfilter + np.sum)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import loudness as OL
+from deep_audio_mixer_b200 import synthetic
+from deep_audio_mixer_b200.loudness import Meter
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('kind,n,dtype', [('music', 44100 * 5, np.float32), ('white', 44100 * 3 + 17, np.float64),
+                                          ('tonal', 44100 * 7 + 255, np.float32), ('music', 17641, np.float32),
+                                          ('pink', 44100 * 30, np.float32)])
+def test_block_energies_and_loudness_match_oracle(cuda_device, kind, n, dtype):
+    x = synthetic.make_song(31, 1, n, kind=kind, dtype=dtype)[0]          # [2, n]
+    meter = Meter(44100)
+    z = meter.block_energies(torch.from_numpy(x).cuda())
+    z_ref = OL.block_energies(x.T, 44100)
+    assert z.shape == z_ref.shape
+    assert np.max(np.abs(z - z_ref) / (np.abs(z_ref) + 1e-300)) < 1e-9
+    L = meter.integrated_loudness(x.T)
+    assert abs(L - OL.integrated_loudness(x.T, 44100)) < 1e-8
+
+
+def test_mono_and_48k_and_interleaved_device_input(cuda_device):
+    sr = 48000
+    t = np.arange(sr * 5) / sr
+    x = np.sin(2 * np.pi * 997 * t)
+    meter = Meter(sr)
+    L = meter.integrated_loudness(x)
+    assert abs(L - OL.integrated_loudness(x, sr)) < 1e-8
+    assert abs(L - (-3.01)) < 0.06                                        # BS.1770 conformance tone
+    st = synthetic.make_song(32, 1, 44100 * 2, kind='music', dtype=np.float64)[0]
+    inter = torch.from_numpy(np.ascontiguousarray(st.T)).cuda()           # [N, 2] contiguous: strided rows
+    assert abs(Meter(44100).integrated_loudness(inter) - OL.integrated_loudness(st.T, 44100)) < 1e-8
+
+
+def test_loudness_linearity_pin(cuda_device):
+    """experiments.ipynb:649-678: x0.8 -> -1.938 LU, x1.4 -> +2.923 LU, x0.5 -> -6.021 LU."""
+    x = synthetic.make_song(9, 1, 44100 * 3, kind='music', dtype=np.float64)[0].T
+    meter = Meter(44100)
+    L = meter.integrated_loudness(x)
+    for gain, delta in ((0.8, -1.938), (1.4, 2.923), (0.5, -6.021)):
+        assert abs(meter.integrated_loudness(gain * x) - L - delta) < 1e-3
+
+
+def test_batch_of_stems_and_gating(cuda_device):
+    song = synthetic.make_song(33, 4, 44100 * 6, kind='music', dtype=np.float32)
+    song[2, :, 44100:3 * 44100] = 0.0                                      # a silent stretch: gating acts
+    meter = Meter(44100)
+    got = meter.integrated_loudness_batch(torch.from_numpy(song).cuda())
+    ref = [OL.integrated_loudness(song[i].T, 44100) for i in range(4)]
+    assert np.max(np.abs(np.array(got) - np.array(ref))) < 1e-8
+    with pytest.raises(ValueError):
+        meter.integrated_loudness(np.zeros((1000, 2)))
+    assert meter.integrated_loudness(np.zeros((44100, 2))) == -np.inf

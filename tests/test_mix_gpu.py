@@ -1,0 +1,137 @@
+"""K2 / N2 / K3 / K5 / K6 against the oracle and the reference goldens.  GPU only.
+Integer/index work and float64 mask arithmetic are checked bit-exactly."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import mix as OM
+from deep_audio_mixer_b200 import mixing, synthetic, inference_utils as IU
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize('S,C,N,K', [(4, 2, 10000, 14), (4, 2, 10001, 7), (3, 1, 999, 999), (2, 2, 4096, 1),
+                                     (8, 2, 12345, 29), (4, 2, 64, 63), (5, 3, 1000, 2), (32, 2, 20000, 9)])
+def test_gain_mix_float64_mask_path_bit_exact(cuda_device, S, C, N, K):
+    rng = np.random.default_rng(S * 1000 + K)
+    stems = rng.normal(size=(S, C, N)).astype(np.float32)
+    gains = rng.uniform(0.2, 1.8, size=(S, K))
+    ref_stems = OM.apply_gains(stems, gains)                      # float64, K == 1 -> zeros
+    ref_mix = OM.stem_sum(ref_stems)
+    res = mixing.gain_mix(cuda(stems), gains, want_mix=True, want_stems=True, want_stats=True)
+    assert res['stems'].dtype == torch.float64 and res['mix'].dtype == torch.float64
+    assert np.array_equal(res['stems'].cpu().numpy(), ref_stems)
+    assert np.array_equal(res['mix'].cpu().numpy(), ref_mix)
+    assert np.allclose(res['peak'].cpu().numpy(), np.abs(ref_mix).max(axis=1), rtol=0, atol=0)
+    assert np.allclose(res['sumsq'].cpu().numpy(), (ref_mix ** 2).sum(axis=1), rtol=1e-12)
+
+
+def test_gain_mix_float64_stems_and_unaligned_views(cuda_device):
+    rng = np.random.default_rng(3)
+    stems = rng.normal(size=(4, 2, 5003))
+    gains = rng.uniform(0.5, 1.5, size=(4, 11))
+    t = cuda(stems)[:, :, 1:5002]                                 # odd offset: scalar path
+    ref = OM.apply_gains(stems[:, :, 1:5002], gains)
+    res = mixing.gain_mix(t, gains, want_stems=True)
+    assert np.array_equal(res['stems'].cpu().numpy(), ref)
+    assert np.array_equal(res['mix'].cpu().numpy(), OM.stem_sum(ref))
+
+
+def test_gain_mix_matches_reference_golden_mix(cuda_device):
+    g = golden('mix_smooth.npz')
+    N = int(g['N'])
+    song = synthetic.make_song(int(g['seed']), 4, N, sr=int(g['sr']), kind='music', dtype=np.float32)
+    assert hashlib.sha256(song.tobytes()).hexdigest() == str(g['input_sha'])
+    res = mixing.gain_mix(cuda(song), g['smooth'], want_stems=True)
+    st = res['stems'].cpu().numpy()
+    assert np.array_equal(st[:, :, ::13], g['mixed_dec'])
+    assert np.array_equal(np.abs(st).sum(axis=-1), g['mixed_abs_sum'])
+    assert np.array_equal(res['mix'].cpu().numpy()[:, ::13], g['mix_sum_dec'])
+
+
+def test_scalar_gain_float32_path_is_random_model(cuda_device):
+    """RandomModel: python float x float32 array -> float32; np.sum of the float32 stack."""
+    rng = np.random.default_rng(4)
+    stems = rng.normal(size=(4, 2, 30000)).astype(np.float32)
+    gains = [float(rng.uniform(0.5, 1.5)) for _ in range(4)]
+    ref = np.stack([g * stems[i] for i, g in enumerate(gains)])
+    assert ref.dtype == np.float32
+    res = mixing.gain_mix(cuda(stems), [[g] for g in gains], hold_single=True, compute_dtype=torch.float32,
+                          want_stems=True)
+    assert res['stems'].dtype == torch.float32
+    assert np.array_equal(res['stems'].cpu().numpy(), ref)
+    assert np.array_equal(res['mix'].cpu().numpy(), np.sum(ref, axis=0))
+    assert np.array_equal(mixing.stem_sum(cuda(stems)).cpu().numpy(), np.sum(stems, axis=0))
+
+
+def test_interpolate_mask_dropin_matches_reference(cuda_device):
+    g = golden('mask.npz')
+    for key in g.files:
+        if key.startswith('g_'):
+            _, K, L = key.split('_')
+            m = IU.interpolate_mask(g[key], int(L))
+            assert m.dtype == np.float64 and np.array_equal(m, g['m_%s_%s' % (K, L)])
+    with pytest.raises(AssertionError):
+        IU.interpolate_mask(np.ones(5), 4)
+
+
+def test_bus_sum(cuda_device):
+    rng = np.random.default_rng(5)
+    st = rng.normal(size=(8, 2, 10001)).astype(np.float32)
+    grp = [0, 1, 1, 2, 3, 3, 3, -1]
+    out = mixing.bus_sum(cuda(st), grp, 4)
+    assert np.array_equal(out.cpu().numpy(), OM.bus_sum(st, grp, 4))
+    st64 = rng.normal(size=(5, 2, 4096))
+    out = mixing.bus_sum(cuda(st64), [3, 3, 0, 0, 0], 4)
+    assert np.array_equal(out.cpu().numpy(), OM.bus_sum(st64, [3, 3, 0, 0, 0], 4))
+
+
+@pytest.mark.parametrize('shape', [(3, 4, 1025, 87), (2, 4, 1025, 173), (1, 4, 7, 5)])
+def test_feature_mix_forward_bit_exact_and_backward(cuda_device, shape):
+    rng = np.random.default_rng(6)
+    x = rng.uniform(-100, 40, size=shape).astype(np.float32)
+    m = rng.normal(size=shape[:2]).astype(np.float32)
+    xt, mt = cuda(x), cuda(m).requires_grad_(True)
+    y = mixing.feature_mix(xt, mt)
+    assert np.array_equal(y.detach().cpu().numpy(), OM.feature_mix(x, m))
+    go = rng.normal(size=y.shape).astype(np.float32)
+    y.backward(cuda(go))
+    gm, gx = OM.feature_mix_grad(x, m, go)
+    assert np.allclose(mt.grad.cpu().numpy(), gm, rtol=2e-5, atol=1e-3 * np.abs(gm).max() * 1e-2)
+    xt2 = cuda(x).requires_grad_(True)
+    mixing.feature_mix(xt2, cuda(m)).backward(cuda(go))
+    assert np.array_equal(xt2.grad.cpu().numpy(), gx.astype(np.float32))
+    # the reference formulation in torch ops gives the same forward bits
+    ref = torch.zeros_like(xt[:, 0])
+    for i in range(4):
+        ref += mt.detach()[:, i:i + 1].unsqueeze(2) * xt[:, i]
+    assert torch.equal(ref, y.detach())
+
+
+def test_db_sum_matches_dummy_model_golden(cuda_device):
+    g = golden('dummy.npz')
+    y = mixing.db_sum(cuda(g['x'])).cpu().numpy()
+    assert y.shape == g['y'].shape
+    assert np.max(np.abs(y - g['y'])) < 2e-5
+    assert np.max(np.abs(y - OM.db_sum(g['x']))) < 2e-5
+
+
+def test_scale_and_normalise(cuda_device):
+    rng = np.random.default_rng(7)
+    x = rng.normal(size=(2, 30001))
+    y = mixing.normalize_loudness(cuda(x), -23.5, -20.0).cpu().numpy()
+    assert np.array_equal(y, OM.normalize_loudness(x, -23.5, -20.0))
+    x32 = x.astype(np.float32)
+    p = mixing.peak_normalize(cuda(x32)).cpu().numpy()
+    ref = OM.peak_normalize(x32)
+    assert p.dtype == np.float32 and np.max(np.abs(p - ref)) <= 6e-8
+    am, sq = mixing.row_reduce(cuda(x32))
+    assert np.array_equal(am.cpu().numpy(), np.abs(x32).max(axis=1).astype(np.float64))
+    assert np.allclose(sq.cpu().numpy(), (x32.astype(np.float64) ** 2).sum(axis=1), rtol=1e-12)

@@ -1,0 +1,184 @@
+"""Drop-in surfaces end to end on the GPU: models, mix_song_smooth, dataset, evaluator."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle import features as OF
+from oracle import loudness as OL
+from oracle import mix as OM
+from deep_audio_mixer_b200 import dataset as D
+from deep_audio_mixer_b200 import evaluation as E
+from deep_audio_mixer_b200 import inference_utils as IU
+from deep_audio_mixer_b200 import models as M
+from deep_audio_mixer_b200 import synthetic, wavio
+
+pytestmark = pytest.mark.gpu
+W = golden('window.npz')['hann_2048']
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+class FakeGainModel(torch.nn.Module):                    # same as tools/gen_golden.py
+    def forward(self, x):
+        mu = x.double().mean(dim=(2, 3))
+        wob = 0.3 * torch.sin(mu[:, :1])
+        m = 0.02 * mu + 0.1 * torch.arange(4, dtype=torch.float64, device=x.device)[None, :] + wob
+        return None, tuple(m[:, i:i + 1] for i in range(4))
+
+
+@pytest.mark.parametrize('name,ctor,T', [('scalar1s', M.MixingModelScalar1s, 87),
+                                         ('scalar2s', M.MixingModelScalar2s, 173),
+                                         ('resnet18', M.ResNet18, 216)])
+def test_models_match_reference_architecture(cuda_device, name, ctor, T):
+    g = golden('models.npz')
+    torch.manual_seed(0)
+    net = ctor().eval()
+    assert sum(p.numel() for p in net.parameters() if p.requires_grad) == int(g['nparams_' + name])
+    assert sorted(net.state_dict().keys()) == list(g['keys_' + name])
+    gen = torch.Generator().manual_seed(11)
+    x = (torch.rand((1, 4, 1025, T), generator=gen) * 100.0 - 80.0)
+    net = net.cuda()
+    with torch.no_grad():
+        masked, ms = net(x.cuda())
+    m = np.array([float(v) for v in ms])
+    # same seed -> same initial weights as the reference; cuDNN vs CPU conv differ in the last bits
+    assert np.allclose(m, g['m_' + name], rtol=2e-3, atol=2e-4)
+    assert masked.shape == (1, 1025, T)
+    assert np.allclose(masked.cpu().numpy()[0, ::41, ::7], g['masked_dec_' + name], rtol=5e-3, atol=5e-2)
+    ref_tail = sum(ms[i].unsqueeze(2) * x.cuda()[:, i] for i in range(4))
+    assert torch.allclose(masked, ref_tail, rtol=0, atol=1e-4)
+    with pytest.raises(Exception):
+        net(x.cuda().double())                              # float64 input raises in the reference too
+
+
+def test_model_trains_through_fused_tail(cuda_device):
+    torch.manual_seed(1)
+    net = M.MixingModelScalar1s().cuda().train()
+    opt = torch.optim.Adam(net.parameters(), weight_decay=1e-5)
+    x = torch.rand(2, 4, 1025, 87, device='cuda') * 60 - 80
+    gt = torch.rand(2, 1025, 87, device='cuda') * 60 - 80
+    masked, _ = net(x)
+    loss = torch.nn.functional.mse_loss(masked, gt)
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    opt.step()
+
+
+def test_mix_song_smooth_matches_reference_golden(cuda_device):
+    g = golden('mix_smooth.npz')
+    sr, cl, N = int(g['sr']), int(g['chunk_length']), int(g['N'])
+    song = synthetic.make_song(int(g['seed']), 4, N, sr=sr, kind='music', dtype=np.float32)
+    assert hashlib.sha256(song.tobytes()).hexdigest() == str(g['input_sha'])
+    tracks = {k: song[i] for i, k in enumerate(OM.STEMS)}
+    mixed, raw, smooth, mix = IU.mix_song_smooth(D.Featuriser(), FakeGainModel(), tracks, chunk_length=cl, sr=sr,
+                                                 want_mix=True)
+    raw = np.array([raw[k] for k in OM.STEMS])
+    smooth = np.array([smooth[k] for k in OM.STEMS])
+    assert raw.shape == g['raw'].shape
+    assert np.max(np.abs(raw / g['raw'] - 1)) < 5e-5            # fp32 feature noise through the fake model
+    assert np.max(np.abs(smooth / g['smooth'] - 1)) < 5e-5
+    arr = np.stack([mixed[k] for k in OM.STEMS])
+    assert arr.dtype == np.float64 and isinstance(mixed['bass'], np.ndarray)
+    assert np.allclose(arr[:, :, ::13], g['mixed_dec'], rtol=5e-5, atol=1e-12)
+    assert np.allclose(mix[:, ::13], g['mix_sum_dec'], rtol=5e-5, atol=1e-6)
+    assert np.array_equal(mix, OM.stem_sum(arr))
+
+
+def test_config1_scalar1s_song_vs_oracle(cuda_device):
+    """BASELINE config 1: scalar-1s inference on one synthetic 4-stem 30 s 44.1 kHz song
+    (chunk_length 2, hop 1024 -> T = 87, 14 gains, savgol window 3, interp_coef 94 500)."""
+    sr, N = 44100, 44100 * 30
+    song = synthetic.make_song(synthetic.config_seed(1, 0), 4, N, kind='music', dtype=np.float32)
+    tracks = {k: song[i] for i, k in enumerate(OM.STEMS)}
+    torch.manual_seed(0)
+    net = M.MixingModelScalar1s().cuda().eval()
+
+    def model_fn(feat):                                      # the oracle's features through the same CNN
+        with torch.no_grad():
+            _, ms = net(torch.from_numpy(feat)[None].float().cuda())
+        return [float(m) for m in ms]
+
+    ref_mixed, ref_raw, ref_smooth = OM.mix_song_smooth(model_fn, tracks, chunk_length=2, sr=sr)
+    mixed, raw, smooth = IU.mix_song_smooth(D.Featuriser(), net, tracks, chunk_length=2, sr=sr)
+    assert len(raw['bass']) == 14
+    for k in OM.STEMS:
+        assert np.allclose(raw[k], ref_raw[k], rtol=1e-4)     # batch-14 vs batch-1 cuDNN + fp32 features
+        assert np.allclose(smooth[k], ref_smooth[k], rtol=1e-4)
+        assert mixed[k].dtype == np.float64 and mixed[k].shape == (2, N)
+        assert np.allclose(mixed[k], ref_mixed[k], rtol=1e-4, atol=1e-9)
+        # given identical gains the mix arithmetic is exact
+        assert np.array_equal(mixed[k], tracks[k] * OM.interpolate_mask(np.array(smooth[k]), N))
+
+
+def _write_dataset(root, n_songs=2, seconds=7, sr=44100):
+    names = []
+    for i in range(n_songs):
+        name = 'Song%d' % i
+        names.append(name)
+        song = synthetic.make_song(500 + i, 5, sr * seconds + 1234 * i, kind='music', dtype=np.float32) * 0.5
+        os.makedirs(os.path.join(root, name, name + '_STEMS_JOINED'))
+        for j, t in enumerate(['bass', 'drums', 'vocals', 'other']):
+            wavio.write(os.path.join(root, name, name + '_STEMS_JOINED', '%s_STEM_%s.wav' % (name, t.upper())),
+                        song[j].T, sr)
+        wavio.write(os.path.join(root, name, name + '_MIX.wav'), song[4].T, sr)
+    return names
+
+
+def test_dataset_dropin(cuda_device, tmp_path):
+    root = str(tmp_path)
+    names = _write_dataset(root)
+    ds = D.MultitrackAudioDataset(root, songlist=list(names), chunk_length=2, seed=3)
+    assert len(ds) == 3 + 3 and ds.get_num_songs() == 2 and ds.get_tracklist()[-1] == 'mix'
+    train, gt = ds[4]
+    assert train.shape == (4, 1025, 87) and gt.shape == (1025, 87)
+    assert train.dtype == torch.float64 and train.device.type == 'cpu'
+    song_i, chunk_i = ds._calculate_song_index(4)
+    audio = ds._read_chunk(song_i, chunk_i)                              # [5, n, 2] float64
+    ref_train, ref_gt = OF.process_chunk(list(audio[:4]), audio[4], channel_axis=1)
+    # the oracle is fed the torch window the product uses (1-ulp cos differences matter at -120 dB)
+    ref = np.stack([OF.compute_features(np.mean(a, axis=1), window=W) for a in audio])
+    assert np.max(np.abs(train.numpy() - ref[:4])) <= 1e-4 and np.max(np.abs(gt.numpy() - ref[4])) <= 1e-4
+    assert np.max(np.abs(ref_train - ref[:4])) < 1e-2
+    tb, gb = ds.get_batch([0, 4, 5])
+    assert tb.shape == (3, 4, 1025, 87) and gb.shape == (3, 1025, 87) and tb.is_cuda
+    assert torch.equal(tb[1].cpu(), train)
+    ml = ds.compute_mean_loudness()
+    name0 = ds.songlist[0]
+    tr, _ = wavio.read(ds._get_track_path(name0, 'bass'))
+    l0 = OL.integrated_loudness(tr, 44100)
+    tr1, _ = wavio.read(ds._get_track_path(ds.songlist[1], 'bass'))
+    assert abs(ml['bass'] - (l0 + OL.integrated_loudness(tr1, 44100)) / 2) < 1e-7
+
+
+def test_evaluator_and_baselines(cuda_device):
+    sr, N = 44100, 44100 * 17
+    ref_song = synthetic.make_song(700, 4, N, kind='music', dtype=np.float32)
+    test_song = synthetic.make_song(701, 4, N, kind='music', dtype=np.float32)
+    ref_tracks = {k: ref_song[i] for i, k in enumerate(OM.STEMS)}
+    test_tracks = {k: test_song[i] for i, k in enumerate(OM.STEMS)}
+    mean_loud = {'bass': -25.0, 'drums': -22.0, 'vocals': -21.0, 'other': -24.0}
+    ev = E.LoudnessEvaluator(D.Featuriser(), mean_loud, FakeGainModel(), sr=sr, seed=5)
+    rel = ev.evaluate_loudness(test_tracks)
+    assert np.allclose(rel, OL.evaluate_loudness(test_tracks, sr), atol=1e-8)
+    norm, loud = ev.sum_and_normalize(test_tracks)
+    s = OM.stem_sum(test_tracks)
+    assert abs(loud - OL.integrated_loudness(s.T, sr)) < 1e-6
+    assert abs(OL.integrated_loudness(norm.cpu().numpy().T.astype(np.float64), sr) - (-20.0)) < 1e-4
+    ln = M.MeanLoudnessModel(mean_loud, sr).forward(test_tracks)
+    for k in OM.STEMS:
+        assert abs(OL.integrated_loudness(ln[k].T, sr) - mean_loud[k]) < 1e-6
+    stats = ev.process_tracks(ref_tracks, test_tracks, n_random_samples=2)
+    assert set(stats) == {'song_name', 'sum_error', 'loudnorm_error', 'mix_error', 'random_error'}
+    ref_rel = OL.evaluate_loudness(ref_tracks, sr)
+    assert abs(stats['sum_error'] - OL.loudness_dict_diff(OL.evaluate_loudness(test_tracks, sr), ref_rel)) < 1e-7
+    mix = E.produce_mixture(test_tracks, sr=sr)
+    assert torch.equal(mix, norm)
