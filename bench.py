@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Headline benchmark: stem-audio-seconds per second through STFT -> dB -> gains -> mix (+loudness).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): model_scalar_2s inference batch of 64 synthetic 8-stem 10 s
+stereo 44.1 kHz segments per GPU: bus sum 8->4, dB-STFT features of every 2 s chunk (hop 512, T=173,
+the only shape model_scalar_2s accepts), per-chunk gains 10**(0.5 m), zero-order-hold masks + stem sum
+(float64, as in the reference), BS.1770 loudness of every mix and -20 LUFS normalisation.  One "step" =
+one pass of that hot path over one batch = 64 x 8 x 10 = 5120 stem-audio-seconds per GPU.  The CNN
+itself stays in PyTorch and is timed separately ("cnn" key), as BASELINE.md section 4 prescribes.
+
+Prints ONE JSON line (rank 0).  Launched by the driver as plain python (N=1) or torchrun (N>1).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 44100
+N_SEG, N_STEMS, N_CH, SECONDS = 64, 8, 2, 10
+CHUNK_SAMPLES, HOP = 2 * SR, 512
+GROUP = (0, 1, 1, 2, 2, 3, 3, 3)
+METRIC = 'stem-audio-sec/sec (STFT->dB->gains->mix)'
+UNIT = 'stem-audio-s/s'
+WORKLOAD = ('config2: model_scalar_2s inference batch of 64 synthetic 8-stem 10 s stereo 44.1 kHz segments; '
+            'bus-sum 8->4, 2 s chunks @ hop 512 (T=173), float64 mask/mix, BS.1770 loudness, -20 LUFS normalise')
+
+
+def synth_m(n_rows, seed=1234 + 2000):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return rng.uniform(-1.0, 0.5, size=(n_rows, 4)).astype(np.float32)
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_reference_throughput(n_seg_sample, steps, warmup):
+    """The oracle port (oracle/cpu_reference.py) on the host cores, on a bounded sample of the workload."""
+    import torch
+    from oracle import cpu_reference as CR
+    from deep_audio_mixer_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n = SECONDS * SR
+    raw = np.stack([synthetic.make_song(synthetic.config_seed(2, i), N_STEMS, n, kind='white', dtype=np.float32)
+                    for i in range(n_seg_sample)])
+    m = synth_m(n_seg_sample * (n // CHUNK_SAMPLES))
+    for _ in range(warmup):
+        CR.batch_step(raw[:1], GROUP, m, CHUNK_SAMPLES, HOP, SR)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        CR.batch_step(raw, GROUP, m, CHUNK_SAMPLES, HOP, SR)
+    dt = (time.perf_counter() - t0) / steps
+    stem_s = n_seg_sample * N_STEMS * SECONDS
+    return stem_s / dt, dt, cores, '%d of %d segments (%d stem-audio-s) per step, float32 features like the inference path' % (
+        n_seg_sample, N_SEG, stem_s)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    value, dt, cores, sample = cpu_reference_throughput(4, max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from deep_audio_mixer_b200 import pipeline as P
+    from deep_audio_mixer_b200 import synthetic, models, _lib
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: there is no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.lib()
+
+    n = SECONDS * SR
+    nc = n // CHUNK_SAMPLES
+    pipe = P.SegmentBatchPipeline(N_STEMS, GROUP, CHUNK_SAMPLES, HOP, device=dev)
+    raw = synthetic.make_batch_torch(synthetic.config_seed(2, rank), (N_SEG, N_STEMS, N_CH, n), dev)
+    m_host = torch.from_numpy(synth_m(N_SEG * nc)).pin_memory()
+    m = m_host.to(dev)
+    F, T = 1025, 1 + CHUNK_SAMPLES // HOP
+    feats_buf = torch.empty((N_SEG * nc, 4, F, T), dtype=torch.float32, device=dev)
+    stat = torch.zeros(2, dtype=torch.float64, device=dev)
+
+    def step():
+        res = pipe.run(raw, m, feats_out=feats_buf)
+        if world > 1:                      # the only collective of the path: a tiny statistics all-reduce
+            stat[0] = res['lufs'].sum()
+            stat[1] = float(N_SEG)
+            dist.all_reduce(stat)
+        return res
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: CUDA events on the launching stream, barrier + synchronize on both sides
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    pipe.timings = {}
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    tim = pipe.timings
+    pipe.timings = None
+    t_ms = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t_ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    def stage_ms(a, b):
+        return float(np.mean([x.elapsed_time(y) for x, y in zip(tim[a], tim[b])]))
+
+    stages = {'bus_sum': stage_ms('bus0', 'bus1'), 'stft_db': stage_ms('bus1', 'stft1'),
+              'gain_mix': stage_ms('gain0', 'mix1'), 'loudness': stage_ms('mix1', 'loud1'),
+              'scale': stage_ms('loud1', 'scale1')}
+    stem_s_per_step = N_SEG * N_STEMS * SECONDS
+    value = world * stem_s_per_step * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (K1, 4 launches per step), timed live above
+    ab = P.algorithmic_bytes(N_SEG, N_STEMS, N_CH, n, nc, CHUNK_SAMPLES, HOP)
+    peak, peak_src = peaks()
+    k1_ms_per_launch = stages['stft_db'] / 4.0
+    achieved = ab['stft_db'] / 4.0 / (k1_ms_per_launch * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'stft_db_kernel<float,float> (K1)', 'achieved': achieved, 'peak': peak,
+                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': ab['stft_db'] / 4.0, 'avg_launch_ms': k1_ms_per_launch,
+                'stage_ms': stages, 'stage_algorithmic_bytes': ab}
+    traffic_path = os.path.join(ROOT, 'profiles', 'k1_traffic.json')
+    if os.path.exists(traffic_path):
+        with open(traffic_path) as f:
+            roofline['traffic'] = json.load(f).get('dram_bytes_per_launch')
+
+    # ---- end to end through the public API with HOST buffers (uploads/downloads inside the timed region)
+    e2e = None
+    cnn = None
+    cpu_base = None
+    if rank == 0 or world > 1:
+        raw_host = torch.empty((N_SEG, N_STEMS, N_CH, n), dtype=torch.float32).pin_memory()
+        raw_host.copy_(raw)
+        out_host = torch.empty((N_SEG, N_CH, n), dtype=torch.float64).pin_memory()
+        lufs_host = torch.empty(N_SEG, dtype=torch.float64).pin_memory()
+        streams = [torch.cuda.Stream(dev) for _ in range(3)]
+        e2e_steps = max(2, min(args.steps, 5))
+        for _ in range(2):
+            pipe.run_host(raw_host, m_host, out_host, lufs_host, streams=streams)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(e2e_steps):
+            pipe.run_host(raw_host, m_host, out_host, lufs_host, streams=streams)
+        b.record()
+        torch.cuda.synchronize()
+        t2 = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_val = world * stem_s_per_step * e2e_steps / (float(t2.item()) * 1e-3)
+        e2e = {'value': e2e_val, 'unit': UNIT,
+               'h2d_bytes_per_step': int(raw_host.numel() * 4 + m_host.numel() * 4),
+               'd2h_bytes_per_step': int(out_host.numel() * 8 + lufs_host.numel() * 8),
+               'ms_per_step': float(t2.item()) / e2e_steps,
+               'check': float(lufs_host[0])}
+        del raw_host, out_host
+
+    if rank == 0:
+        # the CNN between the two halves: PyTorch/cuDNN, random-init scalar-2s, fp32 without TF32
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.manual_seed(0)
+        net = models.MixingModelScalar2s().to(dev).eval()
+        with torch.no_grad():
+            for _ in range(2):
+                for i in range(0, feats_buf.shape[0], 64):
+                    net(feats_buf[i:i + 64])
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(0, feats_buf.shape[0], 64):
+                net(feats_buf[i:i + 64])
+            b.record()
+            torch.cuda.synchronize()
+        cnn_ms = a.elapsed_time(b)
+        hot_ms = elapsed_ms / args.steps
+        cnn = {'model': 'MixingModelScalar2s (PyTorch/cuDNN fp32, TF32 off, random init)', 'ms_per_batch': cnn_ms,
+               'value_with_cnn': stem_s_per_step / ((hot_ms + cnn_ms) * 1e-3), 'unit': UNIT}
+        del net
+        # CPU baseline (the oracle port) on this box's host cores, bounded sample
+        v, dt, cores, sample = cpu_reference_throughput(4, 3, 1)
+        cpu_base = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
+                    'ms_per_step': dt * 1e3}
+
+    if rank == 0:
+        launches = sum(P.KERNEL_LAUNCHES_PER_BATCH.values()) * args.steps
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'segments_per_gpu': N_SEG, 'stems': N_STEMS, 'seconds': SECONDS,
+                       'hop': HOP, 'chunk_samples': CHUNK_SAMPLES,
+                       'l2': 'inputs (1.8 GB per step) are larger than the 126 MB L2; no explicit flush',
+                       'parallelism': 'segments sharded per GPU, no data-path collective'},
+            'roofline': roofline, 'cpu_baseline': cpu_base, 'e2e': e2e, 'gpu_launches': launches,
+            'clocks': clocks, 'cnn': cnn,
+            'check': {'lufs0': float(res['lufs'][0]), 'peak0': float(res['peak'][0, 0])},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -18,17 +18,18 @@ SIGNATURES = {
     'dam_version': (_c.c_char_p, []),
     'dam_last_error': (_c.c_char_p, []),
     'dam_stft_num_frames': (_i64, [_i64, _i]),
-    'dam_stft_db': (_i, [_vp, _i, _i, _i64, _i64, _i64, _i64, _i64, _d, _vp, _vp, _i, _i, _d, _d, _i,
+    'dam_stft_db': (_i, [_vp, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _d, _vp, _vp, _i, _i, _d, _d, _i,
                          _vp, _i, _i64, _vp, _vp]),
-    'dam_gain_mix': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _i,
+    'dam_gain_mix': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _i,
                           _vp, _vp, _vp]),
-    'dam_bus_sum': (_i, [_vp, _i, _i64, _i64, _i64, _c.POINTER(_c.c_int32), _i, _vp, _vp]),
+    'dam_bus_sum': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _c.POINTER(_c.c_int32), _i, _vp, _vp]),
     'dam_feature_mix_fwd': (_i, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     'dam_feature_mix_bwd': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     'dam_db_sum': (_i, [_vp, _i64, _i64, _i64, _vp, _vp]),
     'dam_scale_rows': (_i, [_vp, _i, _i64, _i64, _i64, _vp, _i, _vp, _i, _vp]),
     'dam_row_reduce': (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp, _vp]),
     'dam_kweight_workspace_bytes': (_c.c_size_t, [_i64, _i64]),
+    'dam_gated_loudness': (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i64, _d, _vp, _vp]),
     'dam_kweight_segments': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _c.POINTER(_d), _vp, _i64, _vp, _vp,
                                   _c.c_size_t, _vp]),
 }

@@ -282,6 +282,69 @@ __global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
     if (seg >= 0 && seg < p.n_seg && acc != 0.0) atomicAdd(out + seg, acc);
 }
 
+// Gating + LUFS on the device (one CTA per signal), so batch pipelines never synchronise with the host.
+constexpr int kGateBlock = 256;
+constexpr int kMaxCh = 5;
+
+struct GateParams {
+    const double* seg;             // [n_signals * C][n_seg]
+    long long n_seg, n_blocks;
+    int C;
+    const long long* first;        // [n_blocks] first segment of block j
+    const long long* last;         // [n_blocks] one past the last segment
+    double inv_len;                // 1 / (block_size * rate)
+    double* out;                   // [n_signals]
+};
+
+__device__ __forceinline__ double gate_block_sum(double v, double* s_buf) {
+    v = dam_warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_buf[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < kGateBlock / 32; ++i) t += s_buf[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(kGateBlock) gated_loudness_kernel(const GateParams p) {
+    __shared__ double s_buf[kGateBlock / 32];
+    const double G[kMaxCh] = {1.0, 1.0, 1.0, 1.41, 1.41};
+    const long long sig = blockIdx.x;
+    const double* seg = p.seg + sig * p.C * p.n_seg;
+    double gamma = -70.0;
+    double zavg[kMaxCh];
+    for (int pass = 0; pass < 2; ++pass) {
+        double acc[kMaxCh] = {0, 0, 0, 0, 0};
+        double cnt = 0.0;
+        for (long long j = threadIdx.x; j < p.n_blocks; j += kGateBlock) {
+            double z[kMaxCh];
+            double w = 0.0;
+            for (int c = 0; c < p.C; ++c) {
+                double a = 0.0;
+                for (long long k = p.first[j]; k < p.last[j]; ++k) a += seg[c * p.n_seg + k];
+                z[c] = a * p.inv_len;
+                w += G[c] * z[c];
+            }
+            const double l = -0.691 + 10.0 * log10(w);
+            const bool keep = pass == 0 ? (l >= -70.0) : (l > gamma && l > -70.0);
+            if (keep) {
+                for (int c = 0; c < p.C; ++c) acc[c] += z[c];
+                cnt += 1.0;
+            }
+        }
+        cnt = gate_block_sum(cnt, s_buf);
+        double w = 0.0;
+        for (int c = 0; c < p.C; ++c) {
+            const double t = gate_block_sum(acc[c], s_buf);
+            zavg[c] = cnt > 0.0 ? t / cnt : (pass == 0 ? NAN : 0.0);
+            w += G[c] * zavg[c];
+        }
+        if (pass == 0) gamma = -0.691 + 10.0 * log10(w) - 10.0;      // NaN if nothing passed: pass 2 keeps nothing
+        else if (threadIdx.x == 0) p.out[sig] = -0.691 + 10.0 * log10(w);
+    }
+}
+
 }  // namespace
 
 extern "C" size_t dam_kweight_workspace_bytes(int64_t n_rows, int64_t n_samples) {
@@ -326,6 +389,24 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
     DAM_CHECK_CUDA(cudaGetLastError());
     if (dtype == DAM_F32) kw_apply_kernel<float><<<grid, kBlock, 0, st>>>(p);
     else kw_apply_kernel<double><<<grid, kBlock, 0, st>>>(p);
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
+
+extern "C" int dam_gated_loudness(const double* seg_sumsq, int64_t n_signals, int n_channels, int64_t n_seg,
+                                  const int64_t* block_first, const int64_t* block_last, int64_t n_blocks,
+                                  double inv_block_len, double* lufs_out, void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(seg_sumsq && block_first && block_last && lufs_out, "null pointer argument");
+    DAM_CHECK_ARG(n_channels >= 1 && n_channels <= kMaxCh, "n_channels must be in [1, 5]");
+    DAM_CHECK_ARG(n_signals >= 0 && n_seg >= 1 && n_blocks >= 1, "bad sizes");
+    if (n_signals == 0) return DAM_OK;
+    GateParams p;
+    p.seg = seg_sumsq; p.n_seg = n_seg; p.n_blocks = n_blocks; p.C = n_channels;
+    p.first = reinterpret_cast<const long long*>(block_first);
+    p.last = reinterpret_cast<const long long*>(block_last);
+    p.inv_len = inv_block_len; p.out = lufs_out;
+    gated_loudness_kernel<<<(unsigned)n_signals, kGateBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }

@@ -82,6 +82,7 @@ __device__ __forceinline__ void store_vec(T* p, const Vec<T, V>& r) {
 // K2 gain-mask apply + stem sum
 struct GainMixParams {
     const void* stems;
+    long long n_batch, batch_stride;
     long long n_stems, n_channels, n_samples, stem_stride, chan_stride;
     const double* gains;
     long long n_gains, interp_coef;
@@ -96,12 +97,15 @@ template <typename TS, typename TC, typename TO, int V>
 __global__ void __launch_bounds__(kBlock) gain_mix_kernel(const GainMixParams p) {
     __shared__ double s_red[kBlock / 32];
     const long long c = blockIdx.y;
+    const long long bt = blockIdx.z;
     const long long n = p.n_samples;
     const long long nvec = (n + V - 1) / V;
-    const TS* base = reinterpret_cast<const TS*>(p.stems) + c * p.chan_stride;
-    TO* mix = p.mix_out ? reinterpret_cast<TO*>(p.mix_out) + c * n : nullptr;
+    const TS* base = reinterpret_cast<const TS*>(p.stems) + bt * p.batch_stride + c * p.chan_stride;
+    TO* mix = p.mix_out ? reinterpret_cast<TO*>(p.mix_out) + (bt * p.n_channels + c) * n : nullptr;
     double loc_peak = 0.0, loc_sq = 0.0;
     const long long K = p.n_gains, coef = p.interp_coef;
+    const double* gains = p.gains + bt * p.n_stems * K;
+    TO* stems_out = p.stems_out ? reinterpret_cast<TO*>(p.stems_out) + bt * p.n_stems * p.n_channels * n : nullptr;
 
     for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
         const long long i0 = v * V;
@@ -128,13 +132,12 @@ __global__ void __launch_bounds__(kBlock) gain_mix_kernel(const GainMixParams p)
             Vec<TO, V> y;
 #pragma unroll
             for (int j = 0; j < V; ++j) {
-                const TC g = p.zero_mask ? TC(0) : (TC)__ldg(p.gains + s * K + kidx[j]);
+                const TC g = p.zero_mask ? TC(0) : (TC)__ldg(gains + s * K + kidx[j]);
                 const TC prod = (TC)x.v[j] * g;
                 acc[j] = s == 0 ? prod : acc[j] + prod;
                 y.v[j] = (TO)prod;
             }
-            if (p.stems_out)
-                store_vec<TO, V>(reinterpret_cast<TO*>(p.stems_out) + (s * p.n_channels + c) * n + i0, y);
+            if (stems_out) store_vec<TO, V>(stems_out + (s * p.n_channels + c) * n + i0, y);
         }
         Vec<TO, V> o;
 #pragma unroll
@@ -148,11 +151,11 @@ __global__ void __launch_bounds__(kBlock) gain_mix_kernel(const GainMixParams p)
     }
     if (p.peak) {
         const double m = block_max(loc_peak, s_red);
-        if (threadIdx.x == 0) atomic_max_nonneg(p.peak + c, m);
+        if (threadIdx.x == 0) atomic_max_nonneg(p.peak + bt * p.n_channels + c, m);
     }
     if (p.sumsq) {
         const double m = block_sum(loc_sq, s_red);
-        if (threadIdx.x == 0) atomicAdd(p.sumsq + c, m);
+        if (threadIdx.x == 0) atomicAdd(p.sumsq + bt * p.n_channels + c, m);
     }
 }
 
@@ -161,10 +164,11 @@ int launch_gain_mix(const GainMixParams& p, bool vec_ok, cudaStream_t st) {
     constexpr int V = 4;
     if (vec_ok) {
         const long long nvec = (p.n_samples + V - 1) / V;
-        dim3 grid(grid_for(nvec, 8 / (int)(p.n_channels > 4 ? 4 : p.n_channels) + 1), (unsigned)p.n_channels);
+        const long long planes = p.n_channels * p.n_batch;
+        dim3 grid(grid_for(nvec, (int)(planes >= 16 ? 1 : 16 / planes)), (unsigned)p.n_channels, (unsigned)p.n_batch);
         gain_mix_kernel<TS, TC, TO, V><<<grid, kBlock, 0, st>>>(p);
     } else {
-        dim3 grid(grid_for(p.n_samples, 8), (unsigned)p.n_channels);
+        dim3 grid(grid_for(p.n_samples, 8), (unsigned)p.n_channels, (unsigned)p.n_batch);
         gain_mix_kernel<TS, TC, TO, 1><<<grid, kBlock, 0, st>>>(p);
     }
     DAM_CHECK_CUDA(cudaGetLastError());
@@ -175,6 +179,7 @@ int launch_gain_mix(const GainMixParams& p, bool vec_ok, cudaStream_t st) {
 // N2 bus sum
 struct BusParams {
     const void* stems;
+    long long batch_stride;
     long long n_stems, n_elems, stem_stride;
     int n_bus;
     void* out;
@@ -184,6 +189,8 @@ struct BusParams {
 template <typename T, int V>
 __global__ void __launch_bounds__(kBlock) bus_sum_kernel(const BusParams p) {
     const long long nvec = (p.n_elems + V - 1) / V;
+    const T* in = reinterpret_cast<const T*>(p.stems) + (long long)blockIdx.y * p.batch_stride;
+    T* outp = reinterpret_cast<T*>(p.out) + (long long)blockIdx.y * p.n_bus * p.n_elems;
     for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
         const long long i0 = v * V;
         for (int g = 0; g < p.n_bus; ++g) {
@@ -192,11 +199,11 @@ __global__ void __launch_bounds__(kBlock) bus_sum_kernel(const BusParams p) {
             for (int j = 0; j < V; ++j) acc.v[j] = T(0);
             for (long long s = 0; s < p.n_stems; ++s) {
                 if (p.group[s] != g) continue;
-                const Vec<T, V> x = load_vec<T, V>(reinterpret_cast<const T*>(p.stems) + s * p.stem_stride + i0);
+                const Vec<T, V> x = load_vec<T, V>(in + s * p.stem_stride + i0);
 #pragma unroll
                 for (int j = 0; j < V; ++j) acc.v[j] += x.v[j];
             }
-            store_vec<T, V>(reinterpret_cast<T*>(p.out) + (long long)g * p.n_elems + i0, acc);
+            store_vec<T, V>(outp + (long long)g * p.n_elems + i0, acc);
         }
     }
 }
@@ -359,7 +366,8 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 }  // namespace
 
 // ==========================================================================================
-extern "C" int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_stems, int64_t n_channels,
+extern "C" int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_batch, int64_t batch_stride,
+                            int64_t n_stems, int64_t n_channels,
                             int64_t n_samples, int64_t stem_stride, int64_t chan_stride,
                             const double* gains, int64_t n_gains, int64_t interp_coef, int hold_single,
                             int compute_dtype, void* mix_out, void* stems_out, int out_dtype,
@@ -372,18 +380,21 @@ extern "C" int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_stems,
     DAM_CHECK_ARG(out_dtype == DAM_F32 || out_dtype == DAM_F64, "out_dtype must be F32 or F64");
     DAM_CHECK_ARG(!(stems_dtype == DAM_F64 && compute_dtype == DAM_F32), "F64 stems need F64 compute");
     DAM_CHECK_ARG(n_stems >= 1 && n_channels >= 1 && n_channels <= 65535 && n_samples >= 0, "bad sizes");
+    DAM_CHECK_ARG(n_batch >= 0 && n_batch <= 65535, "n_batch must be in [0, 65535]");
+    if (n_batch == 0) return DAM_OK;
     DAM_CHECK_ARG(n_gains >= 1, "need at least one gain per stem");
     DAM_CHECK_ARG(n_gains <= n_samples || n_samples == 0, "Target mask should be longer than the initial one");
     DAM_CHECK_ARG(interp_coef >= 0, "interp_coef must be non-negative");
     if (n_samples == 0) return DAM_OK;
     GainMixParams p;
     p.stems = stems; p.n_stems = n_stems; p.n_channels = n_channels; p.n_samples = n_samples;
+    p.n_batch = n_batch; p.batch_stride = batch_stride;
     p.stem_stride = stem_stride; p.chan_stride = chan_stride;
     p.gains = gains; p.n_gains = n_gains; p.interp_coef = interp_coef;
     p.zero_mask = (n_gains == 1 && !hold_single) ? 1 : 0;
     p.mix_out = mix_out; p.stems_out = stems_out; p.peak = peak; p.sumsq = sumsq;
     const size_t es = stems_dtype == DAM_F32 ? 4 : 8;
-    bool vec_ok = (n_samples % 4 == 0) && (stem_stride % 4 == 0) && (chan_stride % 4 == 0) &&
+    bool vec_ok = (n_samples % 4 == 0) && (stem_stride % 4 == 0) && (chan_stride % 4 == 0) && (batch_stride % 4 == 0) &&
                   ((reinterpret_cast<uintptr_t>(stems) % (4 * es)) == 0) &&
                   (!mix_out || (reinterpret_cast<uintptr_t>(mix_out) % 32) == 0) &&
                   (!stems_out || (reinterpret_cast<uintptr_t>(stems_out) % 32) == 0);
@@ -400,16 +411,19 @@ extern "C" int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_stems,
                                 : launch_gain_mix<double, double, float>(p, vec_ok, st);
 }
 
-extern "C" int dam_bus_sum(const void* stems, int dtype, int64_t n_stems, int64_t n_elems, int64_t stem_stride,
+extern "C" int dam_bus_sum(const void* stems, int dtype, int64_t n_batch, int64_t batch_stride,
+                           int64_t n_stems, int64_t n_elems, int64_t stem_stride,
                            const int32_t* group_host, int n_bus, void* out, void* stream) {
     dam_clear_error();
     DAM_CHECK_ARG(stems && group_host && out, "null pointer argument");
     DAM_CHECK_ARG(dtype == DAM_F32 || dtype == DAM_F64, "dtype must be F32 or F64");
     DAM_CHECK_ARG(n_stems >= 1 && n_stems <= 64, "n_stems must be in [1, 64]");
     DAM_CHECK_ARG(n_bus >= 1 && n_bus <= 64 && n_elems >= 0, "bad sizes");
-    if (n_elems == 0) return DAM_OK;
+    DAM_CHECK_ARG(n_batch >= 0 && n_batch <= 65535, "n_batch must be in [0, 65535]");
+    if (n_elems == 0 || n_batch == 0) return DAM_OK;
     BusParams p;
     p.stems = stems; p.n_stems = n_stems; p.n_elems = n_elems; p.stem_stride = stem_stride;
+    p.batch_stride = batch_stride;
     p.n_bus = n_bus; p.out = out;
     for (int i = 0; i < 64; ++i) p.group[i] = -1;
     for (int64_t s = 0; s < n_stems; ++s) {
@@ -417,16 +431,16 @@ extern "C" int dam_bus_sum(const void* stems, int dtype, int64_t n_stems, int64_
         p.group[s] = group_host[s];
     }
     const size_t es = dtype == DAM_F32 ? 4 : 8;
-    const bool vec_ok = (n_elems % 4 == 0) && (stem_stride % 4 == 0) &&
+    const bool vec_ok = (n_elems % 4 == 0) && (stem_stride % 4 == 0) && (batch_stride % 4 == 0) &&
                         (reinterpret_cast<uintptr_t>(stems) % (4 * es) == 0) &&
                         (reinterpret_cast<uintptr_t>(out) % (4 * es) == 0);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (dtype == DAM_F32) {
-        if (vec_ok) bus_sum_kernel<float, 4><<<grid_for((n_elems + 3) / 4), kBlock, 0, st>>>(p);
-        else bus_sum_kernel<float, 1><<<grid_for(n_elems), kBlock, 0, st>>>(p);
+        if (vec_ok) bus_sum_kernel<float, 4><<<dim3(grid_for((n_elems + 3) / 4, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p);
+        else bus_sum_kernel<float, 1><<<dim3(grid_for(n_elems, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p);
     } else {
-        if (vec_ok) bus_sum_kernel<double, 4><<<grid_for((n_elems + 3) / 4), kBlock, 0, st>>>(p);
-        else bus_sum_kernel<double, 1><<<grid_for(n_elems), kBlock, 0, st>>>(p);
+        if (vec_ok) bus_sum_kernel<double, 4><<<dim3(grid_for((n_elems + 3) / 4, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p);
+        else bus_sum_kernel<double, 1><<<dim3(grid_for(n_elems, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p);
     }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;

@@ -43,6 +43,7 @@ struct StftParams {
     int audio_dtype;
     int channels;
     long long n_rows, n_samples, row_stride, chan_stride, samp_stride;
+    long long n_inner, outer_stride;   // row r starts at (r / n_inner)*outer_stride + (r % n_inner)*row_stride
     double input_scale;
     const double* row_gain;
     const float* window;
@@ -57,6 +58,12 @@ struct StftParams {
     long long out_row_stride;
     double* stats;
 };
+
+__device__ __forceinline__ long long row_offset(const StftParams& p, long long row) {
+    if (p.n_inner <= 0) return row * p.row_stride;
+    const long long outer = row / p.n_inner;
+    return outer * p.outer_stride + (row - outer * p.n_inner) * p.row_stride;
+}
 
 // ---- staging --------------------------------------------------------------------------------
 // Samples [g0, g0 + span) of one row go to shared memory as the compute type R after the
@@ -111,7 +118,7 @@ __device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ 
                                            long long g0, int span, int tid) {
     constexpr int V = VecOf<SRC>::kN;
     constexpr int U = 4;                         // vector loads in flight per thread and channel
-    const SRC* __restrict__ base = reinterpret_cast<const SRC*>(p.audio) + row * p.row_stride;
+    const SRC* __restrict__ base = reinterpret_cast<const SRC*>(p.audio) + row_offset(p, row);
     const long long n = p.n_samples;
     const int C = p.channels;
     Prologue<P> pro;
@@ -215,7 +222,7 @@ __device__ __forceinline__ void prefetch_tile(const StftParams& p, long long row
     if (p.samp_stride != 1) return;
     long long lo = g0 < 0 ? 0 : g0;
     long long hi = g0 + span > p.n_samples ? p.n_samples : g0 + span;
-    const char* base = reinterpret_cast<const char*>(p.audio) + row * p.row_stride * elem_bytes;
+    const char* base = reinterpret_cast<const char*>(p.audio) + row_offset(p, row) * elem_bytes;
     const long long bytes = (hi - lo) * elem_bytes;
     for (int c = 0; c < p.channels; ++c) {
         const char* q = base + (c * p.chan_stride + lo) * elem_bytes;
@@ -541,6 +548,7 @@ int launch(const StftParams& p, cudaStream_t stream) {
 extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
                            int64_t n_rows, int64_t n_samples,
                            int64_t row_stride, int64_t chan_stride, int64_t samp_stride,
+                           int64_t n_inner, int64_t outer_stride,
                            double input_scale, const double* row_gain,
                            const float* window, int n_fft, int hop,
                            double amin, double multiplier, int compute_dtype,
@@ -562,6 +570,7 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     DAM_CHECK_ARG(hop >= 1 && hop <= n_fft, "hop=%d must be in [1, n_fft]", hop);
     DAM_CHECK_ARG(amin >= 0.0, "amin must be non-negative");
     DAM_CHECK_ARG(out_row_stride >= 0, "out_row_stride must be non-negative");
+    DAM_CHECK_ARG(n_inner >= 0, "n_inner must be non-negative");
     if (n_rows == 0) return DAM_OK;
     DAM_CHECK_ARG(n_samples > n_fft / 2,
                   "reflect padding needs n_samples > n_fft/2 (got %lld)", (long long)n_samples);
@@ -574,6 +583,7 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     p.audio = audio; p.audio_dtype = audio_dtype; p.channels = channels;
     p.n_rows = n_rows; p.n_samples = n_samples;
     p.row_stride = row_stride; p.chan_stride = chan_stride; p.samp_stride = samp_stride;
+    p.n_inner = (n_inner > 0 && n_inner < n_rows) ? n_inner : 0; p.outer_stride = outer_stride;
     p.input_scale = input_scale; p.row_gain = row_gain; p.window = window;
     p.hop = hop; p.T = 1 + n_samples / hop;
     p.tiles_per_row = (p.T + kFT - 1) / kFT;

@@ -47,25 +47,44 @@ def stft_db(audio: torch.Tensor, n_fft: int = 2048, hop: int = 1024, window: tor
     if not audio.is_cuda:
         raise ValueError('stft_db needs a CUDA tensor (host arrays go through compute_features)')
     dev = audio.device
+    n_inner, outer_stride = 0, 0
+    nd = audio.dim()
     if channel_axis is None:
         lead, C, n = audio.shape[:-1], 1, audio.shape[-1]
-        a = audio.reshape(-1, n) if audio.dim() != 2 else audio
-        rows = a.shape[0]
-        row_stride, chan_stride, samp_stride = a.stride(0), 0, a.stride(1)
+        n_lead, chan_stride, samp_stride = nd - 1, 0, audio.stride(-1)
     else:
-        ax = channel_axis % audio.dim()
-        if ax == audio.dim() - 2:
-            lead, C, n = audio.shape[:-2], audio.shape[-2], audio.shape[-1]
-            a = audio.reshape(-1, C, n) if audio.dim() != 3 else audio
-            rows = a.shape[0]
-            row_stride, chan_stride, samp_stride = a.stride(0), a.stride(1), a.stride(2)
-        elif ax == audio.dim() - 1:
-            lead, C, n = audio.shape[:-2], audio.shape[-1], audio.shape[-2]
-            a = audio.reshape(-1, n, C) if audio.dim() != 3 else audio
-            rows = a.shape[0]
-            row_stride, chan_stride, samp_stride = a.stride(0), a.stride(2), a.stride(1)
+        ax = channel_axis % nd
+        lead = audio.shape[:-2]
+        n_lead = nd - 2
+        if ax == nd - 2:
+            C, n = audio.shape[-2], audio.shape[-1]
+            chan_stride, samp_stride = audio.stride(-2), audio.stride(-1)
+        elif ax == nd - 1:
+            C, n = audio.shape[-1], audio.shape[-2]
+            chan_stride, samp_stride = audio.stride(-1), audio.stride(-2)
         else:
             raise ValueError('channel_axis must be one of the last two axes')
+    a = audio
+    if n_lead == 0:
+        rows, row_stride = 1, 0
+    elif n_lead == 1:
+        rows, row_stride = audio.shape[0], audio.stride(0)
+    elif n_lead == 2 and not audio.is_contiguous():
+        # [outer, inner, ...] strided view (e.g. segments x chunks): two-level row addressing
+        rows, row_stride = audio.shape[0] * audio.shape[1], audio.stride(1)
+        n_inner, outer_stride = audio.shape[1], audio.stride(0)
+    else:
+        rows = 1
+        for d in lead:
+            rows *= d
+        a = audio.reshape((rows,) + tuple(audio.shape[n_lead:]))
+        row_stride = a.stride(0)
+        if channel_axis is None:
+            samp_stride = a.stride(-1)
+        elif ax == nd - 2:
+            chan_stride, samp_stride = a.stride(-2), a.stride(-1)
+        else:
+            chan_stride, samp_stride = a.stride(-1), a.stride(-2)
     if rows <= 1:
         row_stride = 0 if rows == 0 else row_stride
     if compute_dtype is None:
@@ -98,7 +117,7 @@ def stft_db(audio: torch.Tensor, n_fft: int = 2048, hop: int = 1024, window: tor
     with torch.cuda.device(dev):
         rc = _lib.lib().dam_stft_db(
             _lib.ptr(a), _lib.dtype_code(audio.dtype), C, rows, n,
-            row_stride, chan_stride, samp_stride, float(input_scale), _lib.ptr(row_gain),
+            row_stride, chan_stride, samp_stride, n_inner, outer_stride, float(input_scale), _lib.ptr(row_gain),
             _lib.ptr(window), n_fft, hop, float(amin), float(multiplier),
             _lib.dtype_code(compute_dtype), _lib.ptr(out), _lib.dtype_code(out_dtype), int(out_row_stride),
             _lib.ptr(stats), _lib.stream_ptr(stream))

@@ -62,7 +62,8 @@ class Meter:
         bounds = np.unique(np.concatenate([lo, hi]))
         first = np.searchsorted(bounds, lo)
         last = np.searchsorted(bounds, hi)           # block j = segments [first, last)
-        geo = (torch.from_numpy(bounds).to(dev), len(bounds) - 1, first, last, num_blocks)
+        geo = (torch.from_numpy(bounds).to(dev), len(bounds) - 1, first, last, num_blocks,
+               torch.from_numpy(first.astype(np.int64)).to(dev), torch.from_numpy(last.astype(np.int64)).to(dev))
         if len(self._bounds_cache) > 64:
             self._bounds_cache.clear()
         self._bounds_cache[key] = geo
@@ -77,7 +78,14 @@ class Meter:
         if n < self.block_size * self.rate:
             raise ValueError('Audio must have length greater than the block size.')
         dev = rows.device
-        bounds, n_seg, first, last, num_blocks = self._geometry(n, dev)
+        seg, first, last = self._segment_sums(rows)
+        csum = np.concatenate([np.zeros((R, 1)), np.cumsum(seg.cpu().numpy(), axis=1)], axis=1)
+        return (csum[:, last] - csum[:, first]) / (self.block_size * self.rate)
+
+    def _segment_sums(self, rows: torch.Tensor):
+        R, n = rows.shape
+        dev = rows.device
+        bounds, n_seg, first, last, num_blocks = self._geometry(n, dev)[:5]
         seg = torch.zeros((R, n_seg), dtype=torch.float64, device=dev)
         lib = _lib.lib()
         ws_bytes = lib.dam_kweight_workspace_bytes(R, n)
@@ -88,8 +96,26 @@ class Meter:
                                           rows.stride(0), rows.stride(1), coeffs, _lib.ptr(bounds), n_seg,
                                           _lib.ptr(seg), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
         _lib.check(rc, 'dam_kweight_segments')
-        csum = np.concatenate([np.zeros((R, 1)), np.cumsum(seg.cpu().numpy(), axis=1)], axis=1)
-        return (csum[:, last] - csum[:, first]) / (self.block_size * self.rate)
+        return seg, first, last
+
+    def integrated_loudness_device(self, signals: torch.Tensor) -> torch.Tensor:
+        """signals [R, C, N] CUDA -> float64 CUDA tensor [R] of LUFS values; K-weighting, block sums
+        and gating all run on the device with no host synchronisation."""
+        R, C, n = signals.shape
+        if n < self.block_size * self.rate:
+            raise ValueError('Audio must have length greater than the block size.')
+        rows = signals.reshape(R * C, n)
+        if rows.stride(1) != 1:
+            rows = rows.contiguous()
+        seg, _, _ = self._segment_sums(rows)
+        geo = self._geometry(n, rows.device)
+        out = torch.empty(R, dtype=torch.float64, device=rows.device)
+        with torch.cuda.device(rows.device):
+            rc = _lib.lib().dam_gated_loudness(_lib.ptr(seg), R, C, geo[1], _lib.ptr(geo[5]), _lib.ptr(geo[6]),
+                                               geo[4], 1.0 / (self.block_size * self.rate), _lib.ptr(out),
+                                               _lib.stream_ptr())
+        _lib.check(rc, 'dam_gated_loudness')
+        return out
 
     @staticmethod
     def gated_loudness(z: np.ndarray) -> float:

@@ -17,60 +17,75 @@ def gain_mix(stems: torch.Tensor, gains, interp_coef: int = None, hold_single: b
              want_mix: bool = True, want_stems: bool = False, want_stats: bool = False, stream=None):
     """Zero-order-hold gain masks x stems, summed over stems (kernel K2).
 
-    stems [S, C, N] CUDA float32/float64 (planar); gains [S, K] (array-like or tensor), amplitude
+    stems [S, C, N] (or a batch [B, S, C, N]) CUDA float32/float64 planar audio; gains [S, K]
+    ([B, S, K]) array-like or tensor, amplitude
     gains.  mask_s[i] = gains[s][min(i // interp_coef, K-1)], interp_coef = int(N / K) by default
     (inference_utils.py:26); K == 1 gives an all-zero mask unless hold_single (the reference quirk).
     Returns dict(mix=[C, N], stems=[S, C, N], peak=[C], sumsq=[C]) for the requested outputs.
     """
     _check_cuda(stems, 'stems')
-    if stems.dim() != 3:
-        raise ValueError('stems must be [S, C, N]')
+    batched = stems.dim() == 4
+    if stems.dim() not in (3, 4):
+        raise ValueError('stems must be [S, C, N] or [B, S, C, N]')
     if stems.stride(-1) != 1:
         stems = stems.contiguous()
-    S, C, N = stems.shape
+    if not batched:
+        stems = stems.unsqueeze(0)
+    B, S, C, N = stems.shape
     dev = stems.device
     g = torch.as_tensor(np.asarray(gains, dtype=np.float64) if not isinstance(gains, torch.Tensor) else gains)
-    g = g.to(device=dev, dtype=torch.float64).reshape(S, -1).contiguous()
-    K = g.shape[1]
+    g = g.to(device=dev, dtype=torch.float64).reshape(B, S, -1).contiguous()
+    K = g.shape[2]
     assert K <= N or N == 0, "Target mask should be longer than the initial one"
     if interp_coef is None:
         interp_coef = int(N / K)
     if out_dtype is None:
         out_dtype = compute_dtype
-    mix = torch.empty((C, N), dtype=out_dtype, device=dev) if want_mix else None
-    st_out = torch.empty((S, C, N), dtype=out_dtype, device=dev) if want_stems else None
-    peak = torch.zeros(C, dtype=torch.float64, device=dev) if want_stats else None
-    sumsq = torch.zeros(C, dtype=torch.float64, device=dev) if want_stats else None
+    mix = torch.empty((B, C, N), dtype=out_dtype, device=dev) if want_mix else None
+    st_out = torch.empty((B, S, C, N), dtype=out_dtype, device=dev) if want_stems else None
+    peak = torch.zeros((B, C), dtype=torch.float64, device=dev) if want_stats else None
+    sumsq = torch.zeros((B, C), dtype=torch.float64, device=dev) if want_stats else None
     with torch.cuda.device(dev):
         rc = _lib.lib().dam_gain_mix(
-            _lib.ptr(stems), _lib.dtype_code(stems.dtype), S, C, N, stems.stride(0), stems.stride(1),
+            _lib.ptr(stems), _lib.dtype_code(stems.dtype), B, stems.stride(0) if B > 1 else 0,
+            S, C, N, stems.stride(1), stems.stride(2),
             _lib.ptr(g), K, int(interp_coef), int(bool(hold_single)), _lib.dtype_code(compute_dtype),
             _lib.ptr(mix), _lib.ptr(st_out), _lib.dtype_code(out_dtype),
             _lib.ptr(peak), _lib.ptr(sumsq), _lib.stream_ptr(stream))
     _lib.check(rc, 'dam_gain_mix')
+    if not batched:
+        mix, st_out, peak, sumsq = [None if t is None else t[0] for t in (mix, st_out, peak, sumsq)]
     return dict(mix=mix, stems=st_out, peak=peak, sumsq=sumsq)
 
 
 def stem_sum(stems: torch.Tensor, out_dtype=None) -> torch.Tensor:
     """np.sum(np.array(list(d.values())), axis=0) (evaluation.py:59-60) for stems [S, C, N]."""
-    ones = torch.ones((stems.shape[0], 1), dtype=torch.float64, device=stems.device)
+    ones = torch.ones(tuple(stems.shape[:-2]) + (1,), dtype=torch.float64, device=stems.device)
     return gain_mix(stems, ones, hold_single=True, compute_dtype=stems.dtype,
                     out_dtype=out_dtype or stems.dtype)['mix']
 
 
-def bus_sum(stems: torch.Tensor, group, n_bus: int = 4) -> torch.Tensor:
+def bus_sum(stems: torch.Tensor, group, n_bus: int = 4, batch_dims: int = 0) -> torch.Tensor:
     """S raw stems -> n_bus buses, summed in stem order in the audio dtype (kernel N2;
-    data/medleydb_data_surgery.ipynb:305-332).  stems [S, ...]; group[s] in [0, n_bus) or -1."""
+    data/medleydb_data_surgery.ipynb:305-332).  stems [S, ...] (or [B, S, ...] with batch_dims=1);
+    group[s] in [0, n_bus) or -1 (dropped)."""
     _check_cuda(stems, 'stems')
-    S = stems.shape[0]
-    flat = stems.reshape(S, -1)
-    if flat.stride(1) != 1:
+    if batch_dims:
+        B, S = stems.shape[0], stems.shape[1]
+        flat = stems.reshape(B, S, -1)
+        tail = tuple(stems.shape[2:])
+    else:
+        B, S = 1, stems.shape[0]
+        flat = stems.reshape(1, S, -1)
+        tail = tuple(stems.shape[1:])
+    if flat.stride(2) != 1:
         flat = flat.contiguous()
-    out = torch.empty((n_bus,) + tuple(stems.shape[1:]), dtype=stems.dtype, device=stems.device)
+    out = torch.empty(((B,) if batch_dims else ()) + (n_bus,) + tail, dtype=stems.dtype, device=stems.device)
     grp = (ctypes.c_int32 * S)(*[int(v) for v in group])
     with torch.cuda.device(stems.device):
-        rc = _lib.lib().dam_bus_sum(_lib.ptr(flat), _lib.dtype_code(stems.dtype), S, flat.shape[1],
-                                    flat.stride(0), grp, n_bus, _lib.ptr(out), _lib.stream_ptr())
+        rc = _lib.lib().dam_bus_sum(_lib.ptr(flat), _lib.dtype_code(stems.dtype), B, flat.stride(0) if B > 1 else 0,
+                                    S, flat.shape[2], flat.stride(1), grp, n_bus, _lib.ptr(out),
+                                    _lib.stream_ptr())
     _lib.check(rc, 'dam_bus_sum')
     return out
 

@@ -1,0 +1,140 @@
+"""Batched segment pipeline: S raw stems -> 4 buses -> dB-STFT features -> (CNN gains) -> gain masks ->
+mixdown -> BS.1770 loudness -> -20 LUFS normalisation, for a batch of independent segments.
+
+This is BASELINE.json config 2 ("model_scalar_2s inference batch of 64 synthetic 8-stem 10 s
+segments") expressed with the kernels of this package; every stage is asynchronous on one CUDA
+stream and nothing synchronises with the host.  Reference semantics per stage:
+
+  bus sum        data/medleydb_data_surgery.ipynb:305-332   (float32, stem order)
+  features       data/dataset.py:132-162 + mono mean :181-183, per chunk of chunk_samples
+  gains          10**(0.5*m) per chunk (data/dataset_utils.py:46-50); segments shorter than
+                 8 chunks cannot go through mix_song_smooth's Savitzky-Golay filter,
+                 so the per-chunk gains are held directly
+  mask + mix     inference_utils.py:12-41,143 and evaluation.py:59-60 (float64)
+  loudness       pyloudnorm integrated loudness of the mix (evaluation.py:63)
+  normalise      x * 10**((-20 - L)/20) (evaluation.py:64)
+"""
+import numpy as np
+import torch
+
+from . import features, mixing
+from .loudness import Meter
+
+KERNEL_LAUNCHES_PER_BATCH = {'bus_sum': 1, 'stft_db': 4, 'gain_mix': 1, 'kweight': 3, 'gating': 1, 'scale': 1}
+
+
+class SegmentBatchPipeline:
+    def __init__(self, n_stems=8, group=(0, 1, 1, 2, 2, 3, 3, 3), chunk_samples=88200, hop=512, n_fft=2048,
+                 sr=44100, target_lufs=-20.0, device=None):
+        self.n_stems, self.group = n_stems, list(group)
+        self.chunk_samples, self.hop, self.n_fft, self.sr = chunk_samples, hop, n_fft, sr
+        self.target = target_lufs
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self.meter = Meter(sr)
+        self.timings = None          # optional dict of CUDA event pairs per stage
+
+    def n_chunks(self, n_samples: int) -> int:
+        return n_samples // self.chunk_samples
+
+    def features(self, buses: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """buses [B, 4, C, N] float32 -> [B * n_chunks, 4, F, T] float32 (model input layout)."""
+        B, S, C, N = buses.shape
+        nc = self.n_chunks(N)
+        F = self.n_fft // 2 + 1
+        T = features.num_frames(self.chunk_samples, self.hop)
+        if out is None:
+            out = torch.empty((B * nc, S, F, T), dtype=torch.float32, device=buses.device)
+        for s in range(S):
+            # rows = (segment, chunk) of bus s: two-level addressing, channels averaged in the kernel
+            view = buses[:, s].as_strided((B, nc, C, self.chunk_samples),
+                                          (buses.stride(0), self.chunk_samples, buses.stride(2), 1),
+                                          buses[:, s].storage_offset())
+            features.stft_db(view, self.n_fft, self.hop, channel_axis=-2, out=out[:, s],
+                             out_row_stride=S * F * T)
+        return out
+
+    def _ev(self, name):
+        if self.timings is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.timings.setdefault(name, []).append(e)
+
+    def run(self, raw: torch.Tensor, m: torch.Tensor = None, model=None, feats_out: torch.Tensor = None):
+        """raw [B, S, C, N] float32 on the device.  ``m`` [B*n_chunks, 4] are the CNN head outputs; if
+        None they are computed with ``model`` from the features.  Returns a dict with the normalised
+        mixes [B, C, N] (float64), their loudness before normalisation [B], the features and m."""
+        B, S, C, N = raw.shape
+        nc = self.n_chunks(N)
+        self._ev('bus0')
+        buses = mixing.bus_sum(raw, self.group, 4, batch_dims=1)                   # [B, 4, C, N]
+        self._ev('bus1')
+        feats = self.features(buses, feats_out)
+        self._ev('stft1')
+        if m is None:
+            with torch.no_grad():
+                _, ms = model(feats)
+            m = torch.cat([v.reshape(-1, 1) for v in ms], dim=1)
+        # gain = 10**(0.5 m) in float32 like the reference, one per (segment, bus, chunk)
+        gains = torch.pow(10.0, 0.5 * m.float()).double().reshape(B, nc, 4).permute(0, 2, 1).contiguous()
+        self._ev('gain0')
+        res = mixing.gain_mix(buses, gains, interp_coef=int(N / nc), compute_dtype=torch.float64,
+                              want_mix=True, want_stats=True)
+        self._ev('mix1')
+        lufs = self.meter.integrated_loudness_device(res['mix'])                    # [B] on the device
+        self._ev('loud1')
+        factor = torch.pow(10.0, (self.target - lufs) / 20.0)
+        norm = mixing.scale_rows(res['mix'].reshape(B, C * N), factor).reshape(B, C, N)
+        self._ev('scale1')
+        return dict(mix=norm, lufs=lufs, peak=res['peak'], sumsq=res['sumsq'], features=feats, m=m)
+
+    def run_host(self, raw_host: torch.Tensor, m_host: torch.Tensor, out_host: torch.Tensor,
+                 lufs_host: torch.Tensor, sub_batch: int = 8, streams=None):
+        """End-to-end form with HOST (pinned) buffers: raw_host [B, S, C, N] float32 -> out_host
+        [B, C, N] float64 and lufs_host [B].  The batch is cut into sub-batches; uploads, kernels and
+        downloads of consecutive sub-batches overlap on three streams."""
+        B = raw_host.shape[0]
+        nc = self.n_chunks(raw_host.shape[-1])
+        dev = self.device
+        if streams is None:
+            streams = [torch.cuda.Stream(dev) for _ in range(3)]
+        s_in, s_cmp, s_out = streams
+        cur = torch.cuda.current_stream(dev)
+        for st in streams:
+            st.wait_stream(cur)
+        keep = []
+        for b0 in range(0, B, sub_batch):
+            b1 = min(B, b0 + sub_batch)
+            with torch.cuda.stream(s_in):
+                raw = raw_host[b0:b1].to(dev, non_blocking=True)
+                m = m_host[b0 * nc:b1 * nc].to(dev, non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in)
+                res = self.run(raw, m)
+                raw.record_stream(s_cmp)
+                m.record_stream(s_cmp)
+                ev_cmp = torch.cuda.Event()
+                ev_cmp.record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp)
+                out_host[b0:b1].copy_(res['mix'], non_blocking=True)
+                lufs_host[b0:b1].copy_(res['lufs'], non_blocking=True)
+                res['mix'].record_stream(s_out)
+                res['lufs'].record_stream(s_out)
+            keep.append(res)
+        for st in streams:
+            cur.wait_stream(st)
+        return keep
+
+
+def algorithmic_bytes(B, S, C, N, n_chunks, chunk_samples, hop, n_fft=2048, n_bus=4):
+    """Minimum HBM bytes per stage for one batch (each operand read/written once)."""
+    F = n_fft // 2 + 1
+    T = 1 + chunk_samples // hop
+    raw = B * S * C * N * 4
+    bus = B * n_bus * C * N * 4
+    feats = B * n_chunks * n_bus * F * T * 4
+    mix = B * C * N * 8
+    return {'bus_sum': raw + bus, 'stft_db': B * n_bus * C * n_chunks * chunk_samples * 4 + feats,
+            'gain_mix': bus + mix, 'kweight': mix, 'scale': 2 * mix}

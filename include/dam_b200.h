@@ -57,6 +57,9 @@ const char* dam_last_error(void);
  *                audio[r*row_stride + c*chan_stride + i*samp_stride]
  *                (planar [C, n]: chan_stride = n, samp_stride = 1;
  *                 interleaved [n, C]: chan_stride = 1, samp_stride = C).
+ *                With n_inner > 0 rows are addressed on two levels (e.g. segment x chunk): row r
+ *                starts at (r / n_inner)*outer_stride + (r % n_inner)*row_stride instead of
+ *                r*row_stride; n_inner = 0 means one level.
  *                channels > 1 are averaged (np.mean over the channel axis) in the source
  *                precision (float for I16/F32, double for F64) before framing.
  *   input_scale  multiplies every loaded sample (use 1/32768 for PCM16, 1 otherwise).
@@ -78,6 +81,7 @@ const char* dam_last_error(void);
 int dam_stft_db(const void* audio, int audio_dtype, int channels,
                 int64_t n_rows, int64_t n_samples,
                 int64_t row_stride, int64_t chan_stride, int64_t samp_stride,
+                int64_t n_inner, int64_t outer_stride,
                 double input_scale, const double* row_gain,
                 const float* window, int n_fft, int hop,
                 double amin, double multiplier, int compute_dtype,
@@ -91,9 +95,10 @@ int dam_stft_db(const void* audio, int audio_dtype, int channels,
  *                                                data/listening_test_data_preparation.py:20-21
  *           RandomModel.forward (scalar gains)   models/baselines/random_model.py:11
  *
- *   stems        [n_stems, n_channels, n_samples] planar, dtype stems_dtype (F32 or F64);
- *                stem_stride / chan_stride in elements, samples contiguous.
- *   gains        [n_stems, n_gains] float64 amplitude gains.
+ *   stems        n_batch songs of [n_stems, n_channels, n_samples] planar audio, dtype stems_dtype
+ *                (F32 or F64); batch_stride / stem_stride / chan_stride in elements, samples
+ *                contiguous.  Outputs and gains are dense with the batch as leading dimension.
+ *   gains        [n_batch, n_stems, n_gains] float64 amplitude gains.
  *   interp_coef  samples held per gain = int(n_samples / n_gains) as Python computes it.
  *                mask_s[i] = gains[s][min(i / interp_coef, n_gains-1)]; with n_gains == 1 and
  *                hold_single == 0 the mask is all zeros (the reference quirk);
@@ -101,12 +106,14 @@ int dam_stft_db(const void* audio, int audio_dtype, int channels,
  *   compute_dtype  F64: product and sum in float64 (float64 mask path, outputs are float64 in
  *                the reference); F32: gain cast to float32, product and sum in float32
  *                (python-float x float32-array path of RandomModel).
- *   mix_out      optional [n_channels, n_samples], dtype out_dtype: sum over stems in stem order.
- *   stems_out    optional [n_stems, n_channels, n_samples] contiguous, dtype out_dtype.
- *   peak, sumsq  optional device double[n_channels]: max |mix| (atomic max) and sum mix^2
+ *   mix_out      optional [n_batch, n_channels, n_samples], dtype out_dtype: sum over stems in
+ *                stem order.
+ *   stems_out    optional [n_batch, n_stems, n_channels, n_samples] contiguous, dtype out_dtype.
+ *   peak, sumsq  optional device double[n_batch, n_channels]: max |mix| (atomic max) and sum mix^2
  *                (atomic add) per channel; caller zeroes them.
  */
-int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_stems, int64_t n_channels,
+int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_batch, int64_t batch_stride,
+                 int64_t n_stems, int64_t n_channels,
                  int64_t n_samples, int64_t stem_stride, int64_t chan_stride,
                  const double* gains, int64_t n_gains, int64_t interp_coef, int hold_single,
                  int compute_dtype, void* mix_out, void* stems_out, int out_dtype,
@@ -115,10 +122,12 @@ int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_stems, int64_t n_
 /*
  * N2: S raw stems -> n_bus bus sums (summed_track += track in stem order, in the audio dtype).
  * Replaces  sum_stems  data/medleydb_data_surgery.ipynb:305-332.
- *   stems [n_stems, n_elems] (rows stem_stride apart), group[n_stems] (host pointer; bus index,
- *   or -1 to drop a stem), out [n_bus, n_elems] contiguous, same dtype (F32 or F64).
+ *   stems: n_batch songs of [n_stems, n_elems] (stems stem_stride apart, songs batch_stride apart),
+ *   group[n_stems] (host pointer; bus index, or -1 to drop a stem),
+ *   out [n_batch, n_bus, n_elems] contiguous, same dtype (F32 or F64).
  */
-int dam_bus_sum(const void* stems, int dtype, int64_t n_stems, int64_t n_elems, int64_t stem_stride,
+int dam_bus_sum(const void* stems, int dtype, int64_t n_batch, int64_t batch_stride,
+                int64_t n_stems, int64_t n_elems, int64_t stem_stride,
                 const int32_t* group_host, int n_bus, void* out, void* stream);
 
 /*
@@ -182,6 +191,18 @@ int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, int64_t n_sam
                          int64_t row_stride, int64_t samp_stride,
                          const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,
                          double* seg_sumsq, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Gating and LUFS of BS.1770 on the device, from the segment sums of dam_kweight_segments:
+ * block j of a signal is the run of segments [block_first[j], block_last[j]); absolute gate
+ * -70 LUFS, relative gate -10 LU, channel weights 1,1,1,1.41,1.41 (the tail of
+ * pyloudnorm.Meter.integrated_loudness).  seg_sumsq is [n_signals * n_channels, n_seg] with the
+ * channels of a signal adjacent; lufs_out is DEVICE double[n_signals].  Lets batch pipelines
+ * normalise (K5 reads its factors from device memory) without a host round trip.
+ */
+int dam_gated_loudness(const double* seg_sumsq, int64_t n_signals, int n_channels, int64_t n_seg,
+                       const int64_t* block_first, const int64_t* block_last, int64_t n_blocks,
+                       double inv_block_len, double* lufs_out, void* stream);
 
 /* Number of frames dam_stft_db produces for n_samples (1 + n_samples / hop). */
 int64_t dam_stft_num_frames(int64_t n_samples, int hop);
