@@ -19,6 +19,7 @@
 #include "fft_codelets.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <mutex>
 #include <vector>
 
@@ -26,17 +27,24 @@ namespace {
 
 constexpr int kNfft = 2048;
 constexpr int kBins = kNfft / 2 + 1;
-constexpr int kFT = 8;            // frames per tile
-constexpr int kThreads = 256;     // 8 warps: stage 1 one warp per frame; stage 2 runs 264 (k', frame) tasks
+// Frames per tile FT is a template parameter: a CTA has FT warps (stage 1: one warp per frame;
+// stage 2: 32 k' x FT frames = 32*FT thread tasks).  float32 uses FT = 8 with two CTAs per SM,
+// float64 FT = 8 with one.
 constexpr int kRow = 34;          // complex elements per k' row in the exchange / twiddle tables
 constexpr int kKp = 33;           // stage-2 tasks per frame
 
 template <typename R> struct Cx;
-// Exchange buffer: per frame 32 rows (k' = 0..31) of kRow complex values (k' = 32 never leaves stage 1).  The per-frame stride is
-// chosen so the 128-bit stage-2 loads (lane = frame + 8*(k' mod 4)) are bank-conflict free:
-// float: stride/2 odd (two complex per load); double: stride odd (one complex per load).
-template <> struct Cx<float>  { using type = float2;  static constexpr int kXch = 32 * kRow + 2; };  // 1090
-template <> struct Cx<double> { using type = double2; static constexpr int kXch = 32 * kRow + 1; };  // 1089
+template <> struct Cx<float>  { using type = float2; };
+template <> struct Cx<double> { using type = double2; };
+// Exchange buffer: per frame 32 rows (k' = 0..31) of kRow complex values (k' = 32 never leaves
+// stage 1).  The per-frame stride, in complex elements, is chosen so the 128-bit stage-2 loads
+// (lane = frame + FT * (k' mod 32/FT)) are bank-conflict free:
+//   float  (two complex per load, row = 17 x 16 B): FT = 8 needs stride/2 odd, FT = 4 stride/2 = 2 mod 8
+//   double (one complex per load):                  FT = 8 needs stride odd
+template <typename R, int FT> struct XchStride;
+template <> struct XchStride<float, 8>  { static constexpr int v = 32 * kRow + 2; };   // 1090
+template <> struct XchStride<float, 4>  { static constexpr int v = 32 * kRow + 4; };   // 1092
+template <> struct XchStride<double, 8> { static constexpr int v = 32 * kRow + 1; };   // 1089
 
 struct StftParams {
     const void* audio;
@@ -113,7 +121,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-template <typename R, typename P, typename SRC>
+template <typename R, typename P, typename SRC, int kThreads>
 __device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ s_stage, long long row,
                                            long long g0, int span, int tid) {
     constexpr int V = VecOf<SRC>::kN;
@@ -217,6 +225,7 @@ __device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ 
 }
 
 // L2 prefetch of the samples the NEXT tile of this CTA will stage (no registers, no smem).
+template <int kThreads>
 __device__ __forceinline__ void prefetch_tile(const StftParams& p, long long row, long long g0, int span,
                                               int elem_bytes, int tid) {
     if (p.samp_stride != 1) return;
@@ -269,11 +278,12 @@ template <typename R> __device__ __forceinline__ R shfl_xor_r(R v, int m);
 template <> __device__ __forceinline__ float shfl_xor_r<float>(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 template <> __device__ __forceinline__ double shfl_xor_r<double>(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
-template <typename R, typename OUT, bool kStats>
-__global__ void __launch_bounds__(kThreads, sizeof(R) == 4 ? 2 : 1)
+template <typename R, typename OUT, bool kStats, int kFT>
+__global__ void __launch_bounds__(32 * kFT, sizeof(R) == 4 ? 16 / kFT : 1)
 stft_db_kernel(const StftParams p) {
     using C = typename Cx<R>::type;
-    constexpr int kXch = Cx<R>::kXch;
+    constexpr int kXch = XchStride<R, kFT>::v;
+    constexpr int kThreads = 32 * kFT;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R* s_win = reinterpret_cast<R*>(smem_raw);                    // [2048]
@@ -327,9 +337,9 @@ stft_db_kernel(const StftParams p) {
         {
             const long long g0 = t0 * hop - kNfft / 2;
             const int span = (nf - 1) * hop + kNfft;
-            if (p.audio_dtype == DAM_F32)      stage_tile<R, float, float>(p, s_stage, row, g0, span, tid);
-            else if (p.audio_dtype == DAM_I16) stage_tile<R, float, short>(p, s_stage, row, g0, span, tid);
-            else                               stage_tile<R, double, double>(p, s_stage, row, g0, span, tid);
+            if (p.audio_dtype == DAM_F32)      stage_tile<R, float, float, kThreads>(p, s_stage, row, g0, span, tid);
+            else if (p.audio_dtype == DAM_I16) stage_tile<R, float, short, kThreads>(p, s_stage, row, g0, span, tid);
+            else                               stage_tile<R, double, double, kThreads>(p, s_stage, row, g0, span, tid);
         }
         __syncthreads();
 
@@ -340,7 +350,7 @@ stft_db_kernel(const StftParams p) {
                 const unsigned nrow = nt / tiles_per_row;
                 const long long nt0 = (long long)(nt - nrow * tiles_per_row) * kFT;
                 const int nnf = (int)((T - nt0) < kFT ? (T - nt0) : kFT);
-                prefetch_tile(p, nrow, nt0 * hop - kNfft / 2, (nnf - 1) * hop + kNfft, elem_bytes, tid);
+                prefetch_tile<kThreads>(p, nrow, nt0 * hop - kNfft / 2, (nnf - 1) * hop + kNfft, elem_bytes, tid);
             }
         }
 
@@ -397,9 +407,9 @@ stft_db_kernel(const StftParams p) {
         }
         __syncthreads();
 
-        // ---- stage 2: thread = (k' = tid / 8 in 0..31, frame = tid % 8)
+        // ---- stage 2: thread = (k' = tid / FT in 0..31, frame = tid % FT)
         {
-            const int kp = tid >> 3, t = tid & 7;
+            const int kp = tid / kFT, t = tid % kFT;
             if (t < nf) {
                 const C* src = s_xch + t * kXch + kp * kRow;
                 const C* tw = s_tw + kp * kRow;
@@ -508,18 +518,23 @@ int get_twiddles(TwiddleTables** out) {
     return DAM_OK;
 }
 
-template <typename R>
+template <typename R, int kFT>
 size_t smem_bytes(int hop) {
     using C = typename Cx<R>::type;
-    const size_t xch = (size_t)kFT * Cx<R>::kXch * sizeof(C);
+    const size_t xch = (size_t)kFT * XchStride<R, kFT>::v * sizeof(C);
     const size_t stage = ((size_t)(kFT - 1) * hop + kNfft) * sizeof(R);
     return kNfft * sizeof(R) + (size_t)kKp * kRow * sizeof(C) + (xch > stage ? xch : stage);
 }
 
-template <typename R, typename OUT, bool kStats>
-int launch(const StftParams& p, cudaStream_t stream) {
-    const size_t smem = smem_bytes<R>(p.hop);
-    auto kern = stft_db_kernel<R, OUT, kStats>;
+template <typename R, typename OUT, bool kStats, int kFT>
+int launch(StftParams p, cudaStream_t stream) {
+    constexpr int kThreads = 32 * kFT;
+    p.tiles_per_row = (p.T + kFT - 1) / kFT;
+    p.n_tiles = p.tiles_per_row * p.n_rows;
+    DAM_CHECK_ARG(p.n_tiles < 0x7fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
+                  (long long)p.n_tiles);
+    const size_t smem = smem_bytes<R, kFT>(p.hop);
+    auto kern = stft_db_kernel<R, OUT, kStats, kFT>;
     static std::mutex mu;
     static bool configured[64] = {};
     static int blocks_per_sm[64] = {};
@@ -586,10 +601,6 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     p.n_inner = (n_inner > 0 && n_inner < n_rows) ? n_inner : 0; p.outer_stride = outer_stride;
     p.input_scale = input_scale; p.row_gain = row_gain; p.window = window;
     p.hop = hop; p.T = 1 + n_samples / hop;
-    p.tiles_per_row = (p.T + kFT - 1) / kFT;
-    p.n_tiles = p.tiles_per_row * n_rows;
-    DAM_CHECK_ARG(p.n_tiles < 0x7fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
-                  (long long)p.n_tiles);
     p.log_scale_d = multiplier * 0.5 * 0.30102999566398119521373889472449302676819;
     p.log_scale = (float)p.log_scale_d;
     p.floor_db_d = amin > 0.0 ? multiplier * log10(amin) : -INFINITY;
@@ -600,9 +611,14 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     const bool st = stats != nullptr;
     if (compute_dtype == DAM_F32) {
         p.twiddle = tw->f32;
-        return st ? launch<float, float, true>(p, s) : launch<float, float, false>(p, s);
+        // frames per tile of the float32 kernel: 8 (two CTAs of 8 warps per SM).  DAM_FT_F32=4 selects
+        // four CTAs of 4 warps -- measured 2-3x SLOWER on B200 (16-byte output segments, 16 KB of L1
+        // left beside 212 KB of shared memory); kept selectable for profiling only.
+        static const int ft = [] { const char* e = getenv("DAM_FT_F32"); return (e && atoi(e) == 4) ? 4 : 8; }();
+        if (ft == 8) return st ? launch<float, float, true, 8>(p, s) : launch<float, float, false, 8>(p, s);
+        return st ? launch<float, float, true, 4>(p, s) : launch<float, float, false, 4>(p, s);
     }
     p.twiddle = tw->f64;
-    if (out_dtype == DAM_F32) return st ? launch<double, float, true>(p, s) : launch<double, float, false>(p, s);
-    return st ? launch<double, double, true>(p, s) : launch<double, double, false>(p, s);
+    if (out_dtype == DAM_F32) return st ? launch<double, float, true, 8>(p, s) : launch<double, float, false, 8>(p, s);
+    return st ? launch<double, double, true, 8>(p, s) : launch<double, double, false, 8>(p, s);
 }
