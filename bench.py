@@ -55,11 +55,18 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.proc, self.lines = index, None, []
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -68,7 +75,7 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -80,7 +87,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for ln in self.lines:
+        # samples taken while the GPU was under this benchmark's load: from the start of the (long)
+        # warm-up to the end of the timed region; the timed region itself can be shorter than one
+        # nvidia-smi sampling period
+        window = [ln for ts, ln in self.lines
+                  if (self.t_begin is None or ts >= self.t_begin) and (self.t_end is None or ts <= self.t_end + 0.05)]
+        for ln in window:
             parts = [p.strip() for p in ln.split(',')]
             if len(parts) < 6:
                 continue
@@ -170,14 +182,24 @@ def run_ours(args):
             dist.all_reduce(stat)
         return res
 
-    for _ in range(max(args.warmup, 3)):
-        res = step()
-    torch.cuda.synchronize()
-
-    # ---- timed region: CUDA events on the launching stream, barrier + synchronize on both sides
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    step()
+    torch.cuda.synchronize()
+    # warm-up: at least W (>= 3) steps and at least ~0.7 s of continuous load, so clocks/power settle and
+    # nvidia-smi (50 ms period) gets samples under this load before the timed region starts
+    sampler.mark_begin()
+    t_w = time.time()
+    n_warm = 0
+    while n_warm < max(args.warmup, 3) or time.time() - t_w < 0.7:
+        res = step()
+        n_warm += 1
+        if n_warm % 8 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+
+    # ---- timed region: CUDA events on the launching stream, barrier + synchronize on both sides
     pipe.timings = {}
     if world > 1:
         dist.barrier()
@@ -190,6 +212,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    sampler.mark_end()
     elapsed_ms = e0.elapsed_time(e1)
     tim = pipe.timings
     pipe.timings = None
@@ -286,7 +309,7 @@ def run_ours(args):
         launches = sum(P.KERNEL_LAUNCHES_PER_BATCH.values()) * args.steps
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': max(args.warmup, 3), 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
+            'warmup': n_warm, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'segments_per_gpu': N_SEG, 'stems': N_STEMS, 'seconds': SECONDS,
                        'hop': HOP, 'chunk_samples': CHUNK_SAMPLES,

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(kBlock) gain_mix_kernel(const GainMixParams p)
     TO* mix = p.mix_out ? reinterpret_cast<TO*>(p.mix_out) + (bt * p.n_channels + c) * n : nullptr;
     double loc_peak = 0.0, loc_sq = 0.0;
     const long long K = p.n_gains, coef = p.interp_coef;
+    const double inv_coef = coef > 0 ? 1.0 / (double)coef : 0.0;
     const double* gains = p.gains + bt * p.n_stems * K;
     TO* stems_out = p.stems_out ? reinterpret_cast<TO*>(p.stems_out) + bt * p.n_stems * p.n_channels * n : nullptr;
 
@@ -111,14 +112,21 @@ __global__ void __launch_bounds__(kBlock) gain_mix_kernel(const GainMixParams p)
         const long long i0 = v * V;
         long long kidx[V];
         {
-            long long k0 = coef > 0 ? i0 / coef : K - 1;
-            if (k0 > K - 1) k0 = K - 1;
+            // k0 = min(i0 / coef, K-1) without a 64-bit integer division: double reciprocal estimate
+            // (exact to within one for i0 < 2^52) followed by an exact correction
+            long long k0 = K - 1;
+            if (coef > 0) {
+                k0 = (long long)((double)i0 * inv_coef);
+                if (k0 * coef > i0) --k0;
+                else if ((k0 + 1) * coef <= i0) ++k0;
+                if (k0 > K - 1) k0 = K - 1;
+            }
             const long long next = (k0 + 1) * coef;          // first sample of gain k0+1
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 long long k = k0;
                 if (k0 < K - 1 && i0 + j >= next) {
-                    k = (i0 + j) / coef;                      // coef < V is legal: recompute
+                    k = (i0 + j) / coef;                      // coef < V is legal: recompute exactly
                     if (k > K - 1) k = K - 1;
                 }
                 kidx[j] = k;
@@ -127,17 +135,34 @@ __global__ void __launch_bounds__(kBlock) gain_mix_kernel(const GainMixParams p)
         TC acc[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = TC(0);
-        for (long long s = 0; s < p.n_stems; ++s) {
-            const Vec<TS, V> x = load_vec<TS, V>(base + s * p.stem_stride + i0);
-            Vec<TO, V> y;
+        const bool one_gain = kidx[0] == kidx[V - 1];
+        constexpr int SU = sizeof(TS) == 4 ? 4 : 2;    // stems whose loads are in flight together
+        for (long long s0 = 0; s0 < p.n_stems; s0 += SU) {
+            Vec<TS, V> x[SU];
+            double g0[SU];
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const TC g = p.zero_mask ? TC(0) : (TC)__ldg(gains + s * K + kidx[j]);
-                const TC prod = (TC)x.v[j] * g;
-                acc[j] = s == 0 ? prod : acc[j] + prod;
-                y.v[j] = (TO)prod;
+            for (int u = 0; u < SU; ++u) {
+                if (s0 + u < p.n_stems) {
+                    x[u] = load_vec<TS, V>(base + (s0 + u) * p.stem_stride + i0);
+                    g0[u] = __ldg(gains + (s0 + u) * K + kidx[0]);
+                }
             }
-            if (stems_out) store_vec<TO, V>(stems_out + (s * p.n_channels + c) * n + i0, y);
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                const long long s = s0 + u;
+                if (s < p.n_stems) {
+                    Vec<TO, V> y;
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        const double gd = one_gain ? g0[u] : __ldg(gains + s * K + kidx[j]);
+                        const TC g = p.zero_mask ? TC(0) : (TC)gd;
+                        const TC prod = (TC)x[u].v[j] * g;
+                        acc[j] = s == 0 ? prod : acc[j] + prod;
+                        y.v[j] = (TO)prod;
+                    }
+                    if (stems_out) store_vec<TO, V>(stems_out + (s * p.n_channels + c) * n + i0, y);
+                }
+            }
         }
         Vec<TO, V> o;
 #pragma unroll
