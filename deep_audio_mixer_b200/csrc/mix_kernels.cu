@@ -94,7 +94,7 @@ struct GainMixParams {
 };
 
 template <typename TS, typename TC, typename TO, int V>
-__global__ void __launch_bounds__(kBlock) gain_mix_kernel(const GainMixParams p) {
+__global__ void __launch_bounds__(kBlock, 3) gain_mix_kernel(const GainMixParams p) {
     __shared__ double s_red[kBlock / 32];
     const long long c = blockIdx.y;
     const long long bt = blockIdx.z;
