@@ -59,6 +59,7 @@ struct StftParams {
     int hop;
     long long T;                  // frames per row
     long long tiles_per_row, n_tiles;
+    int tile_group;               // consecutive tiles a CTA processes back to back
     float log_scale;              // multiplier/2 * log10(2): dB = log_scale * log2(|X|^2)
     float floor_db;               // multiplier * log10(amin), the clamp applied in the dB domain
     double log_scale_d, floor_db_d;
@@ -278,6 +279,147 @@ template <typename R> __device__ __forceinline__ R shfl_xor_r(R v, int m);
 template <> __device__ __forceinline__ float shfl_xor_r<float>(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 template <> __device__ __forceinline__ double shfl_xor_r<double>(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 
+// Per-lane constants of the cross-lane 32-point DFT that turns Y_b[32] into bins 32 + 64 q:
+// pre-twiddle W_64^lane and the decimation-in-frequency twiddles of the distance-16/8/4 stages
+// (1 for the lower lane of a pair).  Lane r ends up holding q = bitrev5(r).
+template <typename R>
+struct NyqConsts {
+    R pre_r, pre_i, wr[3], wi[3];
+    int bin;
+    __device__ __forceinline__ void init(int lane) {
+        double sn, cs;
+        sincospi(-(double)lane / 32.0, &sn, &cs);
+        pre_r = (R)cs; pre_i = (R)sn;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int dist = 16 >> i;
+            const bool upper = (lane & dist) != 0;
+            sincospi(upper ? -(double)((lane & (dist - 1)) * (16 / dist)) / 16.0 : 0.0, &sn, &cs);
+            wr[i] = (R)cs; wi[i] = (R)sn;
+        }
+        bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);
+    }
+};
+
+struct StatAcc {
+    float sum = 0.f, sq = 0.f;
+    double sum_d = 0.0, sq_d = 0.0, cnt = 0.0;
+    __device__ __forceinline__ void add(float db) { sum += db; sq = fmaf(db, db, sq); cnt += 1.0; }
+    __device__ __forceinline__ void fold() { sum_d += sum; sq_d += sq; sum = 0.f; sq = 0.f; }
+    __device__ __forceinline__ void flush(double* stats, int lane) {
+        fold();
+        sum_d = dam_warp_sum(sum_d); sq_d = dam_warp_sum(sq_d); cnt = dam_warp_sum(cnt);
+        if (lane == 0 && cnt > 0.0) {
+            atomicAdd(stats + 0, sum_d);
+            atomicAdd(stats + 1, sq_d);
+            atomicAdd(stats + 2, cnt);
+        }
+    }
+};
+
+// ---- stage 1 of one frame, executed by one warp (lane = b) -------------------------------------
+// x: the lane's 64 windowed samples.  Writes the 32 exchange rows of this frame (dst = row 0 of the
+// frame + lane) and, through the cross-lane DFT, the 16 bins 32 + 64 q straight to global memory
+// (out_frame = &out[row][0][t]).
+template <typename R, typename OUT, bool kStats>
+__device__ __forceinline__ void stage1_frame(R (&x)[64], typename Cx<R>::type* dst, OUT* out_frame, long long T,
+                                             const NyqConsts<R>& nq, const StftParams& p, int lane, StatAcc& st) {
+    using C = typename Cx<R>::type;
+    R sr[32], si[32];
+    dam_rfft64_packed<R>(x, sr, si);
+    {
+        C v; v.x = sr[0]; v.y = R(0);
+        dst[0] = v;                        // row 0: Y[0] (real)
+    }
+#pragma unroll
+    for (int k = 1; k < 32; ++k) {
+        C v; v.x = sr[k]; v.y = si[k];
+        dst[k * kRow] = v;
+    }
+    // k' = 32: Y_b[32] = si[0] is real; bins 32 + 64 q = sum_b Y_b[32] W_64^b W_32^(bq) are a 32-point
+    // DFT ACROSS the lanes of this warp (radix-2 DIF over shuffles; q < 16 are the distinct bins).
+    R vr = si[0] * nq.pre_r, vi = si[0] * nq.pre_i;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int dist = 16 >> i;
+        const R pr = shfl_xor_r<R>(vr, dist), pi = shfl_xor_r<R>(vi, dist);
+        const bool upper = (lane & dist) != 0;
+        const R tr = upper ? pr - vr : vr + pr;
+        const R ti = upper ? pi - vi : vi + pi;
+        if (i < 3) {
+            vr = tr * nq.wr[i] - ti * nq.wi[i];
+            vi = tr * nq.wi[i] + ti * nq.wr[i];
+        } else if (i == 3) {                 // W_4^j: j = 1 on the upper lane of odd pairs -> -i
+            const bool rot = upper && (lane & 1);
+            vr = rot ? ti : tr;
+            vi = rot ? -tr : ti;
+        } else {
+            vr = tr; vi = ti;
+        }
+    }
+    const typename DbOut<R>::type db = DbOut<R>::eval(vr, vi, p);
+    if ((lane & 1) == 0) {
+        out_frame[(long long)nq.bin * T] = (OUT)db;
+        if (kStats) st.add((float)db);
+    }
+}
+
+// ---- stage 2 of one (k', frame) pair, executed by one thread ------------------------------------
+// src: exchange row k' of the frame, tw: twiddle row k', out_frame = &out[row][0][t].
+template <typename R, typename OUT, bool kStats>
+__device__ __forceinline__ void stage2_task(const typename Cx<R>::type* src, const typename Cx<R>::type* tw,
+                                            OUT* out_frame, long long T, int kp, const StftParams& p, StatAcc& st) {
+    using C = typename Cx<R>::type;
+    R sr[32], si[32];
+    if (sizeof(R) == 4) {
+        // two complex values per 128-bit load (rows are 16-byte aligned by construction)
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        const float4* w4 = reinterpret_cast<const float4*>(tw);
+#pragma unroll
+        for (int grp = 0; grp < 4; ++grp) {
+            // four groups of four 128-bit loads each: keeps at most 32 load registers live next to the
+            // 64 result registers (hoisting all 32 loads spills under the 128-register cap)
+            float4 v[4], w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { v[u] = s4[grp * 4 + u]; w[u] = w4[grp * 4 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int b2 = grp * 4 + u;
+                sr[2 * b2] = v[u].x * w[u].x - v[u].y * w[u].y;
+                si[2 * b2] = v[u].x * w[u].y + v[u].y * w[u].x;
+                sr[2 * b2 + 1] = v[u].z * w[u].z - v[u].w * w[u].w;
+                si[2 * b2 + 1] = v[u].z * w[u].w + v[u].w * w[u].z;
+            }
+            asm volatile("" ::: "memory");
+        }
+    } else {
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+            const C v = src[b];
+            const C w = tw[b];
+            sr[b] = v.x * w.x - v.y * w.y;
+            si[b] = v.x * w.y + v.y * w.x;
+        }
+    }
+    dam_cfft32<R>(sr, si);
+
+    // bins k'+64q (q < 16) walk up from row k'; mirrors 2048-k'-64q (q >= 16) walk down from row
+    // 1024-k'.  k' = 0 owns only q <= 16 (bins 0, 64, ..., 1024).
+    const long long stride = 64 * T;
+    OUT* o_lo = out_frame + kp * T;
+    OUT* o_hi = out_frame + (kNfft / 2 - kp) * T;
+    const bool mirror_ok = kp != 0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        const bool valid = q <= 16 ? true : mirror_ok;
+        OUT* o = q < 16 ? o_lo + q * stride : o_hi - (q - 16) * stride;
+        const typename DbOut<R>::type db = DbOut<R>::eval(sr[q], si[q], p);
+        if (valid) *o = (OUT)db;
+        if (kStats && valid) st.add((float)db);
+    }
+    if (kStats) st.fold();
+}
+
 template <typename R, typename OUT, bool kStats, int kFT>
 __global__ void __launch_bounds__(32 * kFT, sizeof(R) == 4 ? 16 / kFT : 1)
 stft_db_kernel(const StftParams p) {
@@ -299,37 +441,30 @@ stft_db_kernel(const StftParams p) {
         const C* tw = reinterpret_cast<const C*>(p.twiddle);
         for (int i = tid; i < kKp * kRow; i += kThreads) s_tw[i] = tw[i];
     }
-
-    // Per-lane constants of the cross-lane 32-point DFT that turns Y_b[32] into bins 32 + 64 q:
-    // pre-twiddle W_64^lane and the decimation-in-frequency twiddles of the distance-16/8/4 stages
-    // (1 for the lower lane of a pair).
-    R nq_pre_r, nq_pre_i, nq_wr[3], nq_wi[3];
-    {
-        double sn, cs;
-        sincospi(-(double)lane / 32.0, &sn, &cs);
-        nq_pre_r = (R)cs; nq_pre_i = (R)sn;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int dist = 16 >> i;
-            const bool upper = (lane & dist) != 0;
-            sincospi(upper ? -(double)((lane & (dist - 1)) * (16 / dist)) / 16.0 : 0.0, &sn, &cs);
-            nq_wr[i] = (R)cs; nq_wi[i] = (R)sn;
-        }
-    }
-    const int nq_bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);     // lane r ends up holding q = bitrev5(r)
+    NyqConsts<R> nq;
+    nq.init(lane);
 
     const int hop = p.hop;
     const long long T = p.T;
     const int elem_bytes = p.audio_dtype == DAM_I16 ? 2 : (p.audio_dtype == DAM_F32 ? 4 : 8);
     const unsigned tiles_per_row = (unsigned)p.tiles_per_row, n_tiles = (unsigned)p.n_tiles;
-    float st_sum = 0.f, st_sq = 0.f;
-    double st_sum_d = 0.0, st_sq_d = 0.0, st_cnt = 0.0;
+    StatAcc st;
 
-    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // Tiles are dealt round-robin in GROUPS of p.tile_group consecutive tiles.  At any moment the resident
+    // CTAs work on adjacent groups, so their 32-byte output row segments complete whole DRAM sectors /
+    // lines in L2 together and their input halos hit in L2; inside a group the CTA itself completes the
+    // sectors that straddle two tiles (rows are T*4 bytes apart, not a multiple of 32 for T = 87 / 173).
+    // (A fully contiguous tile range per CTA was measured 5-40 % slower: every CTA then scatters 1025
+    // isolated 32-byte segments per tile with nobody writing their neighbours.)
+    const unsigned G = (unsigned)p.tile_group;
+    const unsigned n_groups = (n_tiles + G - 1) / G;
+    for (unsigned grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
+    for (unsigned tile = grp * G; tile < (grp + 1) * G && tile < n_tiles; ++tile) {
         const unsigned urow = tile / tiles_per_row;
         const long long row = urow;
         const long long t0 = (long long)(tile - urow * tiles_per_row) * kFT;
         const int nf = (int)((T - t0) < kFT ? (T - t0) : kFT);
+        OUT* out_row = reinterpret_cast<OUT*>(p.out) + row * p.out_row_stride + t0;
 
         __syncthreads();     // previous tile's stage 2 has finished reading s_xch (and tables are loaded)
 
@@ -345,7 +480,7 @@ stft_db_kernel(const StftParams p) {
 
         // pull the next tile's samples towards L2 while this one is transformed
         {
-            const unsigned nt = tile + gridDim.x;
+            const unsigned nt = (tile + 1 < (grp + 1) * G) ? tile + 1 : (grp + gridDim.x) * G;
             if (nt < n_tiles) {
                 const unsigned nrow = nt / tiles_per_row;
                 const long long nt0 = (long long)(nt - nrow * tiles_per_row) * kFT;
@@ -355,7 +490,6 @@ stft_db_kernel(const StftParams p) {
         }
 
         // ---- stage 1: warp = frame, lane = b
-        R sr[32], si[32];
         {
             R x[64];
             if (warp < nf) {
@@ -364,106 +498,174 @@ stft_db_kernel(const StftParams p) {
                 for (int a = 0; a < 64; ++a) x[a] = f[32 * a] * s_win[32 * a + lane];
             }
             __syncthreads();     // all frames are in registers; s_stage may now be overwritten
-            if (warp < nf) {
-                dam_rfft64_packed<R>(x, sr, si);
-                C* dst = s_xch + warp * kXch + lane;
-                {
-                    C v; v.x = sr[0]; v.y = R(0);
-                    dst[0] = v;                        // row 0: Y[0] (real)
-                }
-#pragma unroll
-                for (int k = 1; k < 32; ++k) {
-                    C v; v.x = sr[k]; v.y = si[k];
-                    dst[k * kRow] = v;
-                }
-                // k' = 32: Y_b[32] = si[0] is real; bins 32 + 64 q = sum_b Y_b[32] W_64^b W_32^(bq) are a
-                // 32-point DFT ACROSS the lanes of this warp (radix-2 DIF over shuffles, output lane r
-                // holds q = bitrev5(r); q < 16 are the distinct bins).
-                R vr = si[0] * nq_pre_r, vi = si[0] * nq_pre_i;
-#pragma unroll
-                for (int i = 0; i < 5; ++i) {
-                    const int dist = 16 >> i;
-                    const R pr = shfl_xor_r<R>(vr, dist), pi = shfl_xor_r<R>(vi, dist);
-                    const bool upper = (lane & dist) != 0;
-                    const R tr = upper ? pr - vr : vr + pr;
-                    const R ti = upper ? pi - vi : vi + pi;
-                    if (i < 3) {
-                        vr = tr * nq_wr[i] - ti * nq_wi[i];
-                        vi = tr * nq_wi[i] + ti * nq_wr[i];
-                    } else if (i == 3) {                 // W_4^j: j = 1 on the upper lane of odd pairs -> -i
-                        const bool rot = upper && (lane & 1);
-                        vr = rot ? ti : tr;
-                        vi = rot ? -tr : ti;
-                    } else {
-                        vr = tr; vi = ti;
-                    }
-                }
-                const typename DbOut<R>::type db = DbOut<R>::eval(vr, vi, p);
-                if ((lane & 1) == 0) {
-                    reinterpret_cast<OUT*>(p.out)[row * p.out_row_stride + nq_bin * T + t0 + warp] = (OUT)db;
-                    if (kStats) { st_sum_d += (double)db; st_sq_d += (double)db * (double)db; st_cnt += 1.0; }
-                }
-            }
+            if (warp < nf)
+                stage1_frame<R, OUT, kStats>(x, s_xch + warp * kXch + lane, out_row + warp, T, nq, p, lane, st);
         }
         __syncthreads();
 
         // ---- stage 2: thread = (k' = tid / FT in 0..31, frame = tid % FT)
         {
             const int kp = tid / kFT, t = tid % kFT;
+            if (t < nf)
+                stage2_task<R, OUT, kStats>(s_xch + t * kXch + kp * kRow, s_tw + kp * kRow, out_row + t, T, kp, p, st);
+        }
+    }
+    if (kStats) st.flush(p.stats, lane);
+}
+
+// ==========================================================================================
+// Warp-specialised, software-pipelined variant (float32, hop <= 1024): ONE CTA of 16 warps per SM.
+//   warps 12..15  loaders : stage tile i+1 (global -> prologue -> shared) while tile i is transformed;
+//                           their memory stalls no longer hold up any transform warp
+//   warps  0..5   stage 1 : frame slots of the CTA's tile stream, round-robin
+//   warps  6..11  stage 2 : (4 k' x 8 frames) tasks of the tile stream, round-robin
+// (one loader + three transform warps per SM sub-partition).  The staging buffer and the exchange
+// buffer are double-buffered and handed over with mbarriers (full/empty per buffer), so the three
+// roles run concurrently on different tiles instead of in barrier-separated phases.
+constexpr int kPipeThreads = 512;
+constexpr int kPipeS1 = 6, kPipeS2 = 6, kPipeLd = 4;
+constexpr int kPipeFT = 8;
+constexpr int kPipeMaxHop = 1024;
+constexpr int kPipeStageElems = (kPipeFT - 1) * kPipeMaxHop + kNfft;
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+constexpr size_t pipe_smem_bytes() {
+    return kNfft * sizeof(float) + (size_t)kKp * kRow * sizeof(float2) +
+           2 * (size_t)kPipeFT * XchStride<float, 8>::v * sizeof(float2) + 2 * (size_t)kPipeStageElems * sizeof(float) +
+           8 * sizeof(unsigned long long);
+}
+
+template <bool kStats>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+stft_db_pipe_kernel(const StftParams p) {
+    using R = float;
+    using OUT = float;
+    using C = float2;
+    constexpr int kXch = XchStride<float, 8>::v;
+    constexpr int kFT = kPipeFT;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    R* s_win = reinterpret_cast<R*>(smem_raw);                    // [2048]
+    C* s_tw = reinterpret_cast<C*>(s_win + kNfft);                // [33][34]
+    C* s_xch = s_tw + kKp * kRow;                                 // [2][kFT][kXch]
+    R* s_stage = reinterpret_cast<R*>(s_xch + 2 * kFT * kXch);    // [2][kPipeStageElems]
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_stage + 2 * kPipeStageElems);
+    unsigned long long* full_stage = bars;        // [2] loaders -> stage 1
+    unsigned long long* empty_stage = bars + 2;   // [2] stage 1 -> loaders
+    unsigned long long* full_xch = bars + 4;      // [2] stage 1 -> stage 2
+    unsigned long long* empty_xch = bars + 6;     // [2] stage 2 -> stage 1
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    for (int i = tid; i < kNfft; i += kPipeThreads) s_win[i] = __ldg(p.window + i);
+    {
+        const C* tw = reinterpret_cast<const C*>(p.twiddle);
+        for (int i = tid; i < kKp * kRow; i += kPipeThreads) s_tw[i] = tw[i];
+    }
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(full_stage + b, kPipeLd);     // one arrival per loader warp
+            mbar_init(empty_stage + b, kFT);        // one per frame slot
+            mbar_init(full_xch + b, kFT);           // one per frame slot
+            mbar_init(empty_xch + b, kFT);          // one per stage-2 task (8 per tile)
+        }
+    }
+    __syncthreads();
+
+    const int hop = p.hop;
+    const long long T = p.T;
+    const unsigned tiles_per_row = (unsigned)p.tiles_per_row, n_tiles = (unsigned)p.n_tiles;
+    const unsigned n_local = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    StatAcc st;
+
+    if (warp >= kPipeS1 + kPipeS2) {
+        // ------------------------------------------------------------------ loaders
+        const int ltid = tid - (kPipeS1 + kPipeS2) * 32;
+        for (unsigned i = 0; i < n_local; ++i) {
+            const unsigned tile = blockIdx.x + i * gridDim.x;
+            const unsigned urow = tile / tiles_per_row;
+            const long long t0 = (long long)(tile - urow * tiles_per_row) * kFT;
+            const int nf = (int)((T - t0) < kFT ? (T - t0) : kFT);
+            const int b = i & 1;
+            mbar_wait(empty_stage + b, ((i >> 1) & 1) ^ 1);
+            R* dst = s_stage + b * kPipeStageElems;
+            const long long g0 = t0 * hop - kNfft / 2;
+            const int span = (nf - 1) * hop + kNfft;
+            if (p.audio_dtype == DAM_F32)      stage_tile<R, float, float, kPipeLd * 32>(p, dst, urow, g0, span, ltid);
+            else if (p.audio_dtype == DAM_I16) stage_tile<R, float, short, kPipeLd * 32>(p, dst, urow, g0, span, ltid);
+            else                               stage_tile<R, double, double, kPipeLd * 32>(p, dst, urow, g0, span, ltid);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_stage + b);
+        }
+    } else if (warp < kPipeS1) {
+        // ------------------------------------------------------------------ stage 1
+        NyqConsts<R> nq;
+        nq.init(lane);
+        for (unsigned g = warp; g < n_local * kFT; g += kPipeS1) {
+            const unsigned i = g >> 3;
+            const int t = g & 7;
+            const unsigned tile = blockIdx.x + i * gridDim.x;
+            const unsigned urow = tile / tiles_per_row;
+            const long long t0 = (long long)(tile - urow * tiles_per_row) * kFT;
+            const int nf = (int)((T - t0) < kFT ? (T - t0) : kFT);
+            const int b = i & 1;
+            const unsigned ph = (i >> 1) & 1;
+            R x[64];
+            mbar_wait(full_stage + b, ph);
             if (t < nf) {
-                const C* src = s_xch + t * kXch + kp * kRow;
-                const C* tw = s_tw + kp * kRow;
-                if (sizeof(R) == 4) {
-                    // two complex values per 128-bit load (rows are 16-byte aligned by construction)
-                    const float4* s4 = reinterpret_cast<const float4*>(src);
-                    const float4* w4 = reinterpret_cast<const float4*>(tw);
+                const R* f = s_stage + b * kPipeStageElems + t * hop + lane;
 #pragma unroll
-                    for (int b2 = 0; b2 < 16; ++b2) {
-                        const float4 v = s4[b2];
-                        const float4 w = w4[b2];
-                        sr[2 * b2] = v.x * w.x - v.y * w.y;
-                        si[2 * b2] = v.x * w.y + v.y * w.x;
-                        sr[2 * b2 + 1] = v.z * w.z - v.w * w.w;
-                        si[2 * b2 + 1] = v.z * w.w + v.w * w.z;
-                    }
-                } else {
-#pragma unroll
-                    for (int b = 0; b < 32; ++b) {
-                        const C v = src[b];
-                        const C w = tw[b];
-                        sr[b] = v.x * w.x - v.y * w.y;
-                        si[b] = v.x * w.y + v.y * w.x;
-                    }
-                }
-                dam_cfft32<R>(sr, si);
-
-                // bins k'+64q (q < 16) walk up from row k'; mirrors 2048-k'-64q (q >= 16) walk down
-                // from row 1024-k'.  k' = 0 owns only q <= 16 (bins 0, 64, ..., 1024).
-                const long long stride = 64 * T;
-                OUT* o_lo = reinterpret_cast<OUT*>(p.out) + row * p.out_row_stride + kp * T + t0 + t;
-                OUT* o_hi = reinterpret_cast<OUT*>(p.out) + row * p.out_row_stride + (kNfft / 2 - kp) * T + t0 + t;
-                const bool mirror_ok = kp != 0;
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const bool valid = q <= 16 ? true : mirror_ok;
-                    OUT* o = q < 16 ? o_lo + q * stride : o_hi - (q - 16) * stride;
-                    const typename DbOut<R>::type db = DbOut<R>::eval(sr[q], si[q], p);
-                    if (valid) *o = (OUT)db;
-                    if (kStats && valid) { st_sum += (float)db; st_sq = fmaf((float)db, (float)db, st_sq); st_cnt += 1.0; }
-                }
-                if (kStats) { st_sum_d += st_sum; st_sq_d += st_sq; st_sum = 0.f; st_sq = 0.f; }
+                for (int a = 0; a < 64; ++a) x[a] = f[32 * a] * s_win[32 * a + lane];
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_stage + b);      // this slot's samples are in registers
+            mbar_wait(empty_xch + b, ph ^ 1);                 // stage 2 is done with tile i-2
+            if (t < nf) {
+                OUT* out_frame = reinterpret_cast<OUT*>(p.out) + (long long)urow * p.out_row_stride + t0 + t;
+                stage1_frame<R, OUT, kStats>(x, s_xch + (b * kFT + t) * kXch + lane, out_frame, T, nq, p, lane, st);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_xch + b);
+        }
+    } else {
+        // ------------------------------------------------------------------ stage 2
+        const int v = warp - kPipeS1;
+        for (unsigned g = v; g < n_local * 8; g += kPipeS2) {
+            const unsigned i = g >> 3;
+            const int j = g & 7;                                // k' group: k' = 4j .. 4j+3
+            const unsigned tile = blockIdx.x + i * gridDim.x;
+            const unsigned urow = tile / tiles_per_row;
+            const long long t0 = (long long)(tile - urow * tiles_per_row) * kFT;
+            const int nf = (int)((T - t0) < kFT ? (T - t0) : kFT);
+            const int b = i & 1;
+            mbar_wait(full_xch + b, (i >> 1) & 1);
+            const int kp = j * 4 + (lane >> 3), t = lane & 7;
+            if (t < nf) {
+                OUT* out_frame = reinterpret_cast<OUT*>(p.out) + (long long)urow * p.out_row_stride + t0 + t;
+                stage2_task<R, OUT, kStats>(s_xch + (b * kFT + t) * kXch + kp * kRow, s_tw + kp * kRow, out_frame, T,
+                                            kp, p, st);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_xch + b);
         }
     }
-
-    if (kStats) {
-        st_sum_d = dam_warp_sum(st_sum_d); st_sq_d = dam_warp_sum(st_sq_d); st_cnt = dam_warp_sum(st_cnt);
-        if (lane == 0 && st_cnt > 0.0) {
-            atomicAdd(p.stats + 0, st_sum_d);
-            atomicAdd(p.stats + 1, st_sq_d);
-            atomicAdd(p.stats + 2, st_cnt);
-        }
-    }
+    if (kStats) st.flush(p.stats, lane);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -533,6 +735,8 @@ int launch(StftParams p, cudaStream_t stream) {
     p.n_tiles = p.tiles_per_row * p.n_rows;
     DAM_CHECK_ARG(p.n_tiles < 0x7fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
                   (long long)p.n_tiles);
+    static const int group_env = [] { const char* e = getenv("DAM_K1_GROUP"); return e ? atoi(e) : 0; }();
+    p.tile_group = group_env > 0 ? group_env : 1;
     const size_t smem = smem_bytes<R, kFT>(p.hop);
     auto kern = stft_db_kernel<R, OUT, kStats, kFT>;
     static std::mutex mu;
@@ -554,6 +758,31 @@ int launch(StftParams p, cudaStream_t stream) {
     long long grid = (long long)dam_sm_count() * occ;
     if (grid > p.n_tiles) grid = p.n_tiles;
     kern<<<(unsigned)grid, kThreads, smem, stream>>>(p);
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
+
+template <bool kStats>
+int launch_pipe(StftParams p, cudaStream_t stream) {
+    p.tiles_per_row = (p.T + kPipeFT - 1) / kPipeFT;
+    p.n_tiles = p.tiles_per_row * p.n_rows;
+    DAM_CHECK_ARG(p.n_tiles < 0x0fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
+                  (long long)p.n_tiles);
+    auto kern = stft_db_pipe_kernel<kStats>;
+    static std::mutex mu;
+    static bool configured[64] = {};
+    int dev = 0;
+    DAM_CHECK_CUDA(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!configured[dev]) {
+            DAM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem_bytes()));
+            configured[dev] = true;
+        }
+    }
+    long long grid = dam_sm_count();
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    kern<<<(unsigned)grid, kPipeThreads, pipe_smem_bytes(), stream>>>(p);
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }
@@ -615,6 +844,12 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
         // four CTAs of 4 warps -- measured 2-3x SLOWER on B200 (16-byte output segments, 16 KB of L1
         // left beside 212 KB of shared memory); kept selectable for profiling only.
         static const int ft = [] { const char* e = getenv("DAM_FT_F32"); return (e && atoi(e) == 4) ? 4 : 8; }();
+        // DAM_K1_PIPE=1 selects the warp-specialised mbarrier pipeline (hop <= 1024).  Measured on B200 it
+        // is 10-35 % SLOWER than the phase-structured kernel: with tile-granular double buffering its 6+6
+        // transform warps spend most of their time in mbarrier waits on each other (profiles/), so the
+        // phase kernel stays the default.
+        static const bool use_pipe = [] { const char* e = getenv("DAM_K1_PIPE"); return e && atoi(e) == 1; }();
+        if (use_pipe && hop <= kPipeMaxHop) return st ? launch_pipe<true>(p, s) : launch_pipe<false>(p, s);
         if (ft == 8) return st ? launch<float, float, true, 8>(p, s) : launch<float, float, false, 8>(p, s);
         return st ? launch<float, float, true, 4>(p, s) : launch<float, float, false, 4>(p, s);
     }
