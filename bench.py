@@ -185,49 +185,88 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    step()
+    for _ in range(2):
+        res = step()
     torch.cuda.synchronize()
+
+    # The step is ~11 of our kernel launches plus a few tiny torch ops and takes ~2.4 ms on the device,
+    # about what Python needs to enqueue it, so the whole step is captured ONCE in a CUDA graph and the
+    # timed region replays it (single-GPU; with NCCL in the step the eager path is kept).
+    side = torch.cuda.Stream(dev)
+    graphs = {}
+
+    def capture(fn):
+        g = torch.cuda.CUDAGraph()
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            fn()                           # warm on the capture stream
+            side.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                out = fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        return g, out
+
+    use_graph = world == 1 and os.environ.get('DAM_BENCH_GRAPH', '1') != '0'
+    if use_graph:
+        g_step, res = capture(lambda: pipe.run(raw, m, feats_out=feats_buf))
+        run_step = g_step.replay
+    else:
+        run_step = step
+
     # warm-up: at least W (>= 3) steps and at least ~0.7 s of continuous load, so clocks/power settle and
     # nvidia-smi (50 ms period) gets samples under this load before the timed region starts
     sampler.mark_begin()
     t_w = time.time()
     n_warm = 0
     while n_warm < max(args.warmup, 3) or time.time() - t_w < 0.7:
-        res = step()
+        run_step()
         n_warm += 1
         if n_warm % 8 == 0:
             torch.cuda.synchronize()
     torch.cuda.synchronize()
 
     # ---- timed region: CUDA events on the launching stream, barrier + synchronize on both sides
-    pipe.timings = {}
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        res = step()
+        run_step()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     sampler.mark_end()
     elapsed_ms = e0.elapsed_time(e1)
-    tim = pipe.timings
-    pipe.timings = None
     t_ms = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t_ms.item())
     clocks = sampler.stop() if rank == 0 else None
 
-    def stage_ms(a, b):
-        return float(np.mean([x.elapsed_time(y) for x, y in zip(tim[a], tim[b])]))
+    # ---- per-stage device time: each stage captured in its own graph and replayed back to back
+    # (CUDA events on the launching stream around 10 replays; no host gaps inside a graph)
+    def time_graph(fn, reps=10):
+        g, out = capture(fn)
+        for _ in range(3):
+            g.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps, out
 
-    stages = {'bus_sum': stage_ms('bus0', 'bus1'), 'stft_db': stage_ms('bus1', 'stft1'),
-              'gain_mix': stage_ms('gain0', 'mix1'), 'loudness': stage_ms('mix1', 'loud1'),
-              'scale': stage_ms('loud1', 'scale1')}
+    stages = {}
+    stages['bus_sum'], buses = time_graph(lambda: pipe.stage_bus(raw))
+    stages['stft_db'], _ = time_graph(lambda: pipe.features(buses, feats_buf))
+    gains = pipe.stage_gains(m, N_SEG, nc)
+    stages['gain_mix'], mixres = time_graph(lambda: pipe.stage_mix(buses, gains))
+    stages['loudness'], lufs = time_graph(lambda: pipe.stage_loudness(mixres['mix']))
+    stages['scale'], _ = time_graph(lambda: pipe.stage_normalise(mixres['mix'], lufs))
+    del buses, mixres
     stem_s_per_step = N_SEG * N_STEMS * SECONDS
     value = world * stem_s_per_step * args.steps / (elapsed_ms * 1e-3)
 
@@ -309,7 +348,7 @@ def run_ours(args):
         launches = sum(P.KERNEL_LAUNCHES_PER_BATCH.values()) * args.steps
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': n_warm, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
+            'warmup': n_warm, 'cuda_graph': use_graph, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'segments_per_gpu': N_SEG, 'stems': N_STEMS, 'seconds': SECONDS,
                        'hop': HOP, 'chunk_samples': CHUNK_SAMPLES,

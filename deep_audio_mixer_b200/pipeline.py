@@ -59,6 +59,32 @@ class SegmentBatchPipeline:
             e.record()
             self.timings.setdefault(name, []).append(e)
 
+    # ---- the five stages, separately callable (bench.py captures each in its own CUDA graph) --------
+    def stage_bus(self, raw: torch.Tensor) -> torch.Tensor:
+        """raw [B, S, C, N] -> buses [B, 4, C, N] (kernel N2)."""
+        return mixing.bus_sum(raw, self.group, 4, batch_dims=1)
+
+    def stage_gains(self, m: torch.Tensor, B: int, nc: int) -> torch.Tensor:
+        """head outputs m [B*nc, 4] -> amplitude gains [B, 4, nc]: 10**(0.5 m) in float32 like the
+        reference (data/dataset_utils.py:46-50), widened to float64 for the mask."""
+        return torch.pow(10.0, 0.5 * m.float()).double().reshape(B, nc, 4).permute(0, 2, 1).contiguous()
+
+    def stage_mix(self, buses: torch.Tensor, gains: torch.Tensor):
+        """zero-order-hold masks, per-bus products, stem sum, peak and sum of squares (kernel K2)."""
+        N = buses.shape[-1]
+        return mixing.gain_mix(buses, gains, interp_coef=int(N / gains.shape[-1]), compute_dtype=torch.float64,
+                               want_mix=True, want_stats=True)
+
+    def stage_loudness(self, mix: torch.Tensor) -> torch.Tensor:
+        """BS.1770 integrated loudness of every mix, on the device (kernel K4 + gating)."""
+        return self.meter.integrated_loudness_device(mix)
+
+    def stage_normalise(self, mix: torch.Tensor, lufs: torch.Tensor) -> torch.Tensor:
+        """x * 10**((target - L)/20) (kernel K5; the factors never leave the device)."""
+        B, C, N = mix.shape
+        factor = torch.pow(10.0, (self.target - lufs) / 20.0)
+        return mixing.scale_rows(mix.reshape(B, C * N), factor).reshape(B, C, N)
+
     def run(self, raw: torch.Tensor, m: torch.Tensor = None, model=None, feats_out: torch.Tensor = None):
         """raw [B, S, C, N] float32 on the device.  ``m`` [B*n_chunks, 4] are the CNN head outputs; if
         None they are computed with ``model`` from the features.  Returns a dict with the normalised
@@ -66,7 +92,7 @@ class SegmentBatchPipeline:
         B, S, C, N = raw.shape
         nc = self.n_chunks(N)
         self._ev('bus0')
-        buses = mixing.bus_sum(raw, self.group, 4, batch_dims=1)                   # [B, 4, C, N]
+        buses = self.stage_bus(raw)                                                 # [B, 4, C, N]
         self._ev('bus1')
         feats = self.features(buses, feats_out)
         self._ev('stft1')
@@ -74,16 +100,13 @@ class SegmentBatchPipeline:
             with torch.no_grad():
                 _, ms = model(feats)
             m = torch.cat([v.reshape(-1, 1) for v in ms], dim=1)
-        # gain = 10**(0.5 m) in float32 like the reference, one per (segment, bus, chunk)
-        gains = torch.pow(10.0, 0.5 * m.float()).double().reshape(B, nc, 4).permute(0, 2, 1).contiguous()
+        gains = self.stage_gains(m, B, nc)
         self._ev('gain0')
-        res = mixing.gain_mix(buses, gains, interp_coef=int(N / nc), compute_dtype=torch.float64,
-                              want_mix=True, want_stats=True)
+        res = self.stage_mix(buses, gains)
         self._ev('mix1')
-        lufs = self.meter.integrated_loudness_device(res['mix'])                    # [B] on the device
+        lufs = self.stage_loudness(res['mix'])                                      # [B] on the device
         self._ev('loud1')
-        factor = torch.pow(10.0, (self.target - lufs) / 20.0)
-        norm = mixing.scale_rows(res['mix'].reshape(B, C * N), factor).reshape(B, C, N)
+        norm = self.stage_normalise(res['mix'], lufs)
         self._ev('scale1')
         return dict(mix=norm, lufs=lufs, peak=res['peak'], sumsq=res['sumsq'], features=feats, m=m)
 
