@@ -218,7 +218,11 @@ def run_ours(args):
     sampler.mark_begin()
     t_w = time.time()
     n_warm = 0
-    while n_warm < max(args.warmup, 3) or time.time() - t_w < 0.7:
+    # (with several ranks the step contains a collective, so every rank must run the SAME number of
+    # warm-up steps: a fixed count instead of a time-based one)
+    fixed_warm = max(args.warmup, 3) + 200 if world > 1 else None
+    while (n_warm < fixed_warm) if fixed_warm is not None else \
+            (n_warm < max(args.warmup, 3) or time.time() - t_w < 0.7):
         run_step()
         n_warm += 1
         if n_warm % 8 == 0:
