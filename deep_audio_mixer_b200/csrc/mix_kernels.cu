@@ -233,6 +233,37 @@ __global__ void __launch_bounds__(kBlock) bus_sum_kernel(const BusParams p) {
     }
 }
 
+
+// PCM16 ingest form of the bus sum: int16 stems are converted with x * scale (1/32768 reproduces what
+// librosa.load yields, exactly) and the buses are accumulated and written in float32, so 16-bit audio
+// crosses PCIe and HBM at half the bytes.
+template <int V>
+__global__ void __launch_bounds__(kBlock) bus_sum_i16_kernel(const BusParams p, float scale) {
+    const long long nvec = (p.n_elems + V - 1) / V;
+    const short* in = reinterpret_cast<const short*>(p.stems) + (long long)blockIdx.y * p.batch_stride;
+    float* outp = reinterpret_cast<float*>(p.out) + (long long)blockIdx.y * p.n_bus * p.n_elems;
+    for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
+        const long long i0 = v * V;
+        for (int g = 0; g < p.n_bus; ++g) {
+            float acc[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] = 0.f;
+            for (long long s = 0; s < p.n_stems; ++s) {
+                if (p.group[s] != g) continue;
+                const Vec<short, V> x = load_vec<short, V>(in + s * p.stem_stride + i0);
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc[j] += (float)x.v[j] * scale;
+            }
+            if (V == 8) {
+                reinterpret_cast<float4*>(outp + (long long)g * p.n_elems + i0)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                reinterpret_cast<float4*>(outp + (long long)g * p.n_elems + i0)[1] = make_float4(acc[4 % V], acc[5 % V], acc[6 % V], acc[7 % V]);
+            } else {
+                outp[(long long)g * p.n_elems + i0] = acc[0];
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K3 feature-domain gain-weighted sum and gradients (float32)
 constexpr int kMaxS = 8;
@@ -438,10 +469,10 @@ extern "C" int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_batch,
 
 extern "C" int dam_bus_sum(const void* stems, int dtype, int64_t n_batch, int64_t batch_stride,
                            int64_t n_stems, int64_t n_elems, int64_t stem_stride,
-                           const int32_t* group_host, int n_bus, void* out, void* stream) {
+                           const int32_t* group_host, int n_bus, double input_scale, void* out, void* stream) {
     dam_clear_error();
     DAM_CHECK_ARG(stems && group_host && out, "null pointer argument");
-    DAM_CHECK_ARG(dtype == DAM_F32 || dtype == DAM_F64, "dtype must be F32 or F64");
+    DAM_CHECK_ARG(dtype == DAM_F32 || dtype == DAM_F64 || dtype == DAM_I16, "dtype must be I16, F32 or F64");
     DAM_CHECK_ARG(n_stems >= 1 && n_stems <= 64, "n_stems must be in [1, 64]");
     DAM_CHECK_ARG(n_bus >= 1 && n_bus <= 64 && n_elems >= 0, "bad sizes");
     DAM_CHECK_ARG(n_batch >= 0 && n_batch <= 65535, "n_batch must be in [0, 65535]");
@@ -455,11 +486,20 @@ extern "C" int dam_bus_sum(const void* stems, int dtype, int64_t n_batch, int64_
         DAM_CHECK_ARG(group_host[s] >= -1 && group_host[s] < n_bus, "group[%lld]=%d out of range", (long long)s, group_host[s]);
         p.group[s] = group_host[s];
     }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == DAM_I16) {
+        const bool v8 = (n_elems % 8 == 0) && (stem_stride % 8 == 0) && (batch_stride % 8 == 0) &&
+                        (reinterpret_cast<uintptr_t>(stems) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+        const float scale = (float)input_scale;
+        if (v8) bus_sum_i16_kernel<8><<<dim3(grid_for((n_elems + 7) / 8, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p, scale);
+        else bus_sum_i16_kernel<1><<<dim3(grid_for(n_elems, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p, scale);
+        DAM_CHECK_CUDA(cudaGetLastError());
+        return DAM_OK;
+    }
     const size_t es = dtype == DAM_F32 ? 4 : 8;
     const bool vec_ok = (n_elems % 4 == 0) && (stem_stride % 4 == 0) && (batch_stride % 4 == 0) &&
                         (reinterpret_cast<uintptr_t>(stems) % (4 * es) == 0) &&
                         (reinterpret_cast<uintptr_t>(out) % (4 * es) == 0);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (dtype == DAM_F32) {
         if (vec_ok) bus_sum_kernel<float, 4><<<dim3(grid_for((n_elems + 3) / 4, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p);
         else bus_sum_kernel<float, 1><<<dim3(grid_for(n_elems, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p);

@@ -65,10 +65,12 @@ def stem_sum(stems: torch.Tensor, out_dtype=None) -> torch.Tensor:
                     out_dtype=out_dtype or stems.dtype)['mix']
 
 
-def bus_sum(stems: torch.Tensor, group, n_bus: int = 4, batch_dims: int = 0) -> torch.Tensor:
+def bus_sum(stems: torch.Tensor, group, n_bus: int = 4, batch_dims: int = 0,
+            input_scale: float = 1.0 / 32768.0) -> torch.Tensor:
     """S raw stems -> n_bus buses, summed in stem order in the audio dtype (kernel N2;
     data/medleydb_data_surgery.ipynb:305-332).  stems [S, ...] (or [B, S, ...] with batch_dims=1);
-    group[s] in [0, n_bus) or -1 (dropped)."""
+    group[s] in [0, n_bus) or -1 (dropped).  int16 stems (PCM16) are converted with x * input_scale and
+    summed in float32."""
     _check_cuda(stems, 'stems')
     if batch_dims:
         B, S = stems.shape[0], stems.shape[1]
@@ -80,12 +82,13 @@ def bus_sum(stems: torch.Tensor, group, n_bus: int = 4, batch_dims: int = 0) -> 
         tail = tuple(stems.shape[1:])
     if flat.stride(2) != 1:
         flat = flat.contiguous()
-    out = torch.empty(((B,) if batch_dims else ()) + (n_bus,) + tail, dtype=stems.dtype, device=stems.device)
+    out_dtype = torch.float32 if stems.dtype == torch.int16 else stems.dtype
+    out = torch.empty(((B,) if batch_dims else ()) + (n_bus,) + tail, dtype=out_dtype, device=stems.device)
     grp = (ctypes.c_int32 * S)(*[int(v) for v in group])
     with torch.cuda.device(stems.device):
         rc = _lib.lib().dam_bus_sum(_lib.ptr(flat), _lib.dtype_code(stems.dtype), B, flat.stride(0) if B > 1 else 0,
-                                    S, flat.shape[2], flat.stride(1), grp, n_bus, _lib.ptr(out),
-                                    _lib.stream_ptr())
+                                    S, flat.shape[2], flat.stride(1), grp, n_bus, float(input_scale),
+                                    _lib.ptr(out), _lib.stream_ptr())
     _lib.check(rc, 'dam_bus_sum')
     return out
 

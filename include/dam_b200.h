@@ -125,10 +125,13 @@ int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_batch, int64_t ba
  *   stems: n_batch songs of [n_stems, n_elems] (stems stem_stride apart, songs batch_stride apart),
  *   group[n_stems] (host pointer; bus index, or -1 to drop a stem),
  *   out [n_batch, n_bus, n_elems] contiguous, same dtype (F32 or F64).
+ *   dtype I16 is the PCM16 ingest form: samples are converted with x * input_scale (1/32768
+ *   reproduces librosa.load exactly; N1 of SURVEY 8f) and the buses are float32; input_scale is
+ *   ignored for F32 / F64.
  */
 int dam_bus_sum(const void* stems, int dtype, int64_t n_batch, int64_t batch_stride,
                 int64_t n_stems, int64_t n_elems, int64_t stem_stride,
-                const int32_t* group_host, int n_bus, void* out, void* stream);
+                const int32_t* group_host, int n_bus, double input_scale, void* out, void* stream);
 
 /*
  * K3: the models' tail  masked[b] = sum_i m[b,i] * x[b,i]  (dB maps times raw head outputs) and

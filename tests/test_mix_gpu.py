@@ -88,6 +88,15 @@ def test_bus_sum(cuda_device):
     grp = [0, 1, 1, 2, 3, 3, 3, -1]
     out = mixing.bus_sum(cuda(st), grp, 4)
     assert np.array_equal(out.cpu().numpy(), OM.bus_sum(st, grp, 4))
+    # PCM16 ingest: x/32768 in float32 (what librosa.load yields), then the same float32 bus sums
+    q = synthetic.quantise_int16(st * 0.2)
+    as_f32 = q.astype(np.float32) * np.float32(1.0 / 32768.0)
+    out16 = mixing.bus_sum(cuda(q), grp, 4)
+    assert out16.dtype == torch.float32 and np.array_equal(out16.cpu().numpy(), OM.bus_sum(as_f32, grp, 4))
+    qb = np.stack([q, q[::-1]])[:, :, :, :10000]                   # batched + multiple-of-8 vector path
+    outb = mixing.bus_sum(cuda(qb), grp, 4, batch_dims=1).cpu().numpy()
+    for b in range(2):
+        assert np.array_equal(outb[b], OM.bus_sum(qb[b].astype(np.float32) * np.float32(1.0 / 32768.0), grp, 4))
     st64 = rng.normal(size=(5, 2, 4096))
     out = mixing.bus_sum(cuda(st64), [3, 3, 0, 0, 0], 4)
     assert np.array_equal(out.cpu().numpy(), OM.bus_sum(st64, [3, 3, 0, 0, 0], 4))
