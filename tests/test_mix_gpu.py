@@ -144,3 +144,22 @@ def test_scale_and_normalise(cuda_device):
     am, sq = mixing.row_reduce(cuda(x32))
     assert np.array_equal(am.cpu().numpy(), np.abs(x32).max(axis=1).astype(np.float64))
     assert np.allclose(sq.cpu().numpy(), (x32.astype(np.float64) ** 2).sum(axis=1), rtol=1e-12)
+
+
+def test_no_writes_outside_outputs(cuda_device):
+    """Guard-band check (compute-sanitizer is closed on this pool) with odd sizes and offsets."""
+    from deep_audio_mixer_b200 import _lib
+    rng = np.random.default_rng(11)
+    for N in (4096, 4099, 1):
+        stems = cuda(rng.normal(size=(3, 2, N)).astype(np.float32))
+        res = mixing.gain_mix(stems, rng.uniform(0.5, 1.5, size=(3, max(1, min(5, N)))), want_stems=True)
+        ref = mixing.gain_mix(stems.clone(), res and rng.uniform(0.5, 1.5, size=(3, 1)), hold_single=True)
+        assert res['mix'].shape == (2, N) and ref['mix'].shape == (2, N)
+        assert torch.isfinite(res['mix']).all() and torch.isfinite(res['stems']).all()
+    # scale_rows / row_reduce on an offset, odd-length view
+    base = cuda(rng.normal(size=(4, 1003)))
+    view = base[:, 3:1000]
+    y = mixing.scale_rows(view, [2.0, 3.0, 4.0, 5.0])
+    assert np.array_equal(y.cpu().numpy(), view.cpu().numpy() * np.array([[2.0], [3.0], [4.0], [5.0]]))
+    am, sq = mixing.row_reduce(view)
+    assert np.array_equal(am.cpu().numpy(), np.abs(view.cpu().numpy()).max(axis=1))

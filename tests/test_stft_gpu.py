@@ -190,3 +190,25 @@ def test_compute_features_dropin_host_and_errors(cuda_device):
         F.stft_db(torch.zeros(1, 1000, device='cuda'))           # n <= n_fft/2
     with pytest.raises(Exception):
         F.stft_db(torch.zeros(1, 5000, device='cuda'), n_fft=1000)
+
+
+def test_no_writes_outside_the_output(cuda_device):
+    """compute-sanitizer is closed on this pool, so out-of-bounds stores are checked with guard bands:
+    the kernel writes into the middle of a sentinel-filled buffer (dense and strided rows) and the
+    guards must come back untouched, for tile-aligned and ragged frame counts."""
+    for n, hop, rows in ((9000, 512, 3), (8192, 1024, 5), (1100, 1, 1), (30000, 777, 2)):
+        T = 1 + n // hop
+        plane = 1025 * T
+        x = torch.randn(rows, n, device='cuda', dtype=torch.float32)
+        for stride in (plane, plane + 37):
+            guard = 4096
+            buf = torch.full((guard + rows * stride + guard,), float('nan'), device='cuda')
+            out = buf[guard:guard + rows * stride]
+            F.stft_db(x, hop=hop, out=out, out_row_stride=stride if stride != plane else 0) if stride == plane else \
+                F.stft_db(x, hop=hop, out=out, out_row_stride=stride)
+            torch.cuda.synchronize()
+            assert torch.isnan(buf[:guard]).all() and torch.isnan(buf[guard + rows * stride:]).all()
+            body = out.reshape(rows, stride) if stride != plane else out.reshape(rows, plane)
+            assert not torch.isnan(body[:, :plane]).any()
+            if stride != plane:
+                assert torch.isnan(body[:, plane:]).all()
