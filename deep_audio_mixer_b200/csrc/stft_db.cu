@@ -60,6 +60,7 @@ struct StftParams {
     long long T;                  // frames per row
     long long tiles_per_row, n_tiles;
     int tile_group;               // consecutive tiles a CTA processes back to back
+    int l2_prefetch;              // 1: prefetch the CTA's next tile into L2 while transforming this one
     float log_scale;              // multiplier/2 * log10(2): dB = log_scale * log2(|X|^2)
     float floor_db;               // multiplier * log10(amin), the clamp applied in the dB domain
     double log_scale_d, floor_db_d;
@@ -151,6 +152,34 @@ __device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ 
                 // plain copy (same type, mono, no scaling): asynchronous 16-byte global->shared copies
                 for (int v = tid; v < nvec; v += kThreads) cp_async16(s_stage + v * V, src + v * V);
                 cp_async_wait_all();
+            } else if (C == 2 && pro.unit_scale && !pro.has_gain) {
+                // stereo source, no scaling (the inference path with the mono shim): both channels of
+                // six vectors in flight per thread, (L + R) * 0.5 == numpy's float mean over two channels
+                constexpr int U2 = 6;
+                const uint4* s0 = reinterpret_cast<const uint4*>(src);
+                const uint4* s1 = reinterpret_cast<const uint4*>(src + p.chan_stride);
+                for (int v0 = tid; v0 < nvec; v0 += kThreads * U2) {
+                    uint4 r0[U2], r1[U2];
+#pragma unroll
+                    for (int u = 0; u < U2; ++u) {
+                        const int v = v0 + u * kThreads;
+                        r0[u] = v < nvec ? __ldg(s0 + v) : make_uint4(0, 0, 0, 0);
+                        r1[u] = v < nvec ? __ldg(s1 + v) : make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U2; ++u) {
+                        const int v = v0 + u * kThreads;
+                        if (v < nvec) {
+                            P a[V], c[V];
+                            R r[V];
+                            unpack16<P, SRC>(r0[u], a);
+                            unpack16<P, SRC>(r1[u], c);
+#pragma unroll
+                            for (int j = 0; j < V; ++j) r[j] = (R)((a[j] + c[j]) * (P)0.5);
+                            store_vec<R, V>(s_stage + v * V, r);
+                        }
+                    }
+                }
             } else
             for (int v0 = tid; v0 < nvec; v0 += kThreads * U) {
                 P acc[U][V];
@@ -479,7 +508,7 @@ stft_db_kernel(const StftParams p) {
         __syncthreads();
 
         // pull the next tile's samples towards L2 while this one is transformed
-        {
+        if (p.l2_prefetch) {
             const unsigned nt = (tile + 1 < (grp + 1) * G) ? tile + 1 : (grp + gridDim.x) * G;
             if (nt < n_tiles) {
                 const unsigned nrow = nt / tiles_per_row;
@@ -737,6 +766,8 @@ int launch(StftParams p, cudaStream_t stream) {
                   (long long)p.n_tiles);
     static const int group_env = [] { const char* e = getenv("DAM_K1_GROUP"); return e ? atoi(e) : 0; }();
     p.tile_group = group_env > 0 ? group_env : 1;
+    static const int pf_env = [] { const char* e = getenv("DAM_K1_PREFETCH"); return e ? atoi(e) : 1; }();
+    p.l2_prefetch = pf_env;
     const size_t smem = smem_bytes<R, kFT>(p.hop);
     auto kern = stft_db_kernel<R, OUT, kStats, kFT>;
     static std::mutex mu;

@@ -153,7 +153,7 @@ def test_no_writes_outside_outputs(cuda_device):
     for N in (4096, 4099, 1):
         stems = cuda(rng.normal(size=(3, 2, N)).astype(np.float32))
         res = mixing.gain_mix(stems, rng.uniform(0.5, 1.5, size=(3, max(1, min(5, N)))), want_stems=True)
-        ref = mixing.gain_mix(stems.clone(), res and rng.uniform(0.5, 1.5, size=(3, 1)), hold_single=True)
+        ref = mixing.gain_mix(stems.clone(), rng.uniform(0.5, 1.5, size=(3, 1)), hold_single=True)
         assert res['mix'].shape == (2, N) and ref['mix'].shape == (2, N)
         assert torch.isfinite(res['mix']).all() and torch.isfinite(res['stems']).all()
     # scale_rows / row_reduce on an offset, odd-length view

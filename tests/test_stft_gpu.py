@@ -204,7 +204,9 @@ def test_no_writes_outside_the_output(cuda_device):
             guard = 4096
             buf = torch.full((guard + rows * stride + guard,), float('nan'), device='cuda')
             out = buf[guard:guard + rows * stride]
-            F.stft_db(x, hop=hop, out=out, out_row_stride=stride if stride != plane else 0) if stride == plane else \
+            if stride == plane:
+                F.stft_db(x, hop=hop, out=out)
+            else:
                 F.stft_db(x, hop=hop, out=out, out_row_stride=stride)
             torch.cuda.synchronize()
             assert torch.isnan(buf[:guard]).all() and torch.isnan(buf[guard + rows * stride:]).all()
