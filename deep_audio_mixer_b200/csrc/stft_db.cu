@@ -44,6 +44,7 @@ template <> struct Cx<double> { using type = double2; };
 template <typename R, int FT> struct XchStride;
 template <> struct XchStride<float, 8>  { static constexpr int v = 32 * kRow + 2; };   // 1090
 template <> struct XchStride<float, 4>  { static constexpr int v = 32 * kRow + 4; };   // 1092
+template <> struct XchStride<float, 16> { static constexpr int v = 32 * kRow + 2; };   // 1090
 template <> struct XchStride<double, 8> { static constexpr int v = 32 * kRow + 1; };   // 1089
 
 struct StftParams {
@@ -874,7 +875,14 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
         // frames per tile of the float32 kernel: 8 (two CTAs of 8 warps per SM).  DAM_FT_F32=4 selects
         // four CTAs of 4 warps -- measured 2-3x SLOWER on B200 (16-byte output segments, 16 KB of L1
         // left beside 212 KB of shared memory); kept selectable for profiling only.
-        static const int ft = [] { const char* e = getenv("DAM_FT_F32"); return (e && atoi(e) == 4) ? 4 : 8; }();
+        static const int ft_env = [] { const char* e = getenv("DAM_FT_F32"); return e ? atoi(e) : 0; }();
+        // Default 8 frames per tile (two 8-warp CTAs per SM).  16 frames per tile (one 16-warp CTA per SM)
+        // writes 64-byte row segments: measured +15 % when rows are not sector aligned (T % 8 != 0) at
+        // hop >= 1024, -17 % when they are, -4 % at hop 512; it also wastes more of a short row's last tile.
+        int ft = 8;
+        if (ft_env == 4 || ft_env == 8 || ft_env == 16) ft = ft_env;
+        else if (hop >= 1024 && (p.T % 8) != 0 && p.T >= 160) ft = 16;
+        if (ft == 16) return st ? launch<float, float, true, 16>(p, s) : launch<float, float, false, 16>(p, s);
         // DAM_K1_PIPE=1 selects the warp-specialised mbarrier pipeline (hop <= 1024).  Measured on B200 it
         // is 10-35 % SLOWER than the phase-structured kernel: with tile-granular double buffering its 6+6
         // transform warps spend most of their time in mbarrier waits on each other (profiles/), so the
