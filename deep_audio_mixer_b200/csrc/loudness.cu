@@ -110,6 +110,7 @@ struct KwParams {
     const void* x;
     long long n_rows, n, row_stride, samp_stride;
     long long n_chunks;            // ceil(n / kChunk)
+    long long n_items;             // ceil(n_rows * n_chunks / kBlock): work items of passes A and C
     Coeffs c;
     const double* G;
     double ML[16], MS[16];
@@ -119,22 +120,25 @@ struct KwParams {
     double* states;                // workspace [n_rows][n_chunks][4]
 };
 
-// Cooperative, coalesced, software-pipelined tile loader shared by passes A and C.  A CTA owns
-// kBlock consecutive chunks; per step it stages [kBlock chunks x kSub samples]: a warp reads two rows
-// of 16 consecutive samples (full sectors), registers hold the NEXT step's samples while the current
-// ones are consumed from shared memory, and thread c then walks row c (pitch kSub+1: no conflicts).
-// Thread-per-chunk loads straight from global memory would touch 32 different lines per instruction
-// and are bound by the L1 tag rate (measured: 70 % l1tex, 10 % issue).
+// Cooperative, coalesced, software-pipelined tile loader shared by passes A and C.  The unit of work
+// is kBlock consecutive GLOBAL chunk ids (row-major over all rows, so a work item may straddle two
+// rows and no CTA is padded per row: 220 544 chunks of the bench batch are 862 items, 2.91 rounds of
+// 296 resident CTAs, instead of 896 per-row items = 4 rounds).  Thread c owns chunk c of the item and
+// publishes its base offset and length; per step the CTA stages [kBlock chunks x kSub samples]: a warp
+// reads two rows of 16 consecutive samples (full sectors), registers hold the NEXT step's samples
+// while the current ones are consumed from shared memory, and thread c then walks row c (pitch
+// kSub+1: conflict-free).  Thread-per-chunk loads straight from global memory touch 32 different
+// lines per instruction and are bound by the L1 tag rate (measured: 70 % l1tex, 10 % issue).
 template <typename T>
 struct TileLoader {
     T reg[kSub];
-    __device__ __forceinline__ void load(const T* __restrict__ xrow, long long chunk0, int sb, long long n,
-                                         long long samp_stride) {
+    __device__ __forceinline__ void load(const T* __restrict__ x, const long long* __restrict__ s_base,
+                                         const int* __restrict__ s_len, int sb, long long samp_stride) {
 #pragma unroll
         for (int k = 0; k < kSub; ++k) {
             const int e = threadIdx.x + k * kBlock;
-            const long long gi = (chunk0 + (e >> 4)) * kChunk + (long long)sb * kSub + (e & 15);
-            reg[k] = gi < n ? xrow[gi * samp_stride] : T(0);
+            const int r = e >> 4, idx = sb * kSub + (e & 15);
+            reg[k] = idx < s_len[r] ? x[s_base[r] + idx * samp_stride] : T(0);
         }
     }
     __device__ __forceinline__ void store(T* __restrict__ tile) const {
@@ -147,43 +151,65 @@ struct TileLoader {
 };
 
 template <typename T>
-constexpr size_t kw_smem_bytes() { return kChunk * 4 * sizeof(double) + 2 * kBlock * kPitch * sizeof(T); }
+constexpr size_t kw_smem_bytes() {
+    return kChunk * 4 * sizeof(double) + kBlock * sizeof(long long) + kBlock * sizeof(int) + 2 * kBlock * kPitch * sizeof(T);
+}
+
+struct ChunkId { long long g, row, chunk; int len; bool active; };
+
+// thread c's chunk of work item `item`, published to shared memory for the cooperative loader
+__device__ __forceinline__ ChunkId publish_chunk(const KwParams& p, long long item, long long* s_base, int* s_len) {
+    ChunkId id;
+    id.g = item * kBlock + threadIdx.x;
+    id.active = id.g < p.n_rows * p.n_chunks;
+    id.row = id.active ? id.g / p.n_chunks : 0;
+    id.chunk = id.g - id.row * p.n_chunks;
+    const long long left = p.n - id.chunk * kChunk;
+    id.len = !id.active ? 0 : (left < kChunk ? (int)left : kChunk);
+    s_base[threadIdx.x] = id.row * p.row_stride + id.chunk * kChunk * p.samp_stride;
+    s_len[threadIdx.x] = id.len;
+    return id;
+}
 
 // pass A: zero-state end state of each full chunk (the last chunk's end state is never needed)
 template <typename T>
 __global__ void __launch_bounds__(kBlock) kw_chunk_state_kernel(const KwParams p) {
     extern __shared__ __align__(16) unsigned char kw_smem[];
     double* s_G = reinterpret_cast<double*>(kw_smem);
-    T* s_tile = reinterpret_cast<T*>(s_G + kChunk * 4);
+    long long* s_base = reinterpret_cast<long long*>(s_G + kChunk * 4);
+    int* s_len = reinterpret_cast<int*>(s_base + kBlock);
+    T* s_tile = reinterpret_cast<T*>(s_len + kBlock);
+    const T* x = reinterpret_cast<const T*>(p.x);
     for (int i = threadIdx.x; i < kChunk * 4; i += kBlock) s_G[i] = p.G[i];
-    const long long row = blockIdx.y;
-    const long long chunk0 = (long long)blockIdx.x * kBlock;
-    const long long chunk = chunk0 + threadIdx.x;
-    const T* xrow = reinterpret_cast<const T*>(p.x) + row * p.row_stride;
-    TileLoader<T> ld;
-    ld.load(xrow, chunk0, 0, p.n, p.samp_stride);
-    ld.store(s_tile);
-    __syncthreads();
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    for (int sb = 0; sb < kChunk / kSub; ++sb) {
-        const bool more = sb + 1 < kChunk / kSub;
-        if (more) ld.load(xrow, chunk0, sb + 1, p.n, p.samp_stride);
-        const T* mine = s_tile + (sb & 1) * kBlock * kPitch + threadIdx.x * kPitch;
-#pragma unroll
-        for (int j = 0; j < kSub; ++j) {
-            const double v = (double)mine[j];
-            const double* g = s_G + (sb * kSub + j) * 4;
-            a0 = fma(g[0], v, a0); a1 = fma(g[1], v, a1);
-            a2 = fma(g[2], v, a2); a3 = fma(g[3], v, a3);
-        }
-        if (more) ld.store(s_tile + ((sb + 1) & 1) * kBlock * kPitch);
+    for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        __syncthreads();                      // previous item is fully consumed (and s_G is loaded)
+        const ChunkId id = publish_chunk(p, item, s_base, s_len);
         __syncthreads();
-    }
-    if (chunk < p.n_chunks) {
-        const bool last = chunk == p.n_chunks - 1;      // possibly partial: its end state is unused
-        double* st = p.states + (row * p.n_chunks + chunk) * 4;
-        *reinterpret_cast<double2*>(st) = last ? make_double2(0.0, 0.0) : make_double2(a0, a1);
-        *reinterpret_cast<double2*>(st + 2) = last ? make_double2(0.0, 0.0) : make_double2(a2, a3);
+        TileLoader<T> ld;
+        ld.load(x, s_base, s_len, 0, p.samp_stride);
+        ld.store(s_tile);
+        __syncthreads();
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int sb = 0; sb < kChunk / kSub; ++sb) {
+            const bool more = sb + 1 < kChunk / kSub;
+            if (more) ld.load(x, s_base, s_len, sb + 1, p.samp_stride);
+            const T* mine = s_tile + (sb & 1) * kBlock * kPitch + threadIdx.x * kPitch;
+#pragma unroll
+            for (int j = 0; j < kSub; ++j) {
+                const double v = (double)mine[j];
+                const double* g = s_G + (sb * kSub + j) * 4;
+                a0 = fma(g[0], v, a0); a1 = fma(g[1], v, a1);
+                a2 = fma(g[2], v, a2); a3 = fma(g[3], v, a3);
+            }
+            if (more) ld.store(s_tile + ((sb + 1) & 1) * kBlock * kPitch);
+            __syncthreads();
+        }
+        if (id.active) {
+            const bool last = id.chunk == p.n_chunks - 1;      // possibly partial: its end state is unused
+            double* st = p.states + id.g * 4;
+            *reinterpret_cast<double2*>(st) = last ? make_double2(0.0, 0.0) : make_double2(a0, a1);
+            *reinterpret_cast<double2*>(st + 2) = last ? make_double2(0.0, 0.0) : make_double2(a2, a3);
+        }
     }
 }
 
@@ -250,73 +276,75 @@ __global__ void __launch_bounds__(kScanBlock) kw_scan_kernel(const KwParams p) {
 template <typename T>
 __global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
     extern __shared__ __align__(16) unsigned char kw_smem[];
-    T* s_tile = reinterpret_cast<T*>(reinterpret_cast<double*>(kw_smem) + kChunk * 4);
-    const long long row = blockIdx.y;
-    const long long chunk0 = (long long)blockIdx.x * kBlock;
-    const long long chunk = chunk0 + threadIdx.x;
-    const bool active = chunk < p.n_chunks;
-    const long long i0 = chunk * kChunk;
-    const long long len = !active ? 0 : (p.n - i0 < kChunk ? p.n - i0 : kChunk);
-    const T* xrow = reinterpret_cast<const T*>(p.x) + row * p.row_stride;
-    TileLoader<T> ld;
-    ld.load(xrow, chunk0, 0, p.n, p.samp_stride);
-    double s[4] = {0, 0, 0, 0};
-    if (active) {
-        const double* st = p.states + (row * p.n_chunks + chunk) * 4;
-        s[0] = st[0]; s[1] = st[1]; s[2] = st[2]; s[3] = st[3];
-    }
+    long long* s_base = reinterpret_cast<long long*>(reinterpret_cast<double*>(kw_smem) + kChunk * 4);
+    int* s_len = reinterpret_cast<int*>(s_base + kBlock);
+    T* s_tile = reinterpret_cast<T*>(s_len + kBlock);
+    const T* x = reinterpret_cast<const T*>(p.x);
     const Coeffs c = p.c;
-
-    // segment containing sample i0: largest k with bounds[k] <= i0 (k = -1 before the first bound)
-    long long seg = -1, next = 0x7fffffffffffffffLL;
-    if (active) {
-        long long lo = 0, hi = p.n_seg + 1;
-        while (lo < hi) {
-            const long long mid = (lo + hi) >> 1;
-            if (p.seg_bounds[mid] <= i0) lo = mid + 1; else hi = mid;
+    for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        __syncthreads();                      // previous item is fully consumed
+        const ChunkId id = publish_chunk(p, item, s_base, s_len);
+        __syncthreads();
+        TileLoader<T> ld;
+        ld.load(x, s_base, s_len, 0, p.samp_stride);
+        const long long i0 = id.chunk * kChunk;
+        const long long len = id.len;
+        double s[4] = {0, 0, 0, 0};
+        if (id.active) {
+            const double* st = p.states + id.g * 4;
+            s[0] = st[0]; s[1] = st[1]; s[2] = st[2]; s[3] = st[3];
         }
-        seg = lo - 1;                                 // -1: before first bound; n_seg: after last
-        next = seg + 1 <= p.n_seg ? p.seg_bounds[seg + 1] : (long long)0x7fffffffffffffffLL;
-    }
-    double* out = p.seg_sumsq + row * p.n_seg;
-    double acc = 0.0;
-    ld.store(s_tile);
-    __syncthreads();
+        // segment containing sample i0: largest k with bounds[k] <= i0 (k = -1 before the first bound)
+        long long seg = -1, next = 0x7fffffffffffffffLL;
+        if (id.active) {
+            long long lo = 0, hi = p.n_seg + 1;
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                if (p.seg_bounds[mid] <= i0) lo = mid + 1; else hi = mid;
+            }
+            seg = lo - 1;                             // -1: before first bound; n_seg: after last
+            next = seg + 1 <= p.n_seg ? p.seg_bounds[seg + 1] : (long long)0x7fffffffffffffffLL;
+        }
+        double* out = p.seg_sumsq + id.row * p.n_seg;
+        double acc = 0.0;
+        ld.store(s_tile);
+        __syncthreads();
 
-    for (int sb = 0; sb < kChunk / kSub; ++sb) {
-        const bool more = sb + 1 < kChunk / kSub;
-        if (more) ld.load(xrow, chunk0, sb + 1, p.n, p.samp_stride);
-        const T* mine = s_tile + (sb & 1) * kBlock * kPitch + threadIdx.x * kPitch;
-        const long long base = (long long)sb * kSub;
-        if (base < len) {
-            const long long g_last = i0 + (base + kSub < len ? base + kSub : len) - 1;
-            if (g_last < next && base + kSub <= len) {
-                // no boundary inside this step and a full step (the common case): straight-line recurrence
+        for (int sb = 0; sb < kChunk / kSub; ++sb) {
+            const bool more = sb + 1 < kChunk / kSub;
+            if (more) ld.load(x, s_base, s_len, sb + 1, p.samp_stride);
+            const T* mine = s_tile + (sb & 1) * kBlock * kPitch + threadIdx.x * kPitch;
+            const long long base = (long long)sb * kSub;
+            if (base < len) {
+                const long long g_last = i0 + (base + kSub < len ? base + kSub : len) - 1;
+                if (g_last < next && base + kSub <= len) {
+                    // no boundary inside this step and a full step (the common case): straight-line recurrence
 #pragma unroll
-                for (int j = 0; j < kSub; ++j) {
-                    double y;
-                    step(c, (double)mine[j], s, &y);
-                    acc = fma(y, y, acc);
-                }
-            } else {
-                for (int j = 0; j < kSub && base + j < len; ++j) {
-                    const long long gi = i0 + base + j;
-                    while (gi >= next) {              // crossed a segment boundary: flush
-                        if (seg >= 0 && seg < p.n_seg && acc != 0.0) atomicAdd(out + seg, acc);
-                        acc = 0.0;
-                        ++seg;
-                        next = seg + 1 <= p.n_seg ? p.seg_bounds[seg + 1] : (long long)0x7fffffffffffffffLL;
+                    for (int j = 0; j < kSub; ++j) {
+                        double y;
+                        step(c, (double)mine[j], s, &y);
+                        acc = fma(y, y, acc);
                     }
-                    double y;
-                    step(c, (double)mine[j], s, &y);
-                    acc = fma(y, y, acc);
+                } else {
+                    for (int j = 0; j < kSub && base + j < len; ++j) {
+                        const long long gi = i0 + base + j;
+                        while (gi >= next) {          // crossed a segment boundary: flush
+                            if (seg >= 0 && seg < p.n_seg && acc != 0.0) atomicAdd(out + seg, acc);
+                            acc = 0.0;
+                            ++seg;
+                            next = seg + 1 <= p.n_seg ? p.seg_bounds[seg + 1] : (long long)0x7fffffffffffffffLL;
+                        }
+                        double y;
+                        step(c, (double)mine[j], s, &y);
+                        acc = fma(y, y, acc);
+                    }
                 }
             }
+            if (more) ld.store(s_tile + ((sb + 1) & 1) * kBlock * kPitch);
+            __syncthreads();
         }
-        if (more) ld.store(s_tile + ((sb + 1) & 1) * kBlock * kPitch);
-        __syncthreads();
+        if (seg >= 0 && seg < p.n_seg && acc != 0.0) atomicAdd(out + seg, acc);
     }
-    if (seg >= 0 && seg < p.n_seg && acc != 0.0) atomicAdd(out + seg, acc);
 }
 
 // Gating + LUFS on the device (one CTA per signal), so batch pipelines never synchronise with the host.
@@ -412,27 +440,36 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
     KwParams p;
     p.x = x; p.n_rows = n_rows; p.n = n_samples; p.row_stride = row_stride; p.samp_stride = samp_stride;
     p.n_chunks = (n_samples + kChunk - 1) / kChunk;
+    p.n_items = (n_rows * p.n_chunks + kBlock - 1) / kBlock;
     p.c = c; p.G = t->G;
     memcpy(p.ML, t->ML, sizeof(p.ML));
     memcpy(p.MS, t->MS, sizeof(p.MS));
     p.seg_bounds = reinterpret_cast<const long long*>(seg_bounds); p.n_seg = n_seg;
     p.seg_sumsq = seg_sumsq; p.states = reinterpret_cast<double*>(workspace);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    dim3 grid((unsigned)((p.n_chunks + kBlock - 1) / kBlock), (unsigned)n_rows);
+    static std::mutex mu;
+    static bool configured[64] = {};
+    static int occ_f32[64] = {}, occ_f64[64] = {};
+    int dev = 0;
+    DAM_CHECK_CUDA(cudaGetDevice(&dev));
     {
-        static std::mutex mu;
-        static bool configured[64] = {};
-        int dev = 0;
-        DAM_CHECK_CUDA(cudaGetDevice(&dev));
         std::lock_guard<std::mutex> lock(mu);
         if (!configured[dev]) {
             DAM_CHECK_CUDA(cudaFuncSetAttribute(kw_chunk_state_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes<double>()));
             DAM_CHECK_CUDA(cudaFuncSetAttribute(kw_apply_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes<double>()));
             DAM_CHECK_CUDA(cudaFuncSetAttribute(kw_chunk_state_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes<float>()));
             DAM_CHECK_CUDA(cudaFuncSetAttribute(kw_apply_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kw_smem_bytes<float>()));
+            DAM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f32[dev], kw_apply_kernel<float>, kBlock, kw_smem_bytes<float>()));
+            DAM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f64[dev], kw_apply_kernel<double>, kBlock, kw_smem_bytes<double>()));
             configured[dev] = true;
         }
     }
+    // persistent grid: a whole number of CTAs per SM, work items dealt round-robin
+    const int occ = dtype == DAM_F32 ? occ_f32[dev] : occ_f64[dev];
+    const long long n_items = p.n_items;
+    long long grid_ll = (long long)dam_sm_count() * (occ > 0 ? occ : 1);
+    if (grid_ll > n_items) grid_ll = n_items;
+    const unsigned grid = (unsigned)grid_ll;
     if (dtype == DAM_F32) kw_chunk_state_kernel<float><<<grid, kBlock, kw_smem_bytes<float>(), st>>>(p);
     else kw_chunk_state_kernel<double><<<grid, kBlock, kw_smem_bytes<double>(), st>>>(p);
     DAM_CHECK_CUDA(cudaGetLastError());

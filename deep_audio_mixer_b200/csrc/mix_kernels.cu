@@ -94,7 +94,7 @@ struct GainMixParams {
 };
 
 template <typename TS, typename TC, typename TO, int V>
-__global__ void __launch_bounds__(kBlock, 3) gain_mix_kernel(const GainMixParams p) {
+__global__ void __launch_bounds__(kBlock, 4) gain_mix_kernel(const GainMixParams p) {
     __shared__ double s_red[kBlock / 32];
     const long long c = blockIdx.y;
     const long long bt = blockIdx.z;
@@ -110,57 +110,54 @@ __global__ void __launch_bounds__(kBlock, 3) gain_mix_kernel(const GainMixParams
 
     for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
         const long long i0 = v * V;
-        long long kidx[V];
-        {
-            // k0 = min(i0 / coef, K-1) without a 64-bit integer division: double reciprocal estimate
-            // (exact to within one for i0 < 2^52) followed by an exact correction
-            long long k0 = K - 1;
-            if (coef > 0) {
-                k0 = (long long)((double)i0 * inv_coef);
-                if (k0 * coef > i0) --k0;
-                else if ((k0 + 1) * coef <= i0) ++k0;
-                if (k0 > K - 1) k0 = K - 1;
-            }
-            const long long next = (k0 + 1) * coef;          // first sample of gain k0+1
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-                long long k = k0;
-                if (k0 < K - 1 && i0 + j >= next) {
-                    k = (i0 + j) / coef;                      // coef < V is legal: recompute exactly
-                    if (k > K - 1) k = K - 1;
-                }
-                kidx[j] = k;
+        // gain index of sample i0: k0 = min(i0 / coef, K-1), without a 64-bit integer division (double
+        // reciprocal estimate, exact to within one for i0 < 2^52, then an exact correction).  `cross` is
+        // how many of this thread's V samples still belong to gain k0 (V when no boundary is crossed).
+        int k0 = (int)K - 1;
+        int cross = V;
+        if (coef > 0) {
+            long long kk = (long long)((double)i0 * inv_coef);
+            if (kk * coef > i0) --kk;
+            else if ((kk + 1) * coef <= i0) ++kk;
+            if (kk < K - 1) {
+                k0 = (int)kk;
+                const long long left = (kk + 1) * coef - i0;      // samples until gain k0+1 starts
+                cross = left < V ? (int)left : V;
             }
         }
         TC acc[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = TC(0);
-        const bool one_gain = kidx[0] == kidx[V - 1];
         constexpr int SU = sizeof(TS) == 4 ? 4 : 2;    // stems whose loads are in flight together
-        for (long long s0 = 0; s0 < p.n_stems; s0 += SU) {
+        for (int s0 = 0; s0 < (int)p.n_stems; s0 += SU) {
             Vec<TS, V> x[SU];
             double g0[SU];
 #pragma unroll
             for (int u = 0; u < SU; ++u) {
-                if (s0 + u < p.n_stems) {
-                    x[u] = load_vec<TS, V>(base + (s0 + u) * p.stem_stride + i0);
-                    g0[u] = __ldg(gains + (s0 + u) * K + kidx[0]);
+                if (s0 + u < (int)p.n_stems) {
+                    x[u] = load_vec<TS, V>(base + (long long)(s0 + u) * p.stem_stride + i0);
+                    g0[u] = __ldg(gains + (long long)(s0 + u) * K + k0);
                 }
             }
 #pragma unroll
             for (int u = 0; u < SU; ++u) {
-                const long long s = s0 + u;
-                if (s < p.n_stems) {
+                const int s = s0 + u;
+                if (s < (int)p.n_stems) {
                     Vec<TO, V> y;
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
-                        const double gd = one_gain ? g0[u] : __ldg(gains + s * K + kidx[j]);
+                        double gd = g0[u];
+                        if (j >= cross) {                      // rare: a gain boundary inside the vector
+                            long long k = (i0 + j) / coef;
+                            if (k > K - 1) k = K - 1;
+                            gd = __ldg(gains + (long long)s * K + k);
+                        }
                         const TC g = p.zero_mask ? TC(0) : (TC)gd;
                         const TC prod = (TC)x[u].v[j] * g;
                         acc[j] = s == 0 ? prod : acc[j] + prod;
                         y.v[j] = (TO)prod;
                     }
-                    if (stems_out) store_vec<TO, V>(stems_out + (s * p.n_channels + c) * n + i0, y);
+                    if (stems_out) store_vec<TO, V>(stems_out + ((long long)s * p.n_channels + c) * n + i0, y);
                 }
             }
         }
