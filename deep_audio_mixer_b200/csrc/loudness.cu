@@ -24,7 +24,6 @@
 namespace {
 
 constexpr int kChunk = 256;        // samples per chunk (L)
-constexpr int kSuper = 32;         // chunks per super-chunk in the two-level scan
 constexpr int kBlock = 256;        // chunks (= threads) per CTA in passes A and C
 constexpr int kSub = 16;           // samples per chunk staged per pipeline step
 constexpr int kPitch = kSub + 1;   // shared-memory row pitch: thread c walks row c conflict-free
@@ -36,7 +35,6 @@ struct KwTables {                  // device-resident, per coefficient set
     Coeffs c;
     double* G = nullptr;           // [kChunk][4]
     double ML[16];                 // M^L   (row-major 4x4)
-    double MS[16];                 // M^(L*kSuper)
 };
 
 __host__ __device__ inline void step(const Coeffs& c, double x, double s[4], double* y_out) {
@@ -89,15 +87,13 @@ int get_tables(const Coeffs& c, KwTables** out) {
             step(c, 0.0, v, nullptr);
         }
     }
-    // M^L by running L zero-input steps on unit states; M^(L*kSuper) by repeated squaring
+    // M^L by running L zero-input steps on unit states
     for (int j = 0; j < 4; ++j) {
         double s[4] = {0, 0, 0, 0};
         s[j] = 1.0;
         for (int k = 0; k < kChunk; ++k) step(c, 0.0, s, nullptr);
         for (int i = 0; i < 4; ++i) t->ML[i * 4 + j] = s[i];
     }
-    memcpy(t->MS, t->ML, sizeof(t->ML));
-    for (int sq = 1; sq < kSuper; sq <<= 1) matmul4(t->MS, t->MS, t->MS);
     (void)M;
     DAM_CHECK_CUDA(cudaMalloc(&t->G, G.size() * sizeof(double)));
     DAM_CHECK_CUDA(cudaMemcpy(t->G, G.data(), G.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -113,7 +109,9 @@ struct KwParams {
     long long n_items;             // ceil(n_rows * n_chunks / kBlock): work items of passes A and C
     Coeffs c;
     const double* G;
-    double ML[16], MS[16];
+    double ML[16];                 // M^L (one chunk)
+    double P[8][16];               // (M^(L*super))^(2^j): Kogge-Stone levels of the scan
+    long long super;               // chunks per scan thread
     const long long* seg_bounds;   // [n_seg + 1]
     long long n_seg;
     double* seg_sumsq;             // [n_rows][n_seg]
@@ -219,56 +217,56 @@ __device__ __forceinline__ void matvec_add(const double* M, const double s[4], c
         out[i] = fma(M[i * 4 + 0], s[0], fma(M[i * 4 + 1], s[1], fma(M[i * 4 + 2], s[2], fma(M[i * 4 + 3], s[3], z[i]))));
 }
 
-// scan: turn zero-state end states into true start states, in place.  One CTA per row.
+// scan: turn zero-state end states into true start states, in place.  One CTA per row; thread u owns
+// a run of p.super (= ceil(n_chunks / kScanBlock)) consecutive chunks.
+//   1. fold the run from a zero start state (loads are independent of the recurrence),
+//   2. Kogge-Stone scan of the affine maps s -> P s + e across the CTA: level j combines with the
+//      thread 2^j to the left using P_j = (M^(L*super))^(2^j), precomputed on the host,
+//   3. replay the run from its true start state, storing the start state of every chunk.
 __global__ void __launch_bounds__(kScanBlock) kw_scan_kernel(const KwParams p) {
-    __shared__ double s_end[kScanBlock][4];
-    __shared__ double s_carry[4];
+    __shared__ double s_e[2][kScanBlock][4];
     const long long row = blockIdx.x;
     double* st = p.states + row * p.n_chunks * 4;
-    const long long n_super = (p.n_chunks + kSuper - 1) / kSuper;
-    if (threadIdx.x == 0) s_carry[0] = s_carry[1] = s_carry[2] = s_carry[3] = 0.0;
-    for (long long base = 0; base < n_super; base += kScanBlock) {
-        const long long u = base + threadIdx.x;
-        const long long c0 = u * kSuper;
-        const long long c1 = c0 + kSuper < p.n_chunks ? c0 + kSuper : p.n_chunks;
-        double s[4] = {0, 0, 0, 0};
-        if (u < n_super) {
-#pragma unroll 8
-            for (long long c = c0; c < c1; ++c) {
-                const double2 za = *reinterpret_cast<const double2*>(st + c * 4);
-                const double2 zb = *reinterpret_cast<const double2*>(st + c * 4 + 2);
-                double z[4] = {za.x, za.y, zb.x, zb.y}, o[4];
-                matvec_add(p.ML, s, z, o);
-                s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
-            }
+    const long long u = threadIdx.x;
+    const long long c0 = u * p.super;
+    const long long c1 = c0 + p.super < p.n_chunks ? c0 + p.super : p.n_chunks;
+    double s[4] = {0, 0, 0, 0};
+#pragma unroll 4
+    for (long long c = c0; c < c1; ++c) {
+        const double2 za = *reinterpret_cast<const double2*>(st + c * 4);
+        const double2 zb = *reinterpret_cast<const double2*>(st + c * 4 + 2);
+        double z[4] = {za.x, za.y, zb.x, zb.y}, o[4];
+        matvec_add(p.ML, s, z, o);
+        s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+    }
+    // inclusive scan: after level j thread u holds the end state of runs (u - 2^(j+1), u] from zero
+    int cur = 0;
+    s_e[0][u][0] = s[0]; s_e[0][u][1] = s[1]; s_e[0][u][2] = s[2]; s_e[0][u][3] = s[3];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int d = 1 << j;
+        if (u >= d) {
+            const double l[4] = {s_e[cur][u - d][0], s_e[cur][u - d][1], s_e[cur][u - d][2], s_e[cur][u - d][3]};
+            double o[4];
+            matvec_add(p.P[j], l, s, o);
+            s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
         }
-        s_end[threadIdx.x][0] = s[0]; s_end[threadIdx.x][1] = s[1];
-        s_end[threadIdx.x][2] = s[2]; s_end[threadIdx.x][3] = s[3];
+        cur ^= 1;
+        s_e[cur][u][0] = s[0]; s_e[cur][u][1] = s[1]; s_e[cur][u][2] = s[2]; s_e[cur][u][3] = s[3];
         __syncthreads();
-        if (threadIdx.x == 0) {
-            // serial over the super-chunks of this round; s_end[i] becomes the START state of super-chunk i
-            double cur[4] = {s_carry[0], s_carry[1], s_carry[2], s_carry[3]};
-            const long long cnt = n_super - base < kScanBlock ? n_super - base : kScanBlock;
-            for (long long i = 0; i < cnt; ++i) {
-                double e[4] = {s_end[i][0], s_end[i][1], s_end[i][2], s_end[i][3]}, o[4];
-                s_end[i][0] = cur[0]; s_end[i][1] = cur[1]; s_end[i][2] = cur[2]; s_end[i][3] = cur[3];
-                matvec_add(p.MS, cur, e, o);      // only exact for full super-chunks; a partial one is last
-                cur[0] = o[0]; cur[1] = o[1]; cur[2] = o[2]; cur[3] = o[3];
-            }
-            s_carry[0] = cur[0]; s_carry[1] = cur[1]; s_carry[2] = cur[2]; s_carry[3] = cur[3];
-        }
-        __syncthreads();
-        if (u < n_super) {
-            s[0] = s_end[threadIdx.x][0]; s[1] = s_end[threadIdx.x][1];
-            s[2] = s_end[threadIdx.x][2]; s[3] = s_end[threadIdx.x][3];
-            for (long long c = c0; c < c1; ++c) {
-                double z[4] = {st[c * 4], st[c * 4 + 1], st[c * 4 + 2], st[c * 4 + 3]}, o[4];
-                st[c * 4] = s[0]; st[c * 4 + 1] = s[1]; st[c * 4 + 2] = s[2]; st[c * 4 + 3] = s[3];
-                matvec_add(p.ML, s, z, o);
-                s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
-            }
-        }
-        __syncthreads();
+    }
+    // start state of run u = inclusive result of run u-1
+    if (u == 0) { s[0] = s[1] = s[2] = s[3] = 0.0; }
+    else { s[0] = s_e[cur][u - 1][0]; s[1] = s_e[cur][u - 1][1]; s[2] = s_e[cur][u - 1][2]; s[3] = s_e[cur][u - 1][3]; }
+    for (long long c = c0; c < c1; ++c) {
+        const double2 za = *reinterpret_cast<const double2*>(st + c * 4);
+        const double2 zb = *reinterpret_cast<const double2*>(st + c * 4 + 2);
+        double z[4] = {za.x, za.y, zb.x, zb.y}, o[4];
+        *reinterpret_cast<double2*>(st + c * 4) = make_double2(s[0], s[1]);
+        *reinterpret_cast<double2*>(st + c * 4 + 2) = make_double2(s[2], s[3]);
+        matvec_add(p.ML, s, z, o);
+        s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
     }
 }
 
@@ -443,7 +441,18 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
     p.n_items = (n_rows * p.n_chunks + kBlock - 1) / kBlock;
     p.c = c; p.G = t->G;
     memcpy(p.ML, t->ML, sizeof(p.ML));
-    memcpy(p.MS, t->MS, sizeof(p.MS));
+    p.super = (p.n_chunks + kScanBlock - 1) / kScanBlock;
+    {
+        // P_0 = (M^L)^super by binary exponentiation, P_{j+1} = P_j^2
+        double base[16], acc[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        memcpy(base, t->ML, sizeof(base));
+        for (long long e = p.super; e > 0; e >>= 1) {
+            if (e & 1) matmul4(acc, base, acc);
+            matmul4(base, base, base);
+        }
+        memcpy(p.P[0], acc, sizeof(acc));
+        for (int j = 1; j < 8; ++j) matmul4(p.P[j - 1], p.P[j - 1], p.P[j]);
+    }
     p.seg_bounds = reinterpret_cast<const long long*>(seg_bounds); p.n_seg = n_seg;
     p.seg_sumsq = seg_sumsq; p.states = reinterpret_cast<double*>(workspace);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
