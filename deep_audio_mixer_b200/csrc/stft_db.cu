@@ -698,6 +698,132 @@ stft_db_pipe_kernel(const StftParams p) {
     if (kStats) st.flush(p.stats, lane);
 }
 
+// ==========================================================================================
+// Generic window sizes (power of two, 64..8192 except 2048): a plain shared-memory radix-2 transform,
+// one CTA per (row, tile of 8 frames).  The reference only ever uses window_size = 2048
+// (data/dataset.py:132), so this path exists for API completeness (window_size is a runtime argument
+// of compute_features), not for speed: same staging semantics, same dB epilogue, same output layout.
+constexpr int kGenThreads = 256;     // frames per tile: 8, or fewer when the dB staging would not fit
+
+template <typename R>
+size_t generic_smem_bytes(int n_fft, int ft) {
+    using C = typename Cx<R>::type;
+    return (size_t)n_fft * sizeof(C) + (size_t)(n_fft / 2) * sizeof(C) + (size_t)n_fft * sizeof(R) +
+           (size_t)(n_fft / 2 + 1) * ft * sizeof(float);
+}
+
+template <typename R, typename OUT>
+__global__ void __launch_bounds__(kGenThreads)
+stft_db_generic_kernel(const StftParams p, int n_fft, int log2n, int kGenFT) {
+    using C = typename Cx<R>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* s_buf = reinterpret_cast<C*>(smem_raw);                    // [n_fft] in-place transform
+    C* s_twd = s_buf + n_fft;                                     // [n_fft/2] exp(-2 pi i k / n_fft)
+    R* s_win = reinterpret_cast<R*>(s_twd + n_fft / 2);           // [n_fft]
+    float* s_db = reinterpret_cast<float*>(s_win + n_fft);        // [n_fft/2+1][kGenFT]
+    const int tid = threadIdx.x;
+    const int bins = n_fft / 2 + 1;
+    for (int i = tid; i < n_fft; i += kGenThreads) s_win[i] = (R)__ldg(p.window + i);
+    for (int i = tid; i < n_fft / 2; i += kGenThreads) {
+        double sn, cs;
+        sincospi(-2.0 * (double)i / (double)n_fft, &sn, &cs);
+        C w; w.x = (R)cs; w.y = (R)sn;
+        s_twd[i] = w;
+    }
+    const long long row = blockIdx.y;
+    const long long t0 = (long long)blockIdx.x * kGenFT;
+    const long long T = p.T, n = p.n_samples;
+    const int nf = (int)((T - t0) < kGenFT ? (T - t0) : kGenFT);
+    const long long row_off = row_offset(p, row);
+    const bool f64src = p.audio_dtype == DAM_F64;
+    const double gain = p.row_gain != nullptr ? p.row_gain[row] : 1.0;
+    __syncthreads();
+    for (int t = 0; t < nf; ++t) {
+        // windowed frame in bit-reversed order (prologue in the source precision, like the fast path)
+        for (int i = tid; i < n_fft; i += kGenThreads) {
+            long long g = (t0 + t) * p.hop - n_fft / 2 + i;
+            g = g < 0 ? -g : g;
+            g = g >= n ? 2 * (n - 1) - g : g;
+            const long long off = row_off + g * p.samp_stride;
+            R v;
+            if (f64src) {
+                double acc = __ldg(reinterpret_cast<const double*>(p.audio) + off) * p.input_scale;
+                for (int c = 1; c < p.channels; ++c)
+                    acc += __ldg(reinterpret_cast<const double*>(p.audio) + off + c * p.chan_stride) * p.input_scale;
+                if (p.channels > 1) acc = acc / (double)p.channels;
+                if (p.row_gain != nullptr) acc = gain * acc;
+                v = (R)acc;
+            } else {
+                const float sc = (float)p.input_scale;
+                float acc = p.audio_dtype == DAM_F32 ? __ldg(reinterpret_cast<const float*>(p.audio) + off) * sc
+                                                     : (float)__ldg(reinterpret_cast<const short*>(p.audio) + off) * sc;
+                for (int c = 1; c < p.channels; ++c) {
+                    const long long o2 = off + c * p.chan_stride;
+                    acc += p.audio_dtype == DAM_F32 ? __ldg(reinterpret_cast<const float*>(p.audio) + o2) * sc
+                                                    : (float)__ldg(reinterpret_cast<const short*>(p.audio) + o2) * sc;
+                }
+                if (p.channels > 1) acc = acc / (float)p.channels;
+                if (p.row_gain != nullptr) acc = (float)gain * acc;
+                v = (R)acc;
+            }
+            C z; z.x = v * s_win[i]; z.y = R(0);
+            s_buf[__brev((unsigned)i) >> (32 - log2n)] = z;
+        }
+        __syncthreads();
+        for (int st = 0; st < log2n; ++st) {
+            const int half = 1 << st;
+            for (int j = tid; j < n_fft / 2; j += kGenThreads) {
+                const int k = j & (half - 1);
+                const int i0 = ((j >> st) << (st + 1)) + k;
+                const C w = s_twd[k << (log2n - 1 - st)];
+                const C a = s_buf[i0], b = s_buf[i0 + half];
+                C tw; tw.x = b.x * w.x - b.y * w.y; tw.y = b.x * w.y + b.y * w.x;
+                C u, d; u.x = a.x + tw.x; u.y = a.y + tw.y; d.x = a.x - tw.x; d.y = a.y - tw.y;
+                s_buf[i0] = u; s_buf[i0 + half] = d;
+            }
+            __syncthreads();
+        }
+        for (int f = tid; f < bins; f += kGenThreads)
+            s_db[f * kGenFT + t] = (float)DbOut<R>::eval(s_buf[f].x, s_buf[f].y, p);
+        __syncthreads();
+    }
+    // coalesced-ish store: runs of nf consecutive frames per bin row
+    OUT* out_row = reinterpret_cast<OUT*>(p.out) + row * p.out_row_stride + t0;
+    for (int i = tid; i < bins * kGenFT; i += kGenThreads) {
+        const int f = i / kGenFT, t = i % kGenFT;
+        if (t < nf) out_row[(long long)f * T + t] = (OUT)s_db[i];
+    }
+    if (p.stats != nullptr) {
+        double sm = 0.0, sq = 0.0, cnt = 0.0;
+        for (int i = tid; i < bins * kGenFT; i += kGenThreads)
+            if (i % kGenFT < nf) { const double v = s_db[i]; sm += v; sq += v * v; cnt += 1.0; }
+        sm = dam_warp_sum(sm); sq = dam_warp_sum(sq); cnt = dam_warp_sum(cnt);
+        if ((tid & 31) == 0 && cnt > 0.0) { atomicAdd(p.stats, sm); atomicAdd(p.stats + 1, sq); atomicAdd(p.stats + 2, cnt); }
+    }
+}
+
+template <typename R, typename OUT>
+int launch_generic(const StftParams& p, int n_fft, cudaStream_t stream) {
+    int log2n = 0;
+    while ((1 << log2n) < n_fft) ++log2n;
+    int kGenFT = 8;
+    while (kGenFT > 1 && generic_smem_bytes<R>(n_fft, kGenFT) > 227 * 1024) kGenFT >>= 1;
+    const size_t smem = generic_smem_bytes<R>(n_fft, kGenFT);
+    if (smem > 227 * 1024) {
+        dam_set_error("n_fft=%d with %s arithmetic needs %zu B of shared memory (float64 compute supports n_fft <= 4096)",
+                      n_fft, sizeof(R) == 8 ? "float64" : "float32", smem);
+        return DAM_ERR_UNSUPPORTED;
+    }
+    auto kern = stft_db_generic_kernel<R, OUT>;
+    DAM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long tiles = (p.T + kGenFT - 1) / kGenFT;
+    DAM_CHECK_ARG(tiles < 0x7fffffffLL && p.n_rows <= 65535, "generic path: too many tiles or rows (> 65535 rows)");
+    dim3 grid((unsigned)tiles, (unsigned)p.n_rows);
+    kern<<<grid, kGenThreads, smem, stream>>>(p, n_fft, log2n, kGenFT);
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // Per-device twiddle tables T[k'][b] = s(k') * exp(-2 pi i b k' / 2048), s = 1 for k' in {0, 32},
 // 1/2 otherwise (the stage-1 codelet emits 2*Y for those slots).  Built once, in long double.
@@ -838,9 +964,9 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
                   "out_dtype must be F32, or F64 together with compute_dtype F64");
     DAM_CHECK_ARG(channels >= 1 && channels <= 64, "channels=%d out of range [1, 64]", channels);
     DAM_CHECK_ARG(n_rows >= 0 && n_samples >= 0, "negative size");
-    if (n_fft != kNfft) {
-        dam_set_error("n_fft=%d is not supported (this build instantiates n_fft=2048, the only size the "
-                      "reference uses: data/dataset.py:132)", n_fft);
+    if (n_fft < 64 || n_fft > 8192 || (n_fft & (n_fft - 1)) != 0) {
+        dam_set_error("n_fft=%d is not supported: window sizes are powers of two in [64, 8192] "
+                      "(2048, the only size the reference uses, has the fused fast path)", n_fft);
         return DAM_ERR_UNSUPPORTED;
     }
     DAM_CHECK_ARG(hop >= 1 && hop <= n_fft, "hop=%d must be in [1, n_fft]", hop);
@@ -850,10 +976,6 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     if (n_rows == 0) return DAM_OK;
     DAM_CHECK_ARG(n_samples > n_fft / 2,
                   "reflect padding needs n_samples > n_fft/2 (got %lld)", (long long)n_samples);
-
-    TwiddleTables* tw = nullptr;
-    int rc = get_twiddles(&tw);
-    if (rc != DAM_OK) return rc;
 
     StftParams p;
     p.audio = audio; p.audio_dtype = audio_dtype; p.channels = channels;
@@ -867,8 +989,17 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     p.floor_db_d = amin > 0.0 ? multiplier * log10(amin) : -INFINITY;
     p.floor_db = (float)p.floor_db_d;
     p.out = out; p.stats = stats;
-    p.out_row_stride = out_row_stride > 0 ? out_row_stride : (long long)kBins * p.T;
+    p.out_row_stride = out_row_stride > 0 ? out_row_stride : (long long)(n_fft / 2 + 1) * p.T;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (n_fft != kNfft) {
+        p.twiddle = nullptr;
+        p.tiles_per_row = 0; p.n_tiles = 0; p.tile_group = 1; p.l2_prefetch = 0;
+        if (compute_dtype == DAM_F32) return launch_generic<float, float>(p, n_fft, s);
+        return out_dtype == DAM_F32 ? launch_generic<double, float>(p, n_fft, s) : launch_generic<double, double>(p, n_fft, s);
+    }
+    TwiddleTables* tw = nullptr;
+    int rc = get_twiddles(&tw);
+    if (rc != DAM_OK) return rc;
     const bool st = stats != nullptr;
     if (compute_dtype == DAM_F32) {
         p.twiddle = tw->f32;

@@ -67,7 +67,10 @@ const char* dam_last_error(void);
  *   window       [n_fft] float32 analysis window (torch.hann_window(n_fft) in the reference;
  *                promoted to the compute dtype exactly as torch.stft does).
  *   n_fft, hop   window size and hop; frames are centred (reflect pad n_fft/2), so
- *                T = 1 + n_samples / hop and n_samples must exceed n_fft / 2.
+ *                T = 1 + n_samples / hop and n_samples must exceed n_fft / 2.  n_fft = 2048 (the
+ *                only size the reference uses) runs the fused register-resident kernel; other
+ *                powers of two in [64, 8192] run a plain shared-memory radix-2 kernel with the
+ *                same semantics; anything else returns DAM_ERR_UNSUPPORTED.  1 <= hop <= n_fft.
  *   amin, multiplier   dB = multiplier * log10(max(|X|, amin))   (1e-5 and 20 in the reference).
  *   compute_dtype  DAM_F32 or DAM_F64 arithmetic for the FFT (the reference's dtype follows its
  *                input: float32 on the inference path, float64 on the training path).

@@ -214,3 +214,39 @@ def test_no_writes_outside_the_output(cuda_device):
             assert not torch.isnan(body[:, :plane]).any()
             if stride != plane:
                 assert torch.isnan(body[:, plane:]).all()
+
+
+@pytest.mark.parametrize('n_fft,hop', [(1024, 256), (512, 512), (4096, 1024), (256, 100), (64, 64)])
+def test_other_window_sizes_generic_path(cuda_device, n_fft, hop):
+    """window_size is a runtime argument of compute_features (data/dataset.py:132); sizes other than
+    2048 go through the generic radix-2 kernel with the same semantics."""
+    x = synthetic.make_song(44, 2, 3 * n_fft + 1234, kind='music', dtype=np.float64)   # [2, 2, n]
+    win = torch.hann_window(n_fft)
+    ref = OF.compute_features(np.mean(x, axis=1), n_fft, hop, window=win.numpy())
+    got = run(x, n_fft=n_fft, hop=hop, channel_axis=-2, window=win.cuda())
+    assert got.shape == ref.shape == (2, n_fft // 2 + 1, 1 + x.shape[-1] // hop)
+    assert np.max(np.abs(got - ref)) <= 1e-4
+    got32 = run(x.astype(np.float32), n_fft=n_fft, hop=hop, channel_axis=-2, window=win.cuda())
+    truth = OF.compute_features(np.mean(x.astype(np.float32), axis=1).astype(np.float64), n_fft, hop, window=win.numpy())
+    amp_t, amp_g = 10.0 ** (truth / 20), 10.0 ** (got32.astype(np.float64) / 20)
+    assert np.max(np.abs(amp_g - amp_t) / amp_t.max(axis=1, keepdims=True)) <= 2e-6
+
+
+def test_window_1024_matches_reference_golden(cuda_device):
+    g = golden('features.npz')
+    got = run(g['in_w1024'], n_fft=1024, hop=256, window=torch.from_numpy(golden('window.npz')['hann_1024']).cuda())
+    assert got.shape == g['out_w1024'].shape
+    assert np.max(np.abs(got - g['out_w1024'])) <= 1e-4
+
+
+def test_window_8192_float32_and_unsupported_sizes(cuda_device):
+    x = synthetic.make_song(45, 1, 30000, kind='music', dtype=np.float32)[0, :1]
+    win = torch.hann_window(8192)
+    got = run(x, n_fft=8192, hop=2048, window=win.cuda())
+    truth = OF.compute_features(x.astype(np.float64), 8192, 2048, window=win.numpy())
+    amp_t, amp_g = 10.0 ** (truth / 20), 10.0 ** (got.astype(np.float64) / 20)
+    assert got.shape == (1, 4097, 15)
+    assert np.max(np.abs(amp_g - amp_t) / amp_t.max(axis=1, keepdims=True)) <= 4e-6
+    for bad in (1000, 32, 16384):
+        with pytest.raises(Exception):
+            F.stft_db(torch.zeros(1, 40000, device='cuda'), n_fft=bad, window=torch.ones(bad, device='cuda'))
