@@ -109,25 +109,36 @@ class ClockSampler:
 
 
 def cpu_reference_throughput(n_seg_sample, steps, warmup):
-    """The oracle port (oracle/cpu_reference.py) on the host cores, on a bounded sample of the workload."""
+    """The oracle port (oracle/cpu_reference.py) on the host cores, on a bounded sample of the workload.
+    Segments are independent, so they are spread over a thread pool with one worker per core (torch and
+    numpy release the GIL in their kernels; measured 2.4x faster than one segment at a time with
+    torch's own intra-op threads)."""
+    import concurrent.futures as cf
     import torch
     from oracle import cpu_reference as CR
     from deep_audio_mixer_b200 import synthetic
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    n_seg_sample = max(n_seg_sample, min(cores, N_SEG))
+    torch.set_num_threads(1)
     n = SECONDS * SR
+    nc = n // CHUNK_SAMPLES
     raw = np.stack([synthetic.make_song(synthetic.config_seed(2, i), N_STEMS, n, kind='white', dtype=np.float32)
                     for i in range(n_seg_sample)])
-    m = synth_m(n_seg_sample * (n // CHUNK_SAMPLES))
-    for _ in range(warmup):
-        CR.batch_step(raw[:1], GROUP, m, CHUNK_SAMPLES, HOP, SR)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        CR.batch_step(raw, GROUP, m, CHUNK_SAMPLES, HOP, SR)
-    dt = (time.perf_counter() - t0) / steps
+    m = synth_m(n_seg_sample * nc)
+
+    def one(b):
+        return CR.segment_step(raw[b], GROUP, m[b * nc:(b + 1) * nc], CHUNK_SAMPLES, HOP, SR)[2]
+
+    with cf.ThreadPoolExecutor(max_workers=cores) as ex:
+        for _ in range(warmup):
+            list(ex.map(one, range(min(cores, n_seg_sample))))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            list(ex.map(one, range(n_seg_sample)))
+        dt = (time.perf_counter() - t0) / steps
     stem_s = n_seg_sample * N_STEMS * SECONDS
-    return stem_s / dt, dt, cores, '%d of %d segments (%d stem-audio-s) per step, float32 features like the inference path' % (
-        n_seg_sample, N_SEG, stem_s)
+    return stem_s / dt, dt, cores, ('%d of %d segments (%d stem-audio-s) per step, one worker thread per core, '
+                                    'float32 features like the inference path') % (n_seg_sample, N_SEG, stem_s)
 
 
 def run_reference(args):
