@@ -347,28 +347,13 @@ struct StatAcc {
     }
 };
 
-// ---- stage 1 of one frame, executed by one warp (lane = b) -------------------------------------
-// x: the lane's 64 windowed samples.  Writes the 32 exchange rows of this frame (dst = row 0 of the
-// frame + lane) and, through the cross-lane DFT, the 16 bins 32 + 64 q straight to global memory
-// (out_frame = &out[row][0][t]).
+// k' = 32: y32 = Y_b[32] of lane b is real; bins 32 + 64 q = sum_b Y_b[32] W_64^b W_32^(bq) are a 32-point
+// DFT ACROSS the lanes of the warp (radix-2 DIF over shuffles; lane r ends with q = bitrev5(r), q < 16 are
+// the distinct bins) and go straight to global memory (out_frame = &out[row][0][t]).
 template <typename R, typename OUT, bool kStats>
-__device__ __forceinline__ void stage1_frame(R (&x)[64], typename Cx<R>::type* dst, OUT* out_frame, long long T,
-                                             const NyqConsts<R>& nq, const StftParams& p, int lane, StatAcc& st) {
-    using C = typename Cx<R>::type;
-    R sr[32], si[32];
-    dam_rfft64_packed<R>(x, sr, si);
-    {
-        C v; v.x = sr[0]; v.y = R(0);
-        dst[0] = v;                        // row 0: Y[0] (real)
-    }
-#pragma unroll
-    for (int k = 1; k < 32; ++k) {
-        C v; v.x = sr[k]; v.y = si[k];
-        dst[k * kRow] = v;
-    }
-    // k' = 32: Y_b[32] = si[0] is real; bins 32 + 64 q = sum_b Y_b[32] W_64^b W_32^(bq) are a 32-point
-    // DFT ACROSS the lanes of this warp (radix-2 DIF over shuffles; q < 16 are the distinct bins).
-    R vr = si[0] * nq.pre_r, vi = si[0] * nq.pre_i;
+__device__ __forceinline__ void nyq_bins(R y32, OUT* out_frame, long long T, const NyqConsts<R>& nq,
+                                         const StftParams& p, int lane, StatAcc& st) {
+    R vr = y32 * nq.pre_r, vi = y32 * nq.pre_i;
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         const int dist = 16 >> i;
@@ -392,6 +377,28 @@ __device__ __forceinline__ void stage1_frame(R (&x)[64], typename Cx<R>::type* d
         out_frame[(long long)nq.bin * T] = (OUT)db;
         if (kStats) st.add((float)db);
     }
+}
+
+// ---- stage 1 of one frame, executed by one warp (lane = b) -------------------------------------
+// x: the lane's 64 windowed samples.  Writes the 32 exchange rows of this frame (dst = row 0 of the
+// frame + lane) and, through the cross-lane DFT, the 16 bins 32 + 64 q straight to global memory
+// (out_frame = &out[row][0][t]).
+template <typename R, typename OUT, bool kStats>
+__device__ __forceinline__ void stage1_frame(R (&x)[64], typename Cx<R>::type* dst, OUT* out_frame, long long T,
+                                             const NyqConsts<R>& nq, const StftParams& p, int lane, StatAcc& st) {
+    using C = typename Cx<R>::type;
+    R sr[32], si[32];
+    dam_rfft64_packed<R>(x, sr, si);
+    {
+        C v; v.x = sr[0]; v.y = R(0);
+        dst[0] = v;                        // row 0: Y[0] (real)
+    }
+#pragma unroll
+    for (int k = 1; k < 32; ++k) {
+        C v; v.x = sr[k]; v.y = si[k];
+        dst[k * kRow] = v;
+    }
+    nyq_bins<R, OUT, kStats>(si[0], out_frame, T, nq, p, lane, st);
 }
 
 // ---- stage 2 of one (k', frame) pair, executed by one thread ------------------------------------
@@ -450,7 +457,64 @@ __device__ __forceinline__ void stage2_task(const typename Cx<R>::type* src, con
     if (kStats) st.fold();
 }
 
-template <typename R, typename OUT, bool kStats, int kFT>
+// ---- packed-complex forms of the two stages (float32): one complex value per 64-bit register,
+// arithmetic on sm_100's packed FP32 instructions (FADD2 / FMUL2 / FFMA2).  ptxas folds half swaps,
+// per-half signs and scalar broadcasts into operand modifiers, so a complex add is 1 instruction, a
+// twiddle butterfly 3 and a complex multiply 2 -- half the issue slots of the scalar codelets with the
+// same 64 data registers per thread (tools/gen_codelets.py, dam_cfft32_pc / dam_rfft64_pc).
+template <typename OUT, bool kStats>
+__device__ __forceinline__ void stage1_frame_pc(pk2 (&xp)[32], float2* dst, OUT* out_frame, long long T,
+                                                const NyqConsts<float>& nq, const StftParams& p, int lane, StatAcc& st) {
+    pk2 y0n, s[32];
+    dam_rfft64_pc(xp, y0n, s);
+    float y0, y32;
+    pk_split(y0n, y0, y32);
+    dst[0] = make_float2(y0, 0.f);                       // row 0: Y[0] (real)
+#pragma unroll
+    for (int k = 1; k < 32; ++k) *reinterpret_cast<pk2*>(dst + k * kRow) = s[k];
+    nyq_bins<float, OUT, kStats>(y32, out_frame, T, nq, p, lane, st);
+}
+
+template <typename OUT, bool kStats>
+__device__ __forceinline__ void stage2_task_pc(const float2* src, const float2* tw, OUT* out_frame, long long T, int kp,
+                                               const StftParams& p, StatAcc& st) {
+    pk2 z[32];
+    const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(src);     // two complex values per 128-bit load
+    const float4* w4 = reinterpret_cast<const float4*>(tw);
+#pragma unroll
+    for (int grp = 0; grp < 4; ++grp) {
+        ulonglong2 v[4];
+        float4 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { v[u] = s2[grp * 4 + u]; w[u] = w4[grp * 4 + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int b2 = grp * 4 + u;
+            // v * w = (vr wr - vi wi, vi wr + vr wi) = v * (wr, wr) + swap(v) * (-wi, wi)
+            z[2 * b2] = pk_fma(pk_swap(v[u].x), pk_make(-w[u].y, w[u].y), pk_mul(v[u].x, pk_c(w[u].x)));
+            z[2 * b2 + 1] = pk_fma(pk_swap(v[u].y), pk_make(-w[u].w, w[u].w), pk_mul(v[u].y, pk_c(w[u].z)));
+        }
+        asm volatile("" ::: "memory");
+    }
+    dam_cfft32_pc(z);
+    const long long stride = 64 * T;
+    OUT* o_lo = out_frame + kp * T;
+    OUT* o_hi = out_frame + (kNfft / 2 - kp) * T;
+    const bool mirror_ok = kp != 0;
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+        const bool valid = q <= 16 ? true : mirror_ok;
+        OUT* o = q < 16 ? o_lo + q * stride : o_hi - (q - 16) * stride;
+        float re, im;
+        pk_split(z[q], re, im);
+        const float db = DbOut<float>::eval(re, im, p);
+        if (valid) *o = (OUT)db;
+        if (kStats && valid) st.add(db);
+    }
+    if (kStats) st.fold();
+}
+
+template <typename R, typename OUT, bool kStats, int kFT, bool kPc = false>
 __global__ void __launch_bounds__(32 * kFT, sizeof(R) == 4 ? 16 / kFT : 1)
 stft_db_kernel(const StftParams p) {
     using C = typename Cx<R>::type;
@@ -520,7 +584,20 @@ stft_db_kernel(const StftParams p) {
         }
 
         // ---- stage 1: warp = frame, lane = b
-        {
+        if constexpr (kPc) {
+            pk2 xp[32];          // (x[2m], x[2m+1]) of the lane's 64 samples x[a] = frame[32a + lane]
+            if (warp < nf) {
+                const float* f = reinterpret_cast<const float*>(s_stage) + warp * hop + lane;
+                const float* w = reinterpret_cast<const float*>(s_win) + lane;
+#pragma unroll
+                for (int m = 0; m < 32; ++m)
+                    xp[m] = pk_mul(pk_make(f[64 * m], f[64 * m + 32]), pk_make(w[64 * m], w[64 * m + 32]));
+            }
+            __syncthreads();     // all frames are in registers; s_stage may now be overwritten
+            if (warp < nf)
+                stage1_frame_pc<OUT, kStats>(xp, reinterpret_cast<float2*>(s_xch) + warp * kXch + lane, out_row + warp, T,
+                                             nq, p, lane, st);
+        } else {
             R x[64];
             if (warp < nf) {
                 const R* f = s_stage + warp * hop + lane;
@@ -536,8 +613,13 @@ stft_db_kernel(const StftParams p) {
         // ---- stage 2: thread = (k' = tid / FT in 0..31, frame = tid % FT)
         {
             const int kp = tid / kFT, t = tid % kFT;
-            if (t < nf)
-                stage2_task<R, OUT, kStats>(s_xch + t * kXch + kp * kRow, s_tw + kp * kRow, out_row + t, T, kp, p, st);
+            if (t < nf) {
+                if constexpr (kPc)
+                    stage2_task_pc<OUT, kStats>(reinterpret_cast<const float2*>(s_xch) + t * kXch + kp * kRow,
+                                                reinterpret_cast<const float2*>(s_tw) + kp * kRow, out_row + t, T, kp, p, st);
+                else
+                    stage2_task<R, OUT, kStats>(s_xch + t * kXch + kp * kRow, s_tw + kp * kRow, out_row + t, T, kp, p, st);
+            }
         }
     }
     if (kStats) st.flush(p.stats, lane);
@@ -696,6 +778,199 @@ stft_db_pipe_kernel(const StftParams p) {
         }
     }
     if (kStats) st.flush(p.stats, lane);
+}
+
+// ==========================================================================================
+// Packed-pair variant (float32): every thread carries TWO frames in the halves of 64-bit registers
+// and the transforms run on sm_100's packed FP32 instructions (FADD2 / FMUL2 / FFMA2 with scalar
+// immediates and broadcast operands), which take ONE issue slot for two flops-pairs.  The scalar
+// kernel is instruction-issue bound with the FMA pipe 29 % busy (profiles/), so halving the issue
+// slots of the 57 % of instructions that are FP32 arithmetic is where the time is.
+//   tile = 16 frames, CTA = 8 warps, one CTA per SM (~200 registers per thread)
+//   stage 1: warp w transforms frames (w, w+8) of the tile, lane = b
+//   exchange: float4 (reA, reB, imA, imB) per (pair, k', b)
+//   stage 2: thread (k' = tid / 8, pair = tid % 8) transforms frames (pair, pair+8)
+constexpr int kX2Threads = 256;
+constexpr int kX2FT = 16;
+constexpr int kX2Pair = 32 * kRow + 1;      // float4 elements per frame pair (odd: conflict-free 128-bit loads)
+
+size_t x2_smem_bytes(int hop) {
+    const size_t xch = (size_t)(kX2FT / 2) * kX2Pair * sizeof(float4);
+    const size_t stage = ((size_t)(kX2FT - 1) * hop + kNfft) * sizeof(float);
+    return kNfft * sizeof(float) + (size_t)kKp * kRow * sizeof(float2) + (xch > stage ? xch : stage);
+}
+
+template <bool kStats>
+__global__ void __launch_bounds__(kX2Threads, 1)
+stft_db_x2_kernel(const StftParams p) {
+    using R = float;
+    using OUT = float;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_win = reinterpret_cast<float*>(smem_raw);                    // [2048]
+    float2* s_tw = reinterpret_cast<float2*>(s_win + kNfft);              // [33][34]
+    float4* s_xch = reinterpret_cast<float4*>(s_tw + kKp * kRow);         // [8 pairs][kX2Pair]
+    float* s_stage = reinterpret_cast<float*>(s_xch);                     // aliases s_xch: [15*hop + 2048]
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < kNfft; i += kX2Threads) s_win[i] = __ldg(p.window + i);
+    {
+        const float2* tw = reinterpret_cast<const float2*>(p.twiddle);
+        for (int i = tid; i < kKp * kRow; i += kX2Threads) s_tw[i] = tw[i];
+    }
+    NyqConsts<R> nq;
+    nq.init(lane);
+
+    const int hop = p.hop;
+    const long long T = p.T;
+    const int elem_bytes = p.audio_dtype == DAM_I16 ? 2 : (p.audio_dtype == DAM_F32 ? 4 : 8);
+    const unsigned tiles_per_row = (unsigned)p.tiles_per_row, n_tiles = (unsigned)p.n_tiles;
+    StatAcc st;
+
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned urow = tile / tiles_per_row;
+        const long long row = urow;
+        const long long t0 = (long long)(tile - urow * tiles_per_row) * kX2FT;
+        const int nf = (int)((T - t0) < kX2FT ? (T - t0) : kX2FT);
+        OUT* out_row = reinterpret_cast<OUT*>(p.out) + row * p.out_row_stride + t0;
+
+        __syncthreads();     // previous tile's stage 2 has finished reading s_xch (and tables are loaded)
+        {
+            const long long g0 = t0 * hop - kNfft / 2;
+            const int span = (nf - 1) * hop + kNfft;
+            if (p.audio_dtype == DAM_F32)      stage_tile<R, float, float, kX2Threads>(p, s_stage, row, g0, span, tid);
+            else if (p.audio_dtype == DAM_I16) stage_tile<R, float, short, kX2Threads>(p, s_stage, row, g0, span, tid);
+            else                               stage_tile<R, double, double, kX2Threads>(p, s_stage, row, g0, span, tid);
+        }
+        __syncthreads();
+        if (p.l2_prefetch) {
+            const unsigned nt = tile + gridDim.x;
+            if (nt < n_tiles) {
+                const unsigned nrow = nt / tiles_per_row;
+                const long long nt0 = (long long)(nt - nrow * tiles_per_row) * kX2FT;
+                const int nnf = (int)((T - nt0) < kX2FT ? (T - nt0) : kX2FT);
+                prefetch_tile<kX2Threads>(p, nrow, nt0 * hop - kNfft / 2, (nnf - 1) * hop + kNfft, elem_bytes, tid);
+            }
+        }
+
+        // ---- stage 1: warp w = frames (w, w + 8), lane = b
+        {
+            const bool vA = warp < nf, vB = warp + 8 < nf;
+            pk2 x[64];
+            if (vA) {
+                const float* fa = s_stage + warp * hop + lane;
+                const float* fb = vB ? fa + 8 * hop : fa;        // second half unused when the tile is short
+#pragma unroll
+                for (int a = 0; a < 64; ++a)
+                    x[a] = pk_mul(pk_make(fa[32 * a], fb[32 * a]), pk_c(s_win[32 * a + lane]));
+            }
+            __syncthreads();     // all frames are in registers; s_stage may now be overwritten
+            if (vA) {
+                pk2 sr[32], si[32];
+                dam_rfft64_packed_pk(x, sr, si);
+                float4* dst = s_xch + warp * kX2Pair + lane;
+                float y32a, y32b;
+                {
+                    float a, b;
+                    pk_split(sr[0], a, b);
+                    dst[0] = make_float4(a, b, 0.f, 0.f);               // row 0: Y[0] (real) of both frames
+                    pk_split(si[0], y32a, y32b);                         // Y[32] (real) of both frames
+                }
+#pragma unroll
+                for (int k = 1; k < 32; ++k) {
+                    float a, b, c, d;
+                    pk_split(sr[k], a, b);
+                    pk_split(si[k], c, d);
+                    dst[k * kRow] = make_float4(a, b, c, d);
+                }
+                nyq_bins<R, OUT, kStats>(y32a, out_row + warp, T, nq, p, lane, st);
+                if (vB) nyq_bins<R, OUT, kStats>(y32b, out_row + warp + 8, T, nq, p, lane, st);
+            }
+        }
+        __syncthreads();
+
+        // ---- stage 2: thread = (k' = tid / 8, pair = tid % 8) -> frames (pair, pair + 8)
+        {
+            const int kp = tid >> 3, pr = tid & 7;
+            const bool vA = pr < nf, vB = pr + 8 < nf;
+            if (vA) {
+                const float4* src = s_xch + pr * kX2Pair + kp * kRow;
+                const float2* tw = s_tw + kp * kRow;
+                pk2 sr[32], si[32];
+#pragma unroll
+                for (int grp = 0; grp < 4; ++grp) {
+                    float4 v[8];
+                    float4 w[4];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = src[grp * 8 + u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) w[u] = reinterpret_cast<const float4*>(tw)[grp * 4 + u];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int b = grp * 8 + u;
+                        const float wr = (u & 1) ? w[u >> 1].z : w[u >> 1].x;
+                        const float wi = (u & 1) ? w[u >> 1].w : w[u >> 1].y;
+                        const pk2 re = pk_make(v[u].x, v[u].y), im = pk_make(v[u].z, v[u].w);
+                        sr[b] = pk_sub(pk_mul(re, pk_c(wr)), pk_mul(im, pk_c(wi)));
+                        si[b] = pk_fma(re, pk_c(wi), pk_mul(im, pk_c(wr)));
+                    }
+                    asm volatile("" ::: "memory");
+                }
+                dam_cfft32_pk(sr, si);
+
+                const long long stride = 64 * T;
+                OUT* o_lo = out_row + pr + kp * T;
+                OUT* o_hi = out_row + pr + (kNfft / 2 - kp) * T;
+                const bool mirror_ok = kp != 0;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const bool valid = q <= 16 ? true : mirror_ok;
+                    OUT* o = q < 16 ? o_lo + q * stride : o_hi - (q - 16) * stride;
+                    float pa, pb;
+                    pk_split(pk_fma(sr[q], sr[q], pk_mul(si[q], si[q])), pa, pb);
+                    const float da = fmaxf(p.log_scale * lg2_approx(pa), p.floor_db);
+                    const float db = fmaxf(p.log_scale * lg2_approx(pb), p.floor_db);
+                    if (valid) {
+                        o[0] = da;
+                        if (vB) o[8] = db;
+                        if (kStats) { st.add(da); if (vB) st.add(db); }
+                    }
+                }
+                if (kStats) st.fold();
+            }
+        }
+    }
+    if (kStats) st.flush(p.stats, lane);
+}
+
+template <bool kStats>
+int launch_x2(StftParams p, cudaStream_t stream) {
+    p.tiles_per_row = (p.T + kX2FT - 1) / kX2FT;
+    p.n_tiles = p.tiles_per_row * p.n_rows;
+    DAM_CHECK_ARG(p.n_tiles < 0x7fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
+                  (long long)p.n_tiles);
+    p.tile_group = 1;
+    static const int pf_env = [] { const char* e = getenv("DAM_K1_PREFETCH"); return e ? atoi(e) : 1; }();
+    p.l2_prefetch = pf_env;
+    const size_t smem = x2_smem_bytes(p.hop);
+    auto kern = stft_db_x2_kernel<kStats>;
+    static std::mutex mu;
+    static bool configured[64] = {};
+    int dev = 0;
+    DAM_CHECK_CUDA(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!configured[dev]) {
+            DAM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            configured[dev] = true;
+        }
+    }
+    DAM_CHECK_ARG(smem <= 227 * 1024, "hop=%d needs %zu B of shared memory", p.hop, smem);
+    long long grid = dam_sm_count();
+    if (grid > p.n_tiles) grid = p.n_tiles;
+    kern<<<(unsigned)grid, kX2Threads, smem, stream>>>(p);
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
 }
 
 // ==========================================================================================
@@ -884,7 +1159,7 @@ size_t smem_bytes(int hop) {
     return kNfft * sizeof(R) + (size_t)kKp * kRow * sizeof(C) + (xch > stage ? xch : stage);
 }
 
-template <typename R, typename OUT, bool kStats, int kFT>
+template <typename R, typename OUT, bool kStats, int kFT, bool kPc = false>
 int launch(StftParams p, cudaStream_t stream) {
     constexpr int kThreads = 32 * kFT;
     p.tiles_per_row = (p.T + kFT - 1) / kFT;
@@ -896,7 +1171,7 @@ int launch(StftParams p, cudaStream_t stream) {
     static const int pf_env = [] { const char* e = getenv("DAM_K1_PREFETCH"); return e ? atoi(e) : 1; }();
     p.l2_prefetch = pf_env;
     const size_t smem = smem_bytes<R, kFT>(p.hop);
-    auto kern = stft_db_kernel<R, OUT, kStats, kFT>;
+    auto kern = stft_db_kernel<R, OUT, kStats, kFT, kPc>;
     static std::mutex mu;
     static bool configured[64] = {};
     static int blocks_per_sm[64] = {};
@@ -1013,11 +1288,20 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
         int ft = 8;
         if (ft_env == 4 || ft_env == 8 || ft_env == 16) ft = ft_env;
         else if (hop >= 1024 && (p.T % 8) != 0 && p.T >= 160) ft = 16;
+        // DAM_K1_PC=0 selects the scalar codelets (kept for A/B runs); the default uses the packed-complex
+        // (FFMA2) stage functions.
+        static const bool use_pc = [] { const char* e = getenv("DAM_K1_PC"); return !(e && atoi(e) == 0); }();
+        if (use_pc) {
+            if (ft == 16) return st ? launch<float, float, true, 16, true>(p, s) : launch<float, float, false, 16, true>(p, s);
+            if (ft == 8) return st ? launch<float, float, true, 8, true>(p, s) : launch<float, float, false, 8, true>(p, s);
+        }
         if (ft == 16) return st ? launch<float, float, true, 16>(p, s) : launch<float, float, false, 16>(p, s);
         // DAM_K1_PIPE=1 selects the warp-specialised mbarrier pipeline (hop <= 1024).  Measured on B200 it
         // is 10-35 % SLOWER than the phase-structured kernel: with tile-granular double buffering its 6+6
         // transform warps spend most of their time in mbarrier waits on each other (profiles/), so the
         // phase kernel stays the default.
+        static const bool use_x2 = [] { const char* e = getenv("DAM_K1_X2"); return e && atoi(e) == 1; }();
+        if (use_x2) return st ? launch_x2<true>(p, s) : launch_x2<false>(p, s);
         static const bool use_pipe = [] { const char* e = getenv("DAM_K1_PIPE"); return e && atoi(e) == 1; }();
         if (use_pipe && hop <= kPipeMaxHop) return st ? launch_pipe<true>(p, s) : launch_pipe<false>(p, s);
         if (ft == 8) return st ? launch<float, float, true, 8>(p, s) : launch<float, float, false, 8>(p, s);

@@ -298,6 +298,212 @@ def emit(g, outs, in_place_arrays):
     return lines, counts
 
 
+def emit_packed(g, outs, in_place_arrays):
+    """Same network on PACKED pairs (two independent transforms per thread, one per half of a 64-bit
+    register): every op becomes one sm_100 f32x2 instruction (FADD2 / FMUL2 / FFMA2 with a scalar
+    immediate), i.e. half the issue slots per transform."""
+    live = set()
+    stack = [v.n for _, v in outs if not v.is_zero()]
+    while stack:
+        i = stack.pop()
+        if i in live:
+            continue
+        live.add(i)
+        nd = g.nodes[i]
+        if nd[0] in ('add', 'sub'):
+            stack += [nd[1], nd[2]]
+        elif nd[0] == 'mul':
+            stack.append(nd[2])
+        elif nd[0] == 'fma':
+            stack += [nd[2], nd[3]]
+    counts = {'add': 0, 'mul': 0, 'fma': 0}
+    name = {}
+    lines = []
+    for i in sorted(live):
+        nd = g.nodes[i]
+        if nd[0] == 'in':
+            if in_place_arrays:
+                name[i] = 'i%d' % i
+                lines.append('const pk2 i%d = %s;' % (i, nd[1]))
+            else:
+                name[i] = nd[1]
+
+    def lit(c):
+        return 'pk_c(%sf)' % repr(float(np.float32(c)))
+
+    for i in sorted(live):
+        nd = g.nodes[i]
+        op = nd[0]
+        if op == 'in':
+            continue
+        name[i] = 't%d' % i
+        if op == 'add':
+            lines.append('const pk2 t%d = pk_add(%s, %s);' % (i, name[nd[1]], name[nd[2]]))
+            counts['add'] += 1
+        elif op == 'sub':
+            lines.append('const pk2 t%d = pk_sub(%s, %s);' % (i, name[nd[1]], name[nd[2]]))
+            counts['add'] += 1
+        elif op == 'mul':
+            lines.append('const pk2 t%d = pk_mul(%s, %s);' % (i, name[nd[2]], lit(nd[1])))
+            counts['mul'] += 1
+        elif op == 'fma':
+            lines.append('const pk2 t%d = pk_fma(%s, %s, %s);' % (i, name[nd[2]], lit(nd[1]), name[nd[3]]))
+            counts['fma'] += 1
+    for nm, v in outs:
+        if v.is_zero():
+            lines.append('%s = pk_c(0.0f);' % nm)
+        elif v.s < 0:
+            lines.append('%s = pk_mul(%s, pk_c(-1.0f));' % (nm, name[v.n]))
+            counts['mul'] += 1
+        else:
+            lines.append('%s = %s;' % (nm, name[v.n]))
+    return lines, counts
+
+
+# ---------------------------------------------------------------------------------------------------
+# Packed-COMPLEX codelets: one complex value = one 64-bit register (re in the low half, im in the high
+# half), arithmetic on sm_100's packed FP32 instructions.  ptxas folds half swaps and per-half signs
+# into FFMA2/FADD2 operand modifiers (.LO_HI, .NP/.PN) and equal-magnitude constant pairs into a scalar
+# immediate, so
+#   a +- b                       1 FADD2 each
+#   a +- (-i) b, a +- i b        1 FFMA2 each   (swap(b) * (+-1, -+1) + a)
+#   a +- w b, general twiddle    3 FFMA2        (tangent-factored: u = b + t*(-i or i)b ; a +- c*u')
+# i.e. 194 issue slots for a 32-point complex DFT instead of 388, with the SAME 64 data registers.
+class PC:
+    """Emitter that also evaluates every emitted value numerically (complex128) for verification."""
+
+    def __init__(self):
+        self.lines = []
+        self.n = 0
+        self.val = {}
+
+    def new(self, expr, value):
+        name = 'p%d' % self.n
+        self.n += 1
+        self.lines.append('const pk2 %s = %s;' % (name, expr))
+        self.val[name] = value
+        return name
+
+    def inp(self, name, value):
+        self.val[name] = value
+        return name
+
+    @staticmethod
+    def C(a, b):
+        return 'pk_make(%sf, %sf)' % (repr(float(np.float32(a))), repr(float(np.float32(b))))
+
+    def add(self, a, b):
+        return self.new('pk_add(%s, %s)' % (a, b), self.val[a] + self.val[b])
+
+    def sub(self, a, b):
+        return self.new('pk_sub(%s, %s)' % (a, b), self.val[a] - self.val[b])
+
+    def fma(self, x, ca, cb, y, swap=False, swap_y=False):
+        """(x or swap(x)) * (ca, cb) + (y or swap(y)), per half."""
+        xv = self.val[x]
+        xs = complex(xv.imag, xv.real) if swap else xv
+        yv = self.val[y]
+        ys = complex(yv.imag, yv.real) if swap_y else yv
+        value = complex(xs.real * ca, xs.imag * cb) + ys
+        xe = 'pk_swap(%s)' % x if swap else x
+        ye = 'pk_swap(%s)' % y if swap_y else y
+        return self.new('pk_fma(%s, %s, %s)' % (xe, self.C(ca, cb), ye), value)
+
+    def mul(self, x, ca, cb, swap=False):
+        xv = self.val[x]
+        xs = complex(xv.imag, xv.real) if swap else xv
+        xe = 'pk_swap(%s)' % x if swap else x
+        return self.new('pk_mul(%s, %s)' % (xe, self.C(ca, cb)), complex(xs.real * ca, xs.imag * cb))
+
+
+def pc_butterfly(e, a, b, num, den):
+    """(a + w b, a - w b), w = exp(-2 pi i num/den), on packed complex values."""
+    fr = Fraction(num, den) % 1
+    c, s = exact_cos_sin(num, den)
+    wr, wi = c, -s
+    if fr == 0:
+        return e.add(a, b), e.sub(a, b)
+    if fr == Fraction(1, 2):
+        return e.sub(a, b), e.add(a, b)
+    if fr == Fraction(1, 4):                       # w b = (bi, -br)
+        return e.fma(b, 1.0, -1.0, a, swap=True), e.fma(b, -1.0, 1.0, a, swap=True)
+    if fr == Fraction(3, 4):                       # w b = (-bi, br)
+        return e.fma(b, -1.0, 1.0, a, swap=True), e.fma(b, 1.0, -1.0, a, swap=True)
+    if abs(wr) >= abs(wi):
+        t = wi / wr                                # w b = wr (b + t (-bi, br))
+        u = e.fma(b, -t, t, b, swap=True)
+        return e.fma(u, wr, wr, a), e.fma(u, -wr, -wr, a)
+    t = wr / wi                                    # u = b + t (bi, -br); w b = wi (-ui, ur)
+    u = e.fma(b, t, -t, b, swap=True)
+    return e.fma(u, -wi, wi, a, swap=True), e.fma(u, wi, -wi, a, swap=True)
+
+
+def pc_fft(e, x):
+    n = len(x)
+    if n == 1:
+        return list(x)
+    ev = pc_fft(e, x[0::2])
+    od = pc_fft(e, x[1::2])
+    out = [None] * n
+    for k in range(n // 2):
+        out[k], out[k + n // 2] = pc_butterfly(e, ev[k], od[k], k, n)
+    return out
+
+
+def build_pc_cfft(n):
+    rng = np.random.default_rng(n)
+    e = PC()
+    zin = rng.normal(size=n) + 1j * rng.normal(size=n)
+    x = [e.inp('z[%d]' % i, zin[i]) for i in range(n)]
+    pre = ['const pk2 z%d_ = z[%d];' % (i, i) for i in range(n)]
+    e2 = PC()
+    x = [e2.inp('z%d_' % i, zin[i]) for i in range(n)]
+    out = pc_fft(e2, x)
+    ref = np.fft.fft(zin)
+    got = np.array([e2.val[o] for o in out])
+    assert np.max(np.abs(got - ref)) < 1e-5 * n, np.max(np.abs(got - ref))       # constants are float32
+    lines = pre + e2.lines + ['z[%d] = %s;' % (k, out[k]) for k in range(n)]
+    return lines, e2.n
+
+
+def build_pc_rfft(n2):
+    """n2 real samples given as n2/2 packed pairs xp[m] = (x[2m], x[2m+1]) -> slots:
+       y0n (lo = Y[0], hi = Y[n2/2], both real) and s[k] = 2*Y[k], k = 1..n2/2-1 (packed complex)."""
+    n = n2 // 2
+    rng = np.random.default_rng(n2)
+    xin = rng.normal(size=n2)
+    e = PC()
+    pre = ['const pk2 z%d_ = xp[%d];' % (m, m) for m in range(n)]
+    z = [e.inp('z%d_' % m, complex(xin[2 * m], xin[2 * m + 1])) for m in range(n)]
+    Z = pc_fft(e, z)
+    ref = np.fft.rfft(xin)
+    outs = []
+    # slot 0: (Zr + Zi, Zr - Zi) = Z0 * (1, -1) + swap(Z0)
+    y0n = e.fma(Z[0], 1.0, -1.0, Z[0], swap_y=True)
+    assert abs(e.val[y0n].real - ref[0].real) < 1e-4 and abs(e.val[y0n].imag - ref[n].real) < 1e-4
+    outs.append('y0n = %s;' % y0n)
+    for k in range(1, n // 2 + 1):
+        A, B = Z[k], Z[n - k]
+        if 2 * k == n:
+            yk = e.mul(A, 2.0, -2.0)                 # 2 conj(Z[n/2])
+            assert abs(e.val[yk] - 2 * ref[k]) < 1e-4
+            outs.append('s[%d] = %s;' % (k, yk))
+            continue
+        c, sn = exact_cos_sin(k, n2)
+        wr, wi = c, -sn
+        S = e.fma(B, 1.0, -1.0, A)                   # A + conj(B)
+        D = e.fma(B, -1.0, 1.0, A)                   # A - conj(B)
+        Sc = e.fma(A, 1.0, -1.0, B)                  # conj(A) + B = conj(S)
+        P0 = e.mul(D, wr, wr)
+        P = e.fma(D, -wi, wi, P0, swap=True)         # W * D
+        yk = e.fma(P, 1.0, -1.0, S, swap=True)       # S - i P
+        ynk = e.fma(P, -1.0, -1.0, Sc, swap=True)    # conj(S + i P) = conj(S) + (-Pi, -Pr)
+        assert abs(e.val[yk] - 2 * ref[k]) < 1e-4 and abs(e.val[ynk] - 2 * ref[n - k]) < 1e-4
+        outs.append('s[%d] = %s;' % (k, yk))
+        outs.append('s[%d] = %s;' % (n - k, ynk))
+    return pre + e.lines + outs, e.n
+
+
 def verify():
     rng = np.random.default_rng(0)
     for n in (8, 16, 32):
@@ -346,6 +552,36 @@ def main():
         parts.append('// %d real samples -> %d complex slots: slot 0 = (Y[0], Y[%d]); slot k = 2*Y[k].\n'
                      'template <typename R>\n__device__ __forceinline__ void dam_rfft%d_packed(const R (&x)[%d], R (&sr)[%d], R (&si)[%d]) {\n    %s\n}\n'
                      % (n2, n2 // 2, n2 // 2, n2, n2, n2 // 2, n2 // 2, '\n    '.join(lines)))
+    # ---- packed (f32x2) float-only variants
+    parts.append('// ---- packed pairs: two independent transforms per thread in the halves of 64-bit registers ----\n'
+                 'typedef unsigned long long pk2;\n'
+                 '__device__ __forceinline__ pk2 pk_make(float lo, float hi) { pk2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }\n'
+                 '__device__ __forceinline__ pk2 pk_c(float c) { return pk_make(c, c); }   // ptxas folds this into a scalar immediate / broadcast operand\n'
+                 '__device__ __forceinline__ void pk_split(pk2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }\n'
+                 '__device__ __forceinline__ pk2 pk_add(pk2 a, pk2 b) { pk2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }\n'
+                 '__device__ __forceinline__ pk2 pk_sub(pk2 a, pk2 b) { pk2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }\n'
+                 '__device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b) { pk2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }\n'
+                 '__device__ __forceinline__ pk2 pk_fma(pk2 a, pk2 b, pk2 c) { pk2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }\n')
+    g, outs = build_cfft(32)
+    lines, counts = emit_packed(g, outs, in_place_arrays=True)
+    summary.append('// dam_cfft32_pk: %d packed ops for TWO 32-point transforms' % sum(counts.values()))
+    parts.append('// In-place forward complex DFT of 32 points on packed pairs.\n'
+                 '__device__ __forceinline__ void dam_cfft32_pk(pk2 (&re)[32], pk2 (&im)[32]) {\n    %s\n}\n' % '\n    '.join(lines))
+    g, outs = build_rfft_packed(64)
+    lines, counts = emit_packed(g, outs, in_place_arrays=False)
+    summary.append('// dam_rfft64_packed_pk: %d packed ops for TWO 64-sample real transforms' % sum(counts.values()))
+    parts.append('// 64 real samples -> 32 complex slots (slot 0 = (Y[0], Y[32]); slot k = 2*Y[k]) on packed pairs.\n'
+                 '__device__ __forceinline__ void dam_rfft64_packed_pk(const pk2 (&x)[64], pk2 (&sr)[32], pk2 (&si)[32]) {\n    %s\n}\n' % '\n    '.join(lines))
+    # ---- packed-complex variants (one complex value per 64-bit register)
+    parts.append('__device__ __forceinline__ pk2 pk_swap(pk2 v) { float lo, hi; pk_split(v, lo, hi); return pk_make(hi, lo); }   // folded into an operand modifier\n')
+    lines, nops = build_pc_cfft(32)
+    summary.append('// dam_cfft32_pc: %d packed ops (one 32-point complex transform, packed complex registers)' % nops)
+    parts.append('// In-place forward complex DFT of 32 points; z[k] = (re, im) packed.\n'
+                 '__device__ __forceinline__ void dam_cfft32_pc(pk2 (&z)[32]) {\n    %s\n}\n' % '\n    '.join(lines))
+    lines, nops = build_pc_rfft(64)
+    summary.append('// dam_rfft64_pc: %d packed ops (64 real samples, packed complex registers)' % nops)
+    parts.append('// 64 real samples as 32 packed pairs xp[m] = (x[2m], x[2m+1]) -> y0n = (Y[0], Y[32]) and s[k] = 2*Y[k] (packed complex), k = 1..31.\n'
+                 '__device__ __forceinline__ void dam_rfft64_pc(const pk2 (&xp)[32], pk2& y0n, pk2 (&s)[32]) {\n    %s\n}\n' % '\n    '.join(lines))
     text = parts[0] + '\n' + '\n'.join(summary) + '\n\n' + '\n'.join(parts[1:])
     with open(OUT, 'w') as f:
         f.write(text)
