@@ -29,7 +29,7 @@ constexpr int kNfft = 2048;
 constexpr int kBins = kNfft / 2 + 1;
 // Frames per tile FT is a template parameter: a CTA has FT warps (stage 1: one warp per frame;
 // stage 2: 32 k' x FT frames = 32*FT thread tasks).  float32 uses FT = 8 with two CTAs per SM,
-// float64 FT = 8 with one.
+// float64 FT = 8 with one; FT = 16 (one 16-warp CTA per SM) is used for unaligned long rows at hop >= 1024.
 constexpr int kRow = 34;          // complex elements per k' row in the exchange / twiddle tables
 constexpr int kKp = 33;           // stage-2 tasks per frame
 
@@ -39,11 +39,10 @@ template <> struct Cx<double> { using type = double2; };
 // Exchange buffer: per frame 32 rows (k' = 0..31) of kRow complex values (k' = 32 never leaves
 // stage 1).  The per-frame stride, in complex elements, is chosen so the 128-bit stage-2 loads
 // (lane = frame + FT * (k' mod 32/FT)) are bank-conflict free:
-//   float  (two complex per load, row = 17 x 16 B): FT = 8 needs stride/2 odd, FT = 4 stride/2 = 2 mod 8
+//   float  (two complex per load, row = 17 x 16 B): stride/2 odd
 //   double (one complex per load):                  FT = 8 needs stride odd
 template <typename R, int FT> struct XchStride;
 template <> struct XchStride<float, 8>  { static constexpr int v = 32 * kRow + 2; };   // 1090
-template <> struct XchStride<float, 4>  { static constexpr int v = 32 * kRow + 4; };   // 1092
 template <> struct XchStride<float, 16> { static constexpr int v = 32 * kRow + 2; };   // 1090
 template <> struct XchStride<double, 8> { static constexpr int v = 32 * kRow + 1; };   // 1089
 
@@ -60,7 +59,6 @@ struct StftParams {
     int hop;
     long long T;                  // frames per row
     long long tiles_per_row, n_tiles;
-    int tile_group;               // consecutive tiles a CTA processes back to back
     int l2_prefetch;              // 1: prefetch the CTA's next tile into L2 while transforming this one
     float log_scale;              // multiplier/2 * log10(2): dB = log_scale * log2(|X|^2)
     float floor_db;               // multiplier * log10(amin), the clamp applied in the dB domain
@@ -544,16 +542,11 @@ stft_db_kernel(const StftParams p) {
     const unsigned tiles_per_row = (unsigned)p.tiles_per_row, n_tiles = (unsigned)p.n_tiles;
     StatAcc st;
 
-    // Tiles are dealt round-robin in GROUPS of p.tile_group consecutive tiles.  At any moment the resident
-    // CTAs work on adjacent groups, so their 32-byte output row segments complete whole DRAM sectors /
-    // lines in L2 together and their input halos hit in L2; inside a group the CTA itself completes the
-    // sectors that straddle two tiles (rows are T*4 bytes apart, not a multiple of 32 for T = 87 / 173).
-    // (A fully contiguous tile range per CTA was measured 5-40 % slower: every CTA then scatters 1025
+    // Tiles are dealt round-robin, so at any moment the resident CTAs work on ADJACENT tiles: their 32-byte
+    // output row segments complete whole DRAM sectors / lines in L2 together and their input halos hit in
+    // L2.  (A contiguous tile range per CTA was measured 5-40 % slower: every CTA then scatters 1025
     // isolated 32-byte segments per tile with nobody writing their neighbours.)
-    const unsigned G = (unsigned)p.tile_group;
-    const unsigned n_groups = (n_tiles + G - 1) / G;
-    for (unsigned grp = blockIdx.x; grp < n_groups; grp += gridDim.x)
-    for (unsigned tile = grp * G; tile < (grp + 1) * G && tile < n_tiles; ++tile) {
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const unsigned urow = tile / tiles_per_row;
         const long long row = urow;
         const long long t0 = (long long)(tile - urow * tiles_per_row) * kFT;
@@ -574,7 +567,7 @@ stft_db_kernel(const StftParams p) {
 
         // pull the next tile's samples towards L2 while this one is transformed
         if (p.l2_prefetch) {
-            const unsigned nt = (tile + 1 < (grp + 1) * G) ? tile + 1 : (grp + gridDim.x) * G;
+            const unsigned nt = tile + gridDim.x;
             if (nt < n_tiles) {
                 const unsigned nrow = nt / tiles_per_row;
                 const long long nt0 = (long long)(nt - nrow * tiles_per_row) * kFT;
@@ -623,354 +616,6 @@ stft_db_kernel(const StftParams p) {
         }
     }
     if (kStats) st.flush(p.stats, lane);
-}
-
-// ==========================================================================================
-// Warp-specialised, software-pipelined variant (float32, hop <= 1024): ONE CTA of 16 warps per SM.
-//   warps 12..15  loaders : stage tile i+1 (global -> prologue -> shared) while tile i is transformed;
-//                           their memory stalls no longer hold up any transform warp
-//   warps  0..5   stage 1 : frame slots of the CTA's tile stream, round-robin
-//   warps  6..11  stage 2 : (4 k' x 8 frames) tasks of the tile stream, round-robin
-// (one loader + three transform warps per SM sub-partition).  The staging buffer and the exchange
-// buffer are double-buffered and handed over with mbarriers (full/empty per buffer), so the three
-// roles run concurrently on different tiles instead of in barrier-separated phases.
-constexpr int kPipeThreads = 512;
-constexpr int kPipeS1 = 6, kPipeS2 = 6, kPipeLd = 4;
-constexpr int kPipeFT = 8;
-constexpr int kPipeMaxHop = 1024;
-constexpr int kPipeStageElems = (kPipeFT - 1) * kPipeMaxHop + kNfft;
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-    unsigned ok;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    } while (!ok);
-}
-
-constexpr size_t pipe_smem_bytes() {
-    return kNfft * sizeof(float) + (size_t)kKp * kRow * sizeof(float2) +
-           2 * (size_t)kPipeFT * XchStride<float, 8>::v * sizeof(float2) + 2 * (size_t)kPipeStageElems * sizeof(float) +
-           8 * sizeof(unsigned long long);
-}
-
-template <bool kStats>
-__global__ void __launch_bounds__(kPipeThreads, 1)
-stft_db_pipe_kernel(const StftParams p) {
-    using R = float;
-    using OUT = float;
-    using C = float2;
-    constexpr int kXch = XchStride<float, 8>::v;
-    constexpr int kFT = kPipeFT;
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    R* s_win = reinterpret_cast<R*>(smem_raw);                    // [2048]
-    C* s_tw = reinterpret_cast<C*>(s_win + kNfft);                // [33][34]
-    C* s_xch = s_tw + kKp * kRow;                                 // [2][kFT][kXch]
-    R* s_stage = reinterpret_cast<R*>(s_xch + 2 * kFT * kXch);    // [2][kPipeStageElems]
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(s_stage + 2 * kPipeStageElems);
-    unsigned long long* full_stage = bars;        // [2] loaders -> stage 1
-    unsigned long long* empty_stage = bars + 2;   // [2] stage 1 -> loaders
-    unsigned long long* full_xch = bars + 4;      // [2] stage 1 -> stage 2
-    unsigned long long* empty_xch = bars + 6;     // [2] stage 2 -> stage 1
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-
-    for (int i = tid; i < kNfft; i += kPipeThreads) s_win[i] = __ldg(p.window + i);
-    {
-        const C* tw = reinterpret_cast<const C*>(p.twiddle);
-        for (int i = tid; i < kKp * kRow; i += kPipeThreads) s_tw[i] = tw[i];
-    }
-    if (tid == 0) {
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(full_stage + b, kPipeLd);     // one arrival per loader warp
-            mbar_init(empty_stage + b, kFT);        // one per frame slot
-            mbar_init(full_xch + b, kFT);           // one per frame slot
-            mbar_init(empty_xch + b, kFT);          // one per stage-2 task (8 per tile)
-        }
-    }
-    __syncthreads();
-
-    const int hop = p.hop;
-    const long long T = p.T;
-    const unsigned tiles_per_row = (unsigned)p.tiles_per_row, n_tiles = (unsigned)p.n_tiles;
-    const unsigned n_local = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    StatAcc st;
-
-    if (warp >= kPipeS1 + kPipeS2) {
-        // ------------------------------------------------------------------ loaders
-        const int ltid = tid - (kPipeS1 + kPipeS2) * 32;
-        for (unsigned i = 0; i < n_local; ++i) {
-            const unsigned tile = blockIdx.x + i * gridDim.x;
-            const unsigned urow = tile / tiles_per_row;
-            const long long t0 = (long long)(tile - urow * tiles_per_row) * kFT;
-            const int nf = (int)((T - t0) < kFT ? (T - t0) : kFT);
-            const int b = i & 1;
-            mbar_wait(empty_stage + b, ((i >> 1) & 1) ^ 1);
-            R* dst = s_stage + b * kPipeStageElems;
-            const long long g0 = t0 * hop - kNfft / 2;
-            const int span = (nf - 1) * hop + kNfft;
-            if (p.audio_dtype == DAM_F32)      stage_tile<R, float, float, kPipeLd * 32>(p, dst, urow, g0, span, ltid);
-            else if (p.audio_dtype == DAM_I16) stage_tile<R, float, short, kPipeLd * 32>(p, dst, urow, g0, span, ltid);
-            else                               stage_tile<R, double, double, kPipeLd * 32>(p, dst, urow, g0, span, ltid);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_stage + b);
-        }
-    } else if (warp < kPipeS1) {
-        // ------------------------------------------------------------------ stage 1
-        NyqConsts<R> nq;
-        nq.init(lane);
-        for (unsigned g = warp; g < n_local * kFT; g += kPipeS1) {
-            const unsigned i = g >> 3;
-            const int t = g & 7;
-            const unsigned tile = blockIdx.x + i * gridDim.x;
-            const unsigned urow = tile / tiles_per_row;
-            const long long t0 = (long long)(tile - urow * tiles_per_row) * kFT;
-            const int nf = (int)((T - t0) < kFT ? (T - t0) : kFT);
-            const int b = i & 1;
-            const unsigned ph = (i >> 1) & 1;
-            R x[64];
-            mbar_wait(full_stage + b, ph);
-            if (t < nf) {
-                const R* f = s_stage + b * kPipeStageElems + t * hop + lane;
-#pragma unroll
-                for (int a = 0; a < 64; ++a) x[a] = f[32 * a] * s_win[32 * a + lane];
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty_stage + b);      // this slot's samples are in registers
-            mbar_wait(empty_xch + b, ph ^ 1);                 // stage 2 is done with tile i-2
-            if (t < nf) {
-                OUT* out_frame = reinterpret_cast<OUT*>(p.out) + (long long)urow * p.out_row_stride + t0 + t;
-                stage1_frame<R, OUT, kStats>(x, s_xch + (b * kFT + t) * kXch + lane, out_frame, T, nq, p, lane, st);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_xch + b);
-        }
-    } else {
-        // ------------------------------------------------------------------ stage 2
-        const int v = warp - kPipeS1;
-        for (unsigned g = v; g < n_local * 8; g += kPipeS2) {
-            const unsigned i = g >> 3;
-            const int j = g & 7;                                // k' group: k' = 4j .. 4j+3
-            const unsigned tile = blockIdx.x + i * gridDim.x;
-            const unsigned urow = tile / tiles_per_row;
-            const long long t0 = (long long)(tile - urow * tiles_per_row) * kFT;
-            const int nf = (int)((T - t0) < kFT ? (T - t0) : kFT);
-            const int b = i & 1;
-            mbar_wait(full_xch + b, (i >> 1) & 1);
-            const int kp = j * 4 + (lane >> 3), t = lane & 7;
-            if (t < nf) {
-                OUT* out_frame = reinterpret_cast<OUT*>(p.out) + (long long)urow * p.out_row_stride + t0 + t;
-                stage2_task<R, OUT, kStats>(s_xch + (b * kFT + t) * kXch + kp * kRow, s_tw + kp * kRow, out_frame, T,
-                                            kp, p, st);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty_xch + b);
-        }
-    }
-    if (kStats) st.flush(p.stats, lane);
-}
-
-// ==========================================================================================
-// Packed-pair variant (float32): every thread carries TWO frames in the halves of 64-bit registers
-// and the transforms run on sm_100's packed FP32 instructions (FADD2 / FMUL2 / FFMA2 with scalar
-// immediates and broadcast operands), which take ONE issue slot for two flops-pairs.  The scalar
-// kernel is instruction-issue bound with the FMA pipe 29 % busy (profiles/), so halving the issue
-// slots of the 57 % of instructions that are FP32 arithmetic is where the time is.
-//   tile = 16 frames, CTA = 8 warps, one CTA per SM (~200 registers per thread)
-//   stage 1: warp w transforms frames (w, w+8) of the tile, lane = b
-//   exchange: float4 (reA, reB, imA, imB) per (pair, k', b)
-//   stage 2: thread (k' = tid / 8, pair = tid % 8) transforms frames (pair, pair+8)
-constexpr int kX2Threads = 256;
-constexpr int kX2FT = 16;
-constexpr int kX2Pair = 32 * kRow + 1;      // float4 elements per frame pair (odd: conflict-free 128-bit loads)
-
-size_t x2_smem_bytes(int hop) {
-    const size_t xch = (size_t)(kX2FT / 2) * kX2Pair * sizeof(float4);
-    const size_t stage = ((size_t)(kX2FT - 1) * hop + kNfft) * sizeof(float);
-    return kNfft * sizeof(float) + (size_t)kKp * kRow * sizeof(float2) + (xch > stage ? xch : stage);
-}
-
-template <bool kStats>
-__global__ void __launch_bounds__(kX2Threads, 1)
-stft_db_x2_kernel(const StftParams p) {
-    using R = float;
-    using OUT = float;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_win = reinterpret_cast<float*>(smem_raw);                    // [2048]
-    float2* s_tw = reinterpret_cast<float2*>(s_win + kNfft);              // [33][34]
-    float4* s_xch = reinterpret_cast<float4*>(s_tw + kKp * kRow);         // [8 pairs][kX2Pair]
-    float* s_stage = reinterpret_cast<float*>(s_xch);                     // aliases s_xch: [15*hop + 2048]
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < kNfft; i += kX2Threads) s_win[i] = __ldg(p.window + i);
-    {
-        const float2* tw = reinterpret_cast<const float2*>(p.twiddle);
-        for (int i = tid; i < kKp * kRow; i += kX2Threads) s_tw[i] = tw[i];
-    }
-    NyqConsts<R> nq;
-    nq.init(lane);
-
-    const int hop = p.hop;
-    const long long T = p.T;
-    const int elem_bytes = p.audio_dtype == DAM_I16 ? 2 : (p.audio_dtype == DAM_F32 ? 4 : 8);
-    const unsigned tiles_per_row = (unsigned)p.tiles_per_row, n_tiles = (unsigned)p.n_tiles;
-    StatAcc st;
-
-    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned urow = tile / tiles_per_row;
-        const long long row = urow;
-        const long long t0 = (long long)(tile - urow * tiles_per_row) * kX2FT;
-        const int nf = (int)((T - t0) < kX2FT ? (T - t0) : kX2FT);
-        OUT* out_row = reinterpret_cast<OUT*>(p.out) + row * p.out_row_stride + t0;
-
-        __syncthreads();     // previous tile's stage 2 has finished reading s_xch (and tables are loaded)
-        {
-            const long long g0 = t0 * hop - kNfft / 2;
-            const int span = (nf - 1) * hop + kNfft;
-            if (p.audio_dtype == DAM_F32)      stage_tile<R, float, float, kX2Threads>(p, s_stage, row, g0, span, tid);
-            else if (p.audio_dtype == DAM_I16) stage_tile<R, float, short, kX2Threads>(p, s_stage, row, g0, span, tid);
-            else                               stage_tile<R, double, double, kX2Threads>(p, s_stage, row, g0, span, tid);
-        }
-        __syncthreads();
-        if (p.l2_prefetch) {
-            const unsigned nt = tile + gridDim.x;
-            if (nt < n_tiles) {
-                const unsigned nrow = nt / tiles_per_row;
-                const long long nt0 = (long long)(nt - nrow * tiles_per_row) * kX2FT;
-                const int nnf = (int)((T - nt0) < kX2FT ? (T - nt0) : kX2FT);
-                prefetch_tile<kX2Threads>(p, nrow, nt0 * hop - kNfft / 2, (nnf - 1) * hop + kNfft, elem_bytes, tid);
-            }
-        }
-
-        // ---- stage 1: warp w = frames (w, w + 8), lane = b
-        {
-            const bool vA = warp < nf, vB = warp + 8 < nf;
-            pk2 x[64];
-            if (vA) {
-                const float* fa = s_stage + warp * hop + lane;
-                const float* fb = vB ? fa + 8 * hop : fa;        // second half unused when the tile is short
-#pragma unroll
-                for (int a = 0; a < 64; ++a)
-                    x[a] = pk_mul(pk_make(fa[32 * a], fb[32 * a]), pk_c(s_win[32 * a + lane]));
-            }
-            __syncthreads();     // all frames are in registers; s_stage may now be overwritten
-            if (vA) {
-                pk2 sr[32], si[32];
-                dam_rfft64_packed_pk(x, sr, si);
-                float4* dst = s_xch + warp * kX2Pair + lane;
-                float y32a, y32b;
-                {
-                    float a, b;
-                    pk_split(sr[0], a, b);
-                    dst[0] = make_float4(a, b, 0.f, 0.f);               // row 0: Y[0] (real) of both frames
-                    pk_split(si[0], y32a, y32b);                         // Y[32] (real) of both frames
-                }
-#pragma unroll
-                for (int k = 1; k < 32; ++k) {
-                    float a, b, c, d;
-                    pk_split(sr[k], a, b);
-                    pk_split(si[k], c, d);
-                    dst[k * kRow] = make_float4(a, b, c, d);
-                }
-                nyq_bins<R, OUT, kStats>(y32a, out_row + warp, T, nq, p, lane, st);
-                if (vB) nyq_bins<R, OUT, kStats>(y32b, out_row + warp + 8, T, nq, p, lane, st);
-            }
-        }
-        __syncthreads();
-
-        // ---- stage 2: thread = (k' = tid / 8, pair = tid % 8) -> frames (pair, pair + 8)
-        {
-            const int kp = tid >> 3, pr = tid & 7;
-            const bool vA = pr < nf, vB = pr + 8 < nf;
-            if (vA) {
-                const float4* src = s_xch + pr * kX2Pair + kp * kRow;
-                const float2* tw = s_tw + kp * kRow;
-                pk2 sr[32], si[32];
-#pragma unroll
-                for (int grp = 0; grp < 4; ++grp) {
-                    float4 v[8];
-                    float4 w[4];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = src[grp * 8 + u];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) w[u] = reinterpret_cast<const float4*>(tw)[grp * 4 + u];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int b = grp * 8 + u;
-                        const float wr = (u & 1) ? w[u >> 1].z : w[u >> 1].x;
-                        const float wi = (u & 1) ? w[u >> 1].w : w[u >> 1].y;
-                        const pk2 re = pk_make(v[u].x, v[u].y), im = pk_make(v[u].z, v[u].w);
-                        sr[b] = pk_sub(pk_mul(re, pk_c(wr)), pk_mul(im, pk_c(wi)));
-                        si[b] = pk_fma(re, pk_c(wi), pk_mul(im, pk_c(wr)));
-                    }
-                    asm volatile("" ::: "memory");
-                }
-                dam_cfft32_pk(sr, si);
-
-                const long long stride = 64 * T;
-                OUT* o_lo = out_row + pr + kp * T;
-                OUT* o_hi = out_row + pr + (kNfft / 2 - kp) * T;
-                const bool mirror_ok = kp != 0;
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const bool valid = q <= 16 ? true : mirror_ok;
-                    OUT* o = q < 16 ? o_lo + q * stride : o_hi - (q - 16) * stride;
-                    float pa, pb;
-                    pk_split(pk_fma(sr[q], sr[q], pk_mul(si[q], si[q])), pa, pb);
-                    const float da = fmaxf(p.log_scale * lg2_approx(pa), p.floor_db);
-                    const float db = fmaxf(p.log_scale * lg2_approx(pb), p.floor_db);
-                    if (valid) {
-                        o[0] = da;
-                        if (vB) o[8] = db;
-                        if (kStats) { st.add(da); if (vB) st.add(db); }
-                    }
-                }
-                if (kStats) st.fold();
-            }
-        }
-    }
-    if (kStats) st.flush(p.stats, lane);
-}
-
-template <bool kStats>
-int launch_x2(StftParams p, cudaStream_t stream) {
-    p.tiles_per_row = (p.T + kX2FT - 1) / kX2FT;
-    p.n_tiles = p.tiles_per_row * p.n_rows;
-    DAM_CHECK_ARG(p.n_tiles < 0x7fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
-                  (long long)p.n_tiles);
-    p.tile_group = 1;
-    static const int pf_env = [] { const char* e = getenv("DAM_K1_PREFETCH"); return e ? atoi(e) : 1; }();
-    p.l2_prefetch = pf_env;
-    const size_t smem = x2_smem_bytes(p.hop);
-    auto kern = stft_db_x2_kernel<kStats>;
-    static std::mutex mu;
-    static bool configured[64] = {};
-    int dev = 0;
-    DAM_CHECK_CUDA(cudaGetDevice(&dev));
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (!configured[dev]) {
-            DAM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            configured[dev] = true;
-        }
-    }
-    DAM_CHECK_ARG(smem <= 227 * 1024, "hop=%d needs %zu B of shared memory", p.hop, smem);
-    long long grid = dam_sm_count();
-    if (grid > p.n_tiles) grid = p.n_tiles;
-    kern<<<(unsigned)grid, kX2Threads, smem, stream>>>(p);
-    DAM_CHECK_CUDA(cudaGetLastError());
-    return DAM_OK;
 }
 
 // ==========================================================================================
@@ -1166,8 +811,6 @@ int launch(StftParams p, cudaStream_t stream) {
     p.n_tiles = p.tiles_per_row * p.n_rows;
     DAM_CHECK_ARG(p.n_tiles < 0x7fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
                   (long long)p.n_tiles);
-    static const int group_env = [] { const char* e = getenv("DAM_K1_GROUP"); return e ? atoi(e) : 0; }();
-    p.tile_group = group_env > 0 ? group_env : 1;
     static const int pf_env = [] { const char* e = getenv("DAM_K1_PREFETCH"); return e ? atoi(e) : 1; }();
     p.l2_prefetch = pf_env;
     const size_t smem = smem_bytes<R, kFT>(p.hop);
@@ -1191,31 +834,6 @@ int launch(StftParams p, cudaStream_t stream) {
     long long grid = (long long)dam_sm_count() * occ;
     if (grid > p.n_tiles) grid = p.n_tiles;
     kern<<<(unsigned)grid, kThreads, smem, stream>>>(p);
-    DAM_CHECK_CUDA(cudaGetLastError());
-    return DAM_OK;
-}
-
-template <bool kStats>
-int launch_pipe(StftParams p, cudaStream_t stream) {
-    p.tiles_per_row = (p.T + kPipeFT - 1) / kPipeFT;
-    p.n_tiles = p.tiles_per_row * p.n_rows;
-    DAM_CHECK_ARG(p.n_tiles < 0x0fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
-                  (long long)p.n_tiles);
-    auto kern = stft_db_pipe_kernel<kStats>;
-    static std::mutex mu;
-    static bool configured[64] = {};
-    int dev = 0;
-    DAM_CHECK_CUDA(cudaGetDevice(&dev));
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (!configured[dev]) {
-            DAM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem_bytes()));
-            configured[dev] = true;
-        }
-    }
-    long long grid = dam_sm_count();
-    if (grid > p.n_tiles) grid = p.n_tiles;
-    kern<<<(unsigned)grid, kPipeThreads, pipe_smem_bytes(), stream>>>(p);
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }
@@ -1268,7 +886,7 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (n_fft != kNfft) {
         p.twiddle = nullptr;
-        p.tiles_per_row = 0; p.n_tiles = 0; p.tile_group = 1; p.l2_prefetch = 0;
+        p.tiles_per_row = 0; p.n_tiles = 0; p.l2_prefetch = 0;
         if (compute_dtype == DAM_F32) return launch_generic<float, float>(p, n_fft, s);
         return out_dtype == DAM_F32 ? launch_generic<double, float>(p, n_fft, s) : launch_generic<double, double>(p, n_fft, s);
     }
@@ -1278,34 +896,21 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     const bool st = stats != nullptr;
     if (compute_dtype == DAM_F32) {
         p.twiddle = tw->f32;
-        // frames per tile of the float32 kernel: 8 (two CTAs of 8 warps per SM).  DAM_FT_F32=4 selects
-        // four CTAs of 4 warps -- measured 2-3x SLOWER on B200 (16-byte output segments, 16 KB of L1
-        // left beside 212 KB of shared memory); kept selectable for profiling only.
+        // Frames per tile: 8 (two 8-warp CTAs per SM) by default.  16 (one 16-warp CTA per SM) writes 64-byte
+        // row segments: measured +15 % when rows are not sector aligned (T % 8 != 0) at hop >= 1024, -17 %
+        // when they are, -4 % at hop 512; it also wastes more of a short row's last tile.  DAM_FT_F32 = 8 | 16
+        // overrides the choice, DAM_K1_PC=0 selects the scalar codelets instead of the packed-complex ones.
         static const int ft_env = [] { const char* e = getenv("DAM_FT_F32"); return e ? atoi(e) : 0; }();
-        // Default 8 frames per tile (two 8-warp CTAs per SM).  16 frames per tile (one 16-warp CTA per SM)
-        // writes 64-byte row segments: measured +15 % when rows are not sector aligned (T % 8 != 0) at
-        // hop >= 1024, -17 % when they are, -4 % at hop 512; it also wastes more of a short row's last tile.
-        int ft = 8;
-        if (ft_env == 4 || ft_env == 8 || ft_env == 16) ft = ft_env;
-        else if (hop >= 1024 && (p.T % 8) != 0 && p.T >= 160) ft = 16;
-        // DAM_K1_PC=0 selects the scalar codelets (kept for A/B runs); the default uses the packed-complex
-        // (FFMA2) stage functions.
         static const bool use_pc = [] { const char* e = getenv("DAM_K1_PC"); return !(e && atoi(e) == 0); }();
+        int ft = 8;
+        if (ft_env == 8 || ft_env == 16) ft = ft_env;
+        else if (hop >= 1024 && (p.T % 8) != 0 && p.T >= 160) ft = 16;
         if (use_pc) {
             if (ft == 16) return st ? launch<float, float, true, 16, true>(p, s) : launch<float, float, false, 16, true>(p, s);
-            if (ft == 8) return st ? launch<float, float, true, 8, true>(p, s) : launch<float, float, false, 8, true>(p, s);
+            return st ? launch<float, float, true, 8, true>(p, s) : launch<float, float, false, 8, true>(p, s);
         }
         if (ft == 16) return st ? launch<float, float, true, 16>(p, s) : launch<float, float, false, 16>(p, s);
-        // DAM_K1_PIPE=1 selects the warp-specialised mbarrier pipeline (hop <= 1024).  Measured on B200 it
-        // is 10-35 % SLOWER than the phase-structured kernel: with tile-granular double buffering its 6+6
-        // transform warps spend most of their time in mbarrier waits on each other (profiles/), so the
-        // phase kernel stays the default.
-        static const bool use_x2 = [] { const char* e = getenv("DAM_K1_X2"); return e && atoi(e) == 1; }();
-        if (use_x2) return st ? launch_x2<true>(p, s) : launch_x2<false>(p, s);
-        static const bool use_pipe = [] { const char* e = getenv("DAM_K1_PIPE"); return e && atoi(e) == 1; }();
-        if (use_pipe && hop <= kPipeMaxHop) return st ? launch_pipe<true>(p, s) : launch_pipe<false>(p, s);
-        if (ft == 8) return st ? launch<float, float, true, 8>(p, s) : launch<float, float, false, 8>(p, s);
-        return st ? launch<float, float, true, 4>(p, s) : launch<float, float, false, 4>(p, s);
+        return st ? launch<float, float, true, 8>(p, s) : launch<float, float, false, 8>(p, s);
     }
     p.twiddle = tw->f64;
     if (out_dtype == DAM_F32) return st ? launch<double, float, true, 8>(p, s) : launch<double, float, false, 8>(p, s);

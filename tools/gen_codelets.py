@@ -552,8 +552,8 @@ def main():
         parts.append('// %d real samples -> %d complex slots: slot 0 = (Y[0], Y[%d]); slot k = 2*Y[k].\n'
                      'template <typename R>\n__device__ __forceinline__ void dam_rfft%d_packed(const R (&x)[%d], R (&sr)[%d], R (&si)[%d]) {\n    %s\n}\n'
                      % (n2, n2 // 2, n2 // 2, n2, n2, n2 // 2, n2 // 2, '\n    '.join(lines)))
-    # ---- packed (f32x2) float-only variants
-    parts.append('// ---- packed pairs: two independent transforms per thread in the halves of 64-bit registers ----\n'
+    # ---- packed (f32x2) float-only helpers
+    parts.append('// ---- sm_100 packed FP32 (f32x2) helpers: a 64-bit register holds two floats ----\n'
                  'typedef unsigned long long pk2;\n'
                  '__device__ __forceinline__ pk2 pk_make(float lo, float hi) { pk2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }\n'
                  '__device__ __forceinline__ pk2 pk_c(float c) { return pk_make(c, c); }   // ptxas folds this into a scalar immediate / broadcast operand\n'
@@ -562,16 +562,6 @@ def main():
                  '__device__ __forceinline__ pk2 pk_sub(pk2 a, pk2 b) { pk2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }\n'
                  '__device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b) { pk2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }\n'
                  '__device__ __forceinline__ pk2 pk_fma(pk2 a, pk2 b, pk2 c) { pk2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }\n')
-    g, outs = build_cfft(32)
-    lines, counts = emit_packed(g, outs, in_place_arrays=True)
-    summary.append('// dam_cfft32_pk: %d packed ops for TWO 32-point transforms' % sum(counts.values()))
-    parts.append('// In-place forward complex DFT of 32 points on packed pairs.\n'
-                 '__device__ __forceinline__ void dam_cfft32_pk(pk2 (&re)[32], pk2 (&im)[32]) {\n    %s\n}\n' % '\n    '.join(lines))
-    g, outs = build_rfft_packed(64)
-    lines, counts = emit_packed(g, outs, in_place_arrays=False)
-    summary.append('// dam_rfft64_packed_pk: %d packed ops for TWO 64-sample real transforms' % sum(counts.values()))
-    parts.append('// 64 real samples -> 32 complex slots (slot 0 = (Y[0], Y[32]); slot k = 2*Y[k]) on packed pairs.\n'
-                 '__device__ __forceinline__ void dam_rfft64_packed_pk(const pk2 (&x)[64], pk2 (&sr)[32], pk2 (&si)[32]) {\n    %s\n}\n' % '\n    '.join(lines))
     # ---- packed-complex variants (one complex value per 64-bit register)
     parts.append('__device__ __forceinline__ pk2 pk_swap(pk2 v) { float lo, hi; pk_split(v, lo, hi); return pk_make(hi, lo); }   // folded into an operand modifier\n')
     lines, nops = build_pc_cfft(32)
