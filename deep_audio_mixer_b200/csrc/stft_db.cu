@@ -20,6 +20,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <cstdio>
 #include <mutex>
 #include <vector>
 
@@ -310,24 +311,26 @@ template <> __device__ __forceinline__ double shfl_xor_r<double>(double v, int m
 // Per-lane constants of the cross-lane 32-point DFT that turns Y_b[32] into bins 32 + 64 q:
 // pre-twiddle W_64^lane and the decimation-in-frequency twiddles of the distance-16/8/4 stages
 // (1 for the lower lane of a pair).  Lane r ends up holding q = bitrev5(r).
+// They live in a [8][32] shared-memory table, not in registers: as eight loop-invariant registers
+// ptxas spilled them to local memory around the codelets, and the reloads missed L1 93 % of the
+// time (profiles/: 18 % of warp stall samples were L2 round trips of those reloads).
+constexpr int kNyqTab = 8 * 32;
 template <typename R>
-struct NyqConsts {
-    R pre_r, pre_i, wr[3], wi[3];
-    int bin;
-    __device__ __forceinline__ void init(int lane) {
+__device__ __forceinline__ void nyq_table_init(R* tab, int tid) {
+    if (tid < 32) {
+        const int lane = tid;
         double sn, cs;
         sincospi(-(double)lane / 32.0, &sn, &cs);
-        pre_r = (R)cs; pre_i = (R)sn;
+        tab[0 * 32 + lane] = (R)cs; tab[1 * 32 + lane] = (R)sn;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             const int dist = 16 >> i;
             const bool upper = (lane & dist) != 0;
             sincospi(upper ? -(double)((lane & (dist - 1)) * (16 / dist)) / 16.0 : 0.0, &sn, &cs);
-            wr[i] = (R)cs; wi[i] = (R)sn;
+            tab[(2 + 2 * i) * 32 + lane] = (R)cs; tab[(3 + 2 * i) * 32 + lane] = (R)sn;
         }
-        bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);
     }
-};
+}
 
 struct StatAcc {
     float sum = 0.f, sq = 0.f;
@@ -345,13 +348,17 @@ struct StatAcc {
     }
 };
 
+// Output stores are plain stores: streaming (st.global.cs) stores measured 2 % slower on the phase kernel.
+template <typename OUT> __device__ __forceinline__ void store_out(OUT* o, OUT v) { *o = v; }
+
 // k' = 32: y32 = Y_b[32] of lane b is real; bins 32 + 64 q = sum_b Y_b[32] W_64^b W_32^(bq) are a 32-point
 // DFT ACROSS the lanes of the warp (radix-2 DIF over shuffles; lane r ends with q = bitrev5(r), q < 16 are
 // the distinct bins) and go straight to global memory (out_frame = &out[row][0][t]).
 template <typename R, typename OUT, bool kStats>
-__device__ __forceinline__ void nyq_bins(R y32, OUT* out_frame, long long T, const NyqConsts<R>& nq,
+__device__ __forceinline__ void nyq_bins(R y32, OUT* out_frame, long long T, const R* nq,
                                          const StftParams& p, int lane, StatAcc& st) {
-    R vr = y32 * nq.pre_r, vi = y32 * nq.pre_i;
+    nq += lane;
+    R vr = y32 * nq[0], vi = y32 * nq[32];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         const int dist = 16 >> i;
@@ -360,8 +367,9 @@ __device__ __forceinline__ void nyq_bins(R y32, OUT* out_frame, long long T, con
         const R tr = upper ? pr - vr : vr + pr;
         const R ti = upper ? pi - vi : vi + pi;
         if (i < 3) {
-            vr = tr * nq.wr[i] - ti * nq.wi[i];
-            vi = tr * nq.wi[i] + ti * nq.wr[i];
+            const R wr = nq[(2 + 2 * i) * 32], wi = nq[(3 + 2 * i) * 32];
+            vr = tr * wr - ti * wi;
+            vi = tr * wi + ti * wr;
         } else if (i == 3) {                 // W_4^j: j = 1 on the upper lane of odd pairs -> -i
             const bool rot = upper && (lane & 1);
             vr = rot ? ti : tr;
@@ -372,7 +380,8 @@ __device__ __forceinline__ void nyq_bins(R y32, OUT* out_frame, long long T, con
     }
     const typename DbOut<R>::type db = DbOut<R>::eval(vr, vi, p);
     if ((lane & 1) == 0) {
-        out_frame[(long long)nq.bin * T] = (OUT)db;
+        const int bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);
+        store_out<OUT>(out_frame + (long long)bin * T, (OUT)db);
         if (kStats) st.add((float)db);
     }
 }
@@ -383,7 +392,7 @@ __device__ __forceinline__ void nyq_bins(R y32, OUT* out_frame, long long T, con
 // (out_frame = &out[row][0][t]).
 template <typename R, typename OUT, bool kStats>
 __device__ __forceinline__ void stage1_frame(R (&x)[64], typename Cx<R>::type* dst, OUT* out_frame, long long T,
-                                             const NyqConsts<R>& nq, const StftParams& p, int lane, StatAcc& st) {
+                                             const R* nq, const StftParams& p, int lane, StatAcc& st) {
     using C = typename Cx<R>::type;
     R sr[32], si[32];
     dam_rfft64_packed<R>(x, sr, si);
@@ -449,7 +458,7 @@ __device__ __forceinline__ void stage2_task(const typename Cx<R>::type* src, con
         const bool valid = q <= 16 ? true : mirror_ok;
         OUT* o = q < 16 ? o_lo + q * stride : o_hi - (q - 16) * stride;
         const typename DbOut<R>::type db = DbOut<R>::eval(sr[q], si[q], p);
-        if (valid) *o = (OUT)db;
+        if (valid) store_out<OUT>(o, (OUT)db);
         if (kStats && valid) st.add((float)db);
     }
     if (kStats) st.fold();
@@ -462,7 +471,7 @@ __device__ __forceinline__ void stage2_task(const typename Cx<R>::type* src, con
 // same 64 data registers per thread (tools/gen_codelets.py, dam_cfft32_pc / dam_rfft64_pc).
 template <typename OUT, bool kStats>
 __device__ __forceinline__ void stage1_frame_pc(pk2 (&xp)[32], float2* dst, OUT* out_frame, long long T,
-                                                const NyqConsts<float>& nq, const StftParams& p, int lane, StatAcc& st) {
+                                                const float* nq, const StftParams& p, int lane, StatAcc& st) {
     pk2 y0n, s[32];
     dam_rfft64_pc(xp, y0n, s);
     float y0, y32;
@@ -473,7 +482,7 @@ __device__ __forceinline__ void stage1_frame_pc(pk2 (&xp)[32], float2* dst, OUT*
     nyq_bins<float, OUT, kStats>(y32, out_frame, T, nq, p, lane, st);
 }
 
-template <typename OUT, bool kStats>
+template <typename OUT, bool kStats, bool kGlobalTw = false>
 __device__ __forceinline__ void stage2_task_pc(const float2* src, const float2* tw, OUT* out_frame, long long T, int kp,
                                                const StftParams& p, StatAcc& st) {
     pk2 z[32];
@@ -484,7 +493,7 @@ __device__ __forceinline__ void stage2_task_pc(const float2* src, const float2* 
         ulonglong2 v[4];
         float4 w[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { v[u] = s2[grp * 4 + u]; w[u] = w4[grp * 4 + u]; }
+        for (int u = 0; u < 4; ++u) { v[u] = s2[grp * 4 + u]; w[u] = kGlobalTw ? __ldg(w4 + grp * 4 + u) : w4[grp * 4 + u]; }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int b2 = grp * 4 + u;
@@ -506,7 +515,7 @@ __device__ __forceinline__ void stage2_task_pc(const float2* src, const float2* 
         float re, im;
         pk_split(z[q], re, im);
         const float db = DbOut<float>::eval(re, im, p);
-        if (valid) *o = (OUT)db;
+        if (valid) store_out<OUT>(o, (OUT)db);
         if (kStats && valid) st.add(db);
     }
     if (kStats) st.fold();
@@ -522,7 +531,8 @@ stft_db_kernel(const StftParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     R* s_win = reinterpret_cast<R*>(smem_raw);                    // [2048]
     C* s_tw = reinterpret_cast<C*>(s_win + kNfft);                // [33][34]
-    C* s_xch = s_tw + kKp * kRow;                                 // [kFT][kXch]
+    R* s_nq = reinterpret_cast<R*>(s_tw + kKp * kRow);            // [8][32]
+    C* s_xch = reinterpret_cast<C*>(s_nq + kNyqTab);              // [kFT][kXch]
     R* s_stage = reinterpret_cast<R*>(s_xch);                     // aliases s_xch: [(kFT-1)*hop + 2048]
 
     const int tid = threadIdx.x;
@@ -533,8 +543,8 @@ stft_db_kernel(const StftParams p) {
         const C* tw = reinterpret_cast<const C*>(p.twiddle);
         for (int i = tid; i < kKp * kRow; i += kThreads) s_tw[i] = tw[i];
     }
-    NyqConsts<R> nq;
-    nq.init(lane);
+    nyq_table_init<R>(s_nq, tid);
+    const R* nq = s_nq;
 
     const int hop = p.hop;
     const long long T = p.T;
@@ -578,9 +588,12 @@ stft_db_kernel(const StftParams p) {
 
         // ---- stage 1: warp = frame, lane = b
         if constexpr (kPc) {
-            pk2 xp[32];          // (x[2m], x[2m+1]) of the lane's 64 samples x[a] = frame[32a + lane]
-            if (warp < nf) {
-                const float* f = reinterpret_cast<const float*>(s_stage) + warp * hop + lane;
+            // (x[2m], x[2m+1]) of the lane's 64 samples x[a] = frame[32a + lane].  Loaded by every warp (the
+            // idle warps of a row's last tile re-read its last frame): assigning them under `warp < nf` makes
+            // the registers loop-carried and ptxas spills part of them to local memory.
+            pk2 xp[32];
+            {
+                const float* f = reinterpret_cast<const float*>(s_stage) + (warp < nf ? warp : nf - 1) * hop + lane;
                 const float* w = reinterpret_cast<const float*>(s_win) + lane;
 #pragma unroll
                 for (int m = 0; m < 32; ++m)
@@ -592,8 +605,8 @@ stft_db_kernel(const StftParams p) {
                                              nq, p, lane, st);
         } else {
             R x[64];
-            if (warp < nf) {
-                const R* f = s_stage + warp * hop + lane;
+            {
+                const R* f = s_stage + (warp < nf ? warp : nf - 1) * hop + lane;
 #pragma unroll
                 for (int a = 0; a < 64; ++a) x[a] = f[32 * a] * s_win[32 * a + lane];
             }
@@ -613,6 +626,172 @@ stft_db_kernel(const StftParams p) {
                 else
                     stage2_task<R, OUT, kStats>(s_xch + t * kXch + kp * kRow, s_tw + kp * kRow, out_row + t, T, kp, p, st);
             }
+        }
+    }
+    if (kStats) st.flush(p.stats, lane);
+}
+
+// ==========================================================================================
+// Asynchronously staged variant (float32 source and arithmetic, mono or planar stereo, unit scale,
+// FT = 8, packed-complex codelets).  The phase kernel above stalls every warp of the CTA on the
+// global loads of its next tile (18 % of warp stall samples, profiles/).  Here the staging buffer does
+// NOT alias the exchange buffer: as soon as stage 1 has the samples of tile i in registers, one thread
+// hands the raw samples of tile i+1 to the TMA unit (cp.async.bulk, one contiguous run per channel,
+// completion on an mbarrier), and they land in shared memory while both transform stages of tile i
+// run.  A stereo tile is averaged in place by a short shared->shared pass ((L + R) * 0.5, numpy's
+// float32 mean over two channels); tiles that touch a row end (reflection) or are not 16-byte aligned
+// take the synchronous path of the phase kernel into the same buffer.
+// kTabSmem = false keeps the window and twiddle tables in global memory (L1-resident, 17 KB) to make
+// room for the staging buffer of stereo hop-512 / mono hop-1024 tiles with two CTAs per SM.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes),
+                 "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kAsyncFT = 8;
+
+// shared-memory bytes of the async kernel: [tables] + exchange + staging (channels x span floats) + mbarrier
+inline size_t async_smem_bytes(int hop, int channels, bool tab_smem) {
+    const size_t tables = tab_smem ? kNfft * sizeof(float) + (size_t)kKp * kRow * sizeof(float2) + kNyqTab * sizeof(float) : 0;
+    const size_t xch = (size_t)kAsyncFT * XchStride<float, 8>::v * sizeof(float2);
+    const size_t stage = (size_t)channels * ((size_t)(kAsyncFT - 1) * hop + kNfft) * sizeof(float);
+    return tables + xch + stage + 16;
+}
+
+template <bool kStats, bool kTabSmem>
+__global__ void __launch_bounds__(32 * kAsyncFT, 2)
+stft_db_async_kernel(const StftParams p) {
+    using OUT = float;
+    constexpr int kFT = kAsyncFT;
+    constexpr int kXch = XchStride<float, 8>::v;
+    constexpr int kThreads = 32 * kFT;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_win = reinterpret_cast<float*>(smem_raw);                                  // [2048]   (kTabSmem)
+    float2* s_tw = reinterpret_cast<float2*>(s_win + (kTabSmem ? kNfft : 0));           // [33][34] (kTabSmem)
+    float* s_nq = reinterpret_cast<float*>(s_tw + (kTabSmem ? kKp * kRow : 0));         // [8][32]
+    float2* s_xch = reinterpret_cast<float2*>(s_nq + (kTabSmem ? kNyqTab : 0));         // [kFT][kXch]
+    float* s_stage = reinterpret_cast<float*>(s_xch + kFT * kXch);                      // [C][span_max]
+    const int hop = p.hop;
+    const int span_max = (kFT - 1) * hop + kNfft;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_stage + (size_t)p.channels * span_max);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (kTabSmem) {
+        for (int i = tid; i < kNfft; i += kThreads) s_win[i] = __ldg(p.window + i);
+        const float2* tw = reinterpret_cast<const float2*>(p.twiddle);
+        for (int i = tid; i < kKp * kRow; i += kThreads) s_tw[i] = tw[i];
+    }
+    if (kTabSmem) nyq_table_init<float>(s_nq, tid);
+    const float* nq = kTabSmem ? s_nq : reinterpret_cast<const float*>(p.twiddle) + 2 * kKp * kRow;
+    if (tid == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const long long T = p.T;
+    const long long n = p.n_samples;
+    const int C = p.channels;
+    const unsigned tiles_per_row = (unsigned)p.tiles_per_row, n_tiles = (unsigned)p.n_tiles;
+    const float* win = kTabSmem ? s_win : p.window;
+    const float2* twp = kTabSmem ? s_tw : reinterpret_cast<const float2*>(p.twiddle);
+    StatAcc st;
+
+    // Hand tile `t` to the TMA unit if it is an interior, 16-byte aligned tile; uniform over the CTA.
+    auto prefetch = [&](unsigned t) -> bool {
+        if (t >= n_tiles) return false;
+        const unsigned r = t / tiles_per_row;
+        const long long f0 = (long long)(t - r * tiles_per_row) * kFT;
+        const int cnt = (int)((T - f0) < kFT ? (T - f0) : kFT);
+        const long long g0 = f0 * hop - kNfft / 2;
+        const int span = (cnt - 1) * hop + kNfft;
+        if (g0 < 0 || g0 + span > n) return false;
+        const float* src = reinterpret_cast<const float*>(p.audio) + row_offset(p, r) + g0;
+        if ((reinterpret_cast<unsigned long long>(src) & 15ull) != 0 || (span & 3) != 0) return false;
+        if (C == 2 && ((p.chan_stride * 4) & 15ll) != 0) return false;
+        if (tid == 0) {
+            const unsigned bytes = (unsigned)span * 4u;
+            mbar_expect_tx(bar, bytes * (unsigned)C);
+            bulk_g2s(s_stage, src, bytes, bar);
+            if (C == 2) bulk_g2s(s_stage + span_max, src + p.chan_stride, bytes, bar);
+        }
+        return true;
+    };
+
+    unsigned phase = 0;
+    bool in_flight = prefetch(blockIdx.x);
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned urow = tile / tiles_per_row;
+        const long long row = urow;
+        const long long t0 = (long long)(tile - urow * tiles_per_row) * kFT;
+        const int nf = (int)((T - t0) < kFT ? (T - t0) : kFT);
+        OUT* out_row = reinterpret_cast<OUT*>(p.out) + row * p.out_row_stride + t0;
+        const int span = (nf - 1) * hop + kNfft;
+
+        if (in_flight) {
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            if (C == 2) {
+                // in-place channel mean over the left-channel run; every 16-byte vector has one owner
+                float4* l4 = reinterpret_cast<float4*>(s_stage);
+                const float4* r4 = reinterpret_cast<const float4*>(s_stage + span_max);
+                for (int v = tid; v < span / 4; v += kThreads) {
+                    float4 a = l4[v];
+                    const float4 b = r4[v];
+                    a.x = (a.x + b.x) * 0.5f; a.y = (a.y + b.y) * 0.5f; a.z = (a.z + b.z) * 0.5f; a.w = (a.w + b.w) * 0.5f;
+                    l4[v] = a;
+                }
+                __syncthreads();
+            }
+        } else {
+            stage_tile<float, float, float, kThreads>(p, s_stage, row, t0 * hop - kNfft / 2, span, tid);
+            __syncthreads();
+        }
+
+        // ---- stage 1 loads: warp = frame, lane = b
+        pk2 xp[32];
+        {
+            const float* f = s_stage + (warp < nf ? warp : nf - 1) * hop + lane;
+            const float* w = win + lane;
+#pragma unroll
+            for (int m = 0; m < 32; ++m) {
+                const float w0 = kTabSmem ? w[64 * m] : __ldg(w + 64 * m);
+                const float w1 = kTabSmem ? w[64 * m + 32] : __ldg(w + 64 * m + 32);
+                xp[m] = pk_mul(pk_make(f[64 * m], f[64 * m + 32]), pk_make(w0, w1));
+            }
+        }
+        fence_proxy_async();     // order this thread's generic accesses to s_stage before the TMA writes
+        __syncthreads();         // every frame is in registers (and stage 2 of the previous tile is done)
+
+        in_flight = prefetch(tile + gridDim.x);
+
+        if (warp < nf)
+            stage1_frame_pc<OUT, kStats>(xp, s_xch + warp * kXch + lane, out_row + warp, T, nq, p, lane, st);
+        __syncthreads();
+
+        // ---- stage 2: thread = (k' = tid / FT in 0..31, frame = tid % FT)
+        {
+            const int kp = tid / kFT, t = tid % kFT;
+            if (t < nf)
+                stage2_task_pc<OUT, kStats, !kTabSmem>(s_xch + t * kXch + kp * kRow, twp + kp * kRow, out_row + t, T, kp, p, st);
         }
     }
     if (kStats) st.flush(p.stats, lane);
@@ -783,6 +962,25 @@ int get_twiddles(TwiddleTables** out) {
                 hf[kp * kRow + b] = make_float2((float)(s * c), (float)(-s * sn));
             }
         }
+        // [8][32] per-lane constants of the cross-lane DFT (nyq_table_init) behind the float table, for the
+        // kernel variant that keeps its tables in global memory
+        {
+            const long double pi = 3.141592653589793238462643383279502884L;
+            auto snap = [](long double v) { return fabsl(v) < 1e-17L ? 0.0L : v; };     // cos/sin(pi/2 k) exactly
+            std::vector<float> nq(kNyqTab, 0.f);
+            for (int lane = 0; lane < 32; ++lane) {
+                nq[0 * 32 + lane] = (float)snap(cosl(-pi * lane / 32.0L));
+                nq[1 * 32 + lane] = (float)snap(sinl(-pi * lane / 32.0L));
+                for (int i = 0; i < 3; ++i) {
+                    const int dist = 16 >> i;
+                    const bool upper = (lane & dist) != 0;
+                    const long double a = upper ? -pi * (long double)((lane & (dist - 1)) * (16 / dist)) / 16.0L : 0.0L;
+                    nq[(2 + 2 * i) * 32 + lane] = (float)snap(cosl(a));
+                    nq[(3 + 2 * i) * 32 + lane] = (float)snap(sinl(a));
+                }
+            }
+            for (int i = 0; i < kNyqTab / 2; ++i) hf.push_back(make_float2(nq[2 * i], nq[2 * i + 1]));
+        }
         float2* df = nullptr;
         double2* dd = nullptr;
         DAM_CHECK_CUDA(cudaMalloc(&df, hf.size() * sizeof(float2)));
@@ -801,7 +999,7 @@ size_t smem_bytes(int hop) {
     using C = typename Cx<R>::type;
     const size_t xch = (size_t)kFT * XchStride<R, kFT>::v * sizeof(C);
     const size_t stage = ((size_t)(kFT - 1) * hop + kNfft) * sizeof(R);
-    return kNfft * sizeof(R) + (size_t)kKp * kRow * sizeof(C) + (xch > stage ? xch : stage);
+    return kNfft * sizeof(R) + (size_t)kKp * kRow * sizeof(C) + kNyqTab * sizeof(R) + (xch > stage ? xch : stage);
 }
 
 template <typename R, typename OUT, bool kStats, int kFT, bool kPc = false>
@@ -833,9 +1031,57 @@ int launch(StftParams p, cudaStream_t stream) {
     (void)blocks_per_sm;
     long long grid = (long long)dam_sm_count() * occ;
     if (grid > p.n_tiles) grid = p.n_tiles;
+    static const bool trace = getenv("DAM_K1_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[dam] stft_db_kernel FT=%d pc=%d f%d smem=%zu occ=%d hop=%d C=%d T=%lld\n", kFT, (int)kPc,
+                       (int)sizeof(R) * 8, smem, occ, p.hop, p.channels, (long long)p.T);
     kern<<<(unsigned)grid, kThreads, smem, stream>>>(p);
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
+}
+
+// Async kernel launch: returns DAM_OK after launching, or 1 when the shape does not fit two CTAs per SM
+// (the caller then uses the phase kernel).
+template <bool kStats>
+int launch_async(StftParams p, cudaStream_t stream, int force_tab) {
+    constexpr int kThreads = 32 * kAsyncFT;
+    p.tiles_per_row = (p.T + kAsyncFT - 1) / kAsyncFT;
+    p.n_tiles = p.tiles_per_row * p.n_rows;
+    DAM_CHECK_ARG(p.n_tiles < 0x7fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
+                  (long long)p.n_tiles);
+    p.l2_prefetch = 0;
+    static std::mutex mu;
+    static bool configured[64] = {};
+    int dev = 0;
+    DAM_CHECK_CUDA(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!configured[dev]) {
+            DAM_CHECK_CUDA(cudaFuncSetAttribute(stft_db_async_kernel<kStats, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            DAM_CHECK_CUDA(cudaFuncSetAttribute(stft_db_async_kernel<kStats, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            DAM_CHECK_CUDA(cudaFuncSetAttribute(stft_db_async_kernel<kStats, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            DAM_CHECK_CUDA(cudaFuncSetAttribute(stft_db_async_kernel<kStats, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            configured[dev] = true;
+        }
+    }
+    for (int tab = 1; tab >= 0; --tab) {
+        if (force_tab >= 0 && tab != force_tab) continue;
+        const size_t smem = async_smem_bytes(p.hop, p.channels, tab != 0);
+        if (smem > 227 * 1024) continue;
+        int occ = 0;
+        if (tab) DAM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stft_db_async_kernel<kStats, true>, kThreads, smem));
+        else     DAM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stft_db_async_kernel<kStats, false>, kThreads, smem));
+        if (occ < 2) continue;
+        long long grid = (long long)dam_sm_count() * 2;
+        if (grid > p.n_tiles) grid = p.n_tiles;
+        static const bool trace = getenv("DAM_K1_TRACE") != nullptr;
+        if (trace) fprintf(stderr, "[dam] stft_db_async_kernel tables=%s smem=%zu hop=%d C=%d T=%lld\n", tab ? "smem" : "global",
+                           smem, p.hop, p.channels, (long long)p.T);
+        if (tab) stft_db_async_kernel<kStats, true><<<(unsigned)grid, kThreads, smem, stream>>>(p);
+        else     stft_db_async_kernel<kStats, false><<<(unsigned)grid, kThreads, smem, stream>>>(p);
+        DAM_CHECK_CUDA(cudaGetLastError());
+        return DAM_OK;
+    }
+    return 1;
 }
 
 }  // namespace
@@ -905,6 +1151,20 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
         int ft = 8;
         if (ft_env == 8 || ft_env == 16) ft = ft_env;
         else if (hop >= 1024 && (p.T % 8) != 0 && p.T >= 160) ft = 16;
+        // TMA-staged kernel: measured +7..10 % on mono rows whose length is a multiple of 8 frames (sector-aligned
+        // output rows) at hop >= 512, neutral on stereo, and 4..27 % SLOWER on unaligned rows (T = 173, 87), where
+        // every 32-byte output segment straddles two sectors and the phase kernel's lock-step CTAs cope better.
+        // DAM_K1_ASYNC: 0 = never, 1 (default) = where it measured faster, 2 / 3 / 4 = wherever it applies with
+        // the tables in shared memory / in global memory / wherever they fit.
+        static const int async_env = [] { const char* e = getenv("DAM_K1_ASYNC"); return e ? atoi(e) : 1; }();
+        const bool async_ok = use_pc && ft == 8 && audio_dtype == DAM_F32 && (channels == 1 || channels == 2) &&
+                              input_scale == 1.0 && row_gain == nullptr && samp_stride == 1 && (hop % 4) == 0;
+        const bool async_wins = channels == 1 && (p.T % 8) == 0 && hop >= 512;
+        if (async_ok && (async_env >= 2 || (async_env == 1 && async_wins))) {
+            const int force = async_env == 2 ? 1 : (async_env == 3 ? 0 : -1);
+            const int rc2 = st ? launch_async<true>(p, s, force) : launch_async<false>(p, s, force);
+            if (rc2 <= 0) return rc2;
+        }
         if (use_pc) {
             if (ft == 16) return st ? launch<float, float, true, 16, true>(p, s) : launch<float, float, false, 16, true>(p, s);
             return st ? launch<float, float, true, 8, true>(p, s) : launch<float, float, false, 8, true>(p, s);

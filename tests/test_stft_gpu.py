@@ -250,3 +250,72 @@ def test_window_8192_float32_and_unsupported_sizes(cuda_device):
     for bad in (1000, 32, 16384):
         with pytest.raises(Exception):
             F.stft_db(torch.zeros(1, 40000, device='cuda'), n_fft=bad, window=torch.ones(bad, device='cuda'))
+
+
+# ---- TMA-staged kernel (stft_db_async_kernel): chosen by default for mono float32 rows of 8k frames ----
+@pytest.mark.parametrize('n,hop', [(512 * 175, 512), (1024 * 39 + 500, 1024), (220500, 1024), (512 * 23, 512)])
+def test_async_staged_kernel_matches_oracle(cuda_device, n, hop):
+    assert (1 + n // hop) % 8 == 0
+    x = synthetic.make_song(77, 3, n, kind='music', dtype=np.float32)[:, 0]         # [3, n] float32
+    ref = oracle(x.astype(np.float64), hop=hop)
+    got = run(x, hop=hop)
+    peak = 10.0 ** (ref.max() / 20.0)
+    err = np.abs(10.0 ** (got.astype(np.float64) / 20.0) - 10.0 ** (ref / 20.0)).max()
+    assert err <= 1e-6 * peak, (err, peak)
+    # unaligned row starts (row stride not a multiple of 4 samples) fall back per tile inside the kernel
+    base = torch.from_numpy(synthetic.make_song(78, 1, 3 * (n + 1), kind='white', dtype=np.float32)[0, 0]).cuda()
+    rows = base[:3 * (n + 1)].reshape(3, n + 1)[:, :n]
+    got2 = F.stft_db(rows, hop=hop, window=torch.from_numpy(W).cuda()).cpu().numpy()
+    ref2 = oracle(rows.cpu().numpy().astype(np.float64), hop=hop)
+    peak2 = 10.0 ** (ref2.max() / 20.0)
+    assert np.abs(10.0 ** (got2.astype(np.float64) / 20.0) - 10.0 ** (ref2 / 20.0)).max() <= 1e-6 * peak2
+
+
+def test_async_staged_kernel_guard_bands(cuda_device):
+    for n, hop, rows in ((512 * 175, 512, 5), (1024 * 23, 1024, 3)):
+        T = 1 + n // hop
+        assert T % 8 == 0
+        plane = 1025 * T
+        x = torch.randn(rows, n, device='cuda', dtype=torch.float32)
+        guard = 4096
+        buf = torch.full((guard + rows * plane + guard,), float('nan'), device='cuda')
+        F.stft_db(x, hop=hop, out=buf[guard:guard + rows * plane])
+        torch.cuda.synchronize()
+        assert torch.isnan(buf[:guard]).all() and torch.isnan(buf[guard + rows * plane:]).all()
+        assert not torch.isnan(buf[guard:guard + rows * plane]).any()
+
+
+_AB_CHILD = r'''
+import hashlib, sys, numpy as np, torch
+sys.path.insert(0, %r)
+from deep_audio_mixer_b200 import features as F
+g = torch.Generator(device='cuda').manual_seed(5)
+h = hashlib.sha1()
+for rows, ch, n, hop in ((7, 1, 88200, 512), (5, 2, 88200, 512), (4, 1, 176400, 1024), (6, 1, 89600, 512),
+                         (3, 2, 89600, 512), (9, 1, 220500, 1024), (2, 1, 30001, 512), (3, 1, 44100, 256)):
+    x = torch.randn((rows, ch, n) if ch > 1 else (rows, n), device='cuda', generator=g) * 0.2
+    kw = {'channel_axis': -2} if ch > 1 else {}
+    stats = torch.zeros(3, dtype=torch.float64, device='cuda')
+    out = F.stft_db(x, hop=hop, stats=stats, **kw)
+    h.update(out.cpu().numpy().tobytes()); h.update(stats.cpu().numpy().tobytes()[16:])
+    out = F.stft_db(x, hop=hop, **kw)
+    h.update(out.cpu().numpy().tobytes())
+print('DIGEST', h.hexdigest())
+'''
+
+
+def test_async_and_phase_kernels_are_bit_identical(cuda_device):
+    """The staging mode is read once per process (DAM_K1_ASYNC), so each mode runs in a child process:
+    phase kernel only, the default choice, and the TMA-staged kernel forced wherever it applies (stereo,
+    unaligned rows, with the tables in shared or global memory) must produce the same bytes."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for mode in ('0', '1', '2', '3', '4'):
+        env = dict(os.environ, DAM_K1_ASYNC=mode)
+        r = subprocess.run([sys.executable, '-c', _AB_CHILD % root], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests[mode] = [l for l in r.stdout.splitlines() if l.startswith('DIGEST')][0]
+    assert len(set(digests.values())) == 1, digests
