@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(kBlock, 4) gain_mix_kernel(const GainMixParams
     const double inv_coef = coef > 0 ? 1.0 / (double)coef : 0.0;
     const double* gains = p.gains + bt * p.n_stems * K;
     TO* stems_out = p.stems_out ? reinterpret_cast<TO*>(p.stems_out) + bt * p.n_stems * p.n_channels * n : nullptr;
+    const int n_stems = (int)p.n_stems;
+    const bool zero_mask = p.zero_mask != 0;
 
     for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
         const long long i0 = v * V;
@@ -129,36 +131,56 @@ __global__ void __launch_bounds__(kBlock, 4) gain_mix_kernel(const GainMixParams
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = TC(0);
         constexpr int SU = sizeof(TS) == 4 ? 4 : 2;    // stems whose loads are in flight together
-        for (int s0 = 0; s0 < (int)p.n_stems; s0 += SU) {
-            Vec<TS, V> x[SU];
-            double g0[SU];
+        const TS* src = base + i0;
+        const double* grow = gains + k0;
+        TO* sout = stems_out ? stems_out + c * n + i0 : nullptr;
+        if (cross == V) {
+            // common case, no gain boundary inside the vector: one gain per stem, no per-sample index work
+            // (this loop was 535 instructions per vector with the per-sample boundary checks inlined)
+            for (int s0 = 0; s0 < n_stems; s0 += SU) {
+                Vec<TS, V> x[SU];
+                TC g[SU];
 #pragma unroll
-            for (int u = 0; u < SU; ++u) {
-                if (s0 + u < (int)p.n_stems) {
-                    x[u] = load_vec<TS, V>(base + (long long)(s0 + u) * p.stem_stride + i0);
-                    g0[u] = __ldg(gains + (long long)(s0 + u) * K + k0);
+                for (int u = 0; u < SU; ++u) {
+                    if (s0 + u < n_stems) {
+                        x[u] = load_vec<TS, V>(src + (long long)(s0 + u) * p.stem_stride);
+                        g[u] = zero_mask ? TC(0) : (TC)__ldg(grow + (long long)(s0 + u) * K);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < SU; ++u) {
+                    if (s0 + u < n_stems) {
+                        Vec<TO, V> y;
+#pragma unroll
+                        for (int j = 0; j < V; ++j) {
+                            const TC prod = (TC)x[u].v[j] * g[u];
+                            acc[j] = (s0 + u) == 0 ? prod : acc[j] + prod;
+                            y.v[j] = (TO)prod;
+                        }
+                        if (sout) store_vec<TO, V>(sout + (long long)(s0 + u) * p.n_channels * n, y);
+                    }
                 }
             }
+        } else {
+            // a gain boundary falls inside this vector (once per interp_coef samples)
+            for (int s = 0; s < n_stems; ++s) {
+                const Vec<TS, V> x = load_vec<TS, V>(src + (long long)s * p.stem_stride);
+                const double g0 = __ldg(grow + (long long)s * K);
+                Vec<TO, V> y;
 #pragma unroll
-            for (int u = 0; u < SU; ++u) {
-                const int s = s0 + u;
-                if (s < (int)p.n_stems) {
-                    Vec<TO, V> y;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        double gd = g0[u];
-                        if (j >= cross) {                      // rare: a gain boundary inside the vector
-                            long long k = (i0 + j) / coef;
-                            if (k > K - 1) k = K - 1;
-                            gd = __ldg(gains + (long long)s * K + k);
-                        }
-                        const TC g = p.zero_mask ? TC(0) : (TC)gd;
-                        const TC prod = (TC)x[u].v[j] * g;
-                        acc[j] = s == 0 ? prod : acc[j] + prod;
-                        y.v[j] = (TO)prod;
+                for (int j = 0; j < V; ++j) {
+                    double gd = g0;
+                    if (j >= cross) {
+                        long long k = (i0 + j) / coef;
+                        if (k > K - 1) k = K - 1;
+                        gd = __ldg(gains + (long long)s * K + k);
                     }
-                    if (stems_out) store_vec<TO, V>(stems_out + ((long long)s * p.n_channels + c) * n + i0, y);
+                    const TC g = zero_mask ? TC(0) : (TC)gd;
+                    const TC prod = (TC)x.v[j] * g;
+                    acc[j] = s == 0 ? prod : acc[j] + prod;
+                    y.v[j] = (TO)prod;
                 }
+                if (sout) store_vec<TO, V>(sout + (long long)s * p.n_channels * n, y);
             }
         }
         Vec<TO, V> o;
@@ -187,7 +209,13 @@ int launch_gain_mix(const GainMixParams& p, bool vec_ok, cudaStream_t st) {
     if (vec_ok) {
         const long long nvec = (p.n_samples + V - 1) / V;
         const long long planes = p.n_channels * p.n_batch;
-        dim3 grid(grid_for(nvec, (int)(planes >= 16 ? 1 : 16 / planes)), (unsigned)p.n_channels, (unsigned)p.n_batch);
+        // about two waves of resident CTAs (4 per SM) over all planes: the per-CTA prologue (index set-up) and
+        // epilogue (block reduction + two atomics) are then amortised over tens of vectors per thread
+        long long per_plane = (2LL * 4 * dam_sm_count()) / (planes > 0 ? planes : 1);
+        const long long max_blocks = (nvec + kBlock - 1) / kBlock;
+        if (per_plane < 1) per_plane = 1;
+        if (per_plane > max_blocks) per_plane = max_blocks;
+        dim3 grid((unsigned)per_plane, (unsigned)p.n_channels, (unsigned)p.n_batch);
         gain_mix_kernel<TS, TC, TO, V><<<grid, kBlock, 0, st>>>(p);
     } else {
         dim3 grid(grid_for(p.n_samples, 8), (unsigned)p.n_channels, (unsigned)p.n_batch);

@@ -3,6 +3,10 @@ usage: python tools/ncu_src_summary.py src.csv [n_hot]"""
 import csv, sys, collections
 path = sys.argv[1]; nhot = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 rows = list(csv.reader(open(path)))
+# a dump may hold several sections (one per launch, each starting with a 'Kernel Name' row): keep the first
+ends = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+if len(ends) > 1:
+    rows = rows[:ends[1]]
 hdr = rows[1]
 col = {h: i for i, h in enumerate(hdr)}
 data = [r for r in rows[2:] if len(r) == len(hdr)]
