@@ -118,31 +118,35 @@ struct KwParams {
     double* states;                // workspace [n_rows][n_chunks][4]
 };
 
-// Cooperative, coalesced, software-pipelined tile loader shared by passes A and C.  The unit of work
+// Coalesced, software-pipelined, WARP-PRIVATE tile loader shared by passes A and C.  The unit of work
 // is kBlock consecutive GLOBAL chunk ids (row-major over all rows, so a work item may straddle two
 // rows and no CTA is padded per row: 220 544 chunks of the bench batch are 862 items, 2.91 rounds of
-// 296 resident CTAs, instead of 896 per-row items = 4 rounds).  Thread c owns chunk c of the item and
-// publishes its base offset and length; per step the CTA stages [kBlock chunks x kSub samples]: a warp
+// 296 resident CTAs, instead of 896 per-row items = 4 rounds).  Lane l of warp w owns chunk 32 w + l of
+// the item and publishes its base offset and length to the warp's slice of shared memory; per step the
+// warp stages [32 chunks x kSub samples] into ITS OWN double-buffered tile: one load instruction
 // reads two rows of 16 consecutive samples (full sectors), registers hold the NEXT step's samples
-// while the current ones are consumed from shared memory, and thread c then walks row c (pitch
-// kSub+1: conflict-free).  Thread-per-chunk loads straight from global memory touch 32 different
-// lines per instruction and are bound by the L1 tag rate (measured: 70 % l1tex, 10 % issue).
+// while the current ones are consumed from shared memory, and lane l then walks row l (pitch
+// kSub+1: conflict-free).  Only __syncwarp() separates the steps: with a CTA-wide tile and a
+// __syncthreads() per 16 samples, 41 % of pass C's warp stall samples were barrier waits (profiles/).
+// Thread-per-chunk loads straight from global memory touch 32 different lines per instruction and
+// are bound by the L1 tag rate (measured: 70 % l1tex, 10 % issue).
 template <typename T>
 struct TileLoader {
     T reg[kSub];
-    __device__ __forceinline__ void load(const T* __restrict__ x, const long long* __restrict__ s_base,
-                                         const int* __restrict__ s_len, int sb, long long samp_stride) {
+    // w_base / w_len / tile: this warp's slices
+    __device__ __forceinline__ void load(const T* __restrict__ x, const long long* __restrict__ w_base,
+                                         const int* __restrict__ w_len, int sb, long long samp_stride, int lane) {
 #pragma unroll
         for (int k = 0; k < kSub; ++k) {
-            const int e = threadIdx.x + k * kBlock;
+            const int e = lane + k * 32;
             const int r = e >> 4, idx = sb * kSub + (e & 15);
-            reg[k] = idx < s_len[r] ? x[s_base[r] + idx * samp_stride] : T(0);
+            reg[k] = idx < w_len[r] ? x[w_base[r] + idx * samp_stride] : T(0);
         }
     }
-    __device__ __forceinline__ void store(T* __restrict__ tile) const {
+    __device__ __forceinline__ void store(T* __restrict__ tile, int lane) const {
 #pragma unroll
         for (int k = 0; k < kSub; ++k) {
-            const int e = threadIdx.x + k * kBlock;
+            const int e = lane + k * 32;
             tile[(e >> 4) * kPitch + (e & 15)] = reg[k];
         }
     }
@@ -155,7 +159,7 @@ constexpr size_t kw_smem_bytes() {
 
 struct ChunkId { long long g, row, chunk; int len; bool active; };
 
-// thread c's chunk of work item `item`, published to shared memory for the cooperative loader
+// thread c's chunk of work item `item`, published to shared memory for its warp's loader
 __device__ __forceinline__ ChunkId publish_chunk(const KwParams& p, long long item, long long* s_base, int* s_len) {
     ChunkId id;
     id.g = item * kBlock + threadIdx.x;
@@ -179,19 +183,24 @@ __global__ void __launch_bounds__(kBlock) kw_chunk_state_kernel(const KwParams p
     T* s_tile = reinterpret_cast<T*>(s_len + kBlock);
     const T* x = reinterpret_cast<const T*>(p.x);
     for (int i = threadIdx.x; i < kChunk * 4; i += kBlock) s_G[i] = p.G[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long* w_base = s_base + warp * 32;
+    const int* w_len = s_len + warp * 32;
+    T* w_tile = s_tile + warp * 32 * kPitch;               // [2][32][kPitch] with buffer stride kBlock * kPitch
     for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        __syncthreads();                      // previous item is fully consumed (and s_G is loaded)
+        __syncwarp();                         // the warp has consumed its previous item
         const ChunkId id = publish_chunk(p, item, s_base, s_len);
-        __syncthreads();
+        __syncwarp();
         TileLoader<T> ld;
-        ld.load(x, s_base, s_len, 0, p.samp_stride);
-        ld.store(s_tile);
-        __syncthreads();
+        ld.load(x, w_base, w_len, 0, p.samp_stride, lane);
+        ld.store(w_tile, lane);
+        __syncwarp();
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         for (int sb = 0; sb < kChunk / kSub; ++sb) {
             const bool more = sb + 1 < kChunk / kSub;
-            if (more) ld.load(x, s_base, s_len, sb + 1, p.samp_stride);
-            const T* mine = s_tile + (sb & 1) * kBlock * kPitch + threadIdx.x * kPitch;
+            if (more) ld.load(x, w_base, w_len, sb + 1, p.samp_stride, lane);
+            const T* mine = w_tile + (sb & 1) * kBlock * kPitch + lane * kPitch;
 #pragma unroll
             for (int j = 0; j < kSub; ++j) {
                 const double v = (double)mine[j];
@@ -199,8 +208,8 @@ __global__ void __launch_bounds__(kBlock) kw_chunk_state_kernel(const KwParams p
                 a0 = fma(g[0], v, a0); a1 = fma(g[1], v, a1);
                 a2 = fma(g[2], v, a2); a3 = fma(g[3], v, a3);
             }
-            if (more) ld.store(s_tile + ((sb + 1) & 1) * kBlock * kPitch);
-            __syncthreads();
+            if (more) ld.store(w_tile + ((sb + 1) & 1) * kBlock * kPitch, lane);
+            __syncwarp();
         }
         if (id.active) {
             const bool last = id.chunk == p.n_chunks - 1;      // possibly partial: its end state is unused
@@ -279,12 +288,16 @@ __global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
     T* s_tile = reinterpret_cast<T*>(s_len + kBlock);
     const T* x = reinterpret_cast<const T*>(p.x);
     const Coeffs c = p.c;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long* w_base = s_base + warp * 32;
+    const int* w_len = s_len + warp * 32;
+    T* w_tile = s_tile + warp * 32 * kPitch;
     for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        __syncthreads();                      // previous item is fully consumed
+        __syncwarp();                         // the warp has consumed its previous item
         const ChunkId id = publish_chunk(p, item, s_base, s_len);
-        __syncthreads();
+        __syncwarp();
         TileLoader<T> ld;
-        ld.load(x, s_base, s_len, 0, p.samp_stride);
+        ld.load(x, w_base, w_len, 0, p.samp_stride, lane);
         const long long i0 = id.chunk * kChunk;
         const long long len = id.len;
         double s[4] = {0, 0, 0, 0};
@@ -305,13 +318,13 @@ __global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
         }
         double* out = p.seg_sumsq + id.row * p.n_seg;
         double acc = 0.0;
-        ld.store(s_tile);
-        __syncthreads();
+        ld.store(w_tile, lane);
+        __syncwarp();
 
         for (int sb = 0; sb < kChunk / kSub; ++sb) {
             const bool more = sb + 1 < kChunk / kSub;
-            if (more) ld.load(x, s_base, s_len, sb + 1, p.samp_stride);
-            const T* mine = s_tile + (sb & 1) * kBlock * kPitch + threadIdx.x * kPitch;
+            if (more) ld.load(x, w_base, w_len, sb + 1, p.samp_stride, lane);
+            const T* mine = w_tile + (sb & 1) * kBlock * kPitch + lane * kPitch;
             const long long base = (long long)sb * kSub;
             if (base < len) {
                 const long long g_last = i0 + (base + kSub < len ? base + kSub : len) - 1;
@@ -338,8 +351,8 @@ __global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
                     }
                 }
             }
-            if (more) ld.store(s_tile + ((sb + 1) & 1) * kBlock * kPitch);
-            __syncthreads();
+            if (more) ld.store(w_tile + ((sb + 1) & 1) * kBlock * kPitch, lane);
+            __syncwarp();
         }
         if (seg >= 0 && seg < p.n_seg && acc != 0.0) atomicAdd(out + seg, acc);
     }
