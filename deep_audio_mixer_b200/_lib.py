@@ -19,7 +19,7 @@ SIGNATURES = {
     'dam_last_error': (_c.c_char_p, []),
     'dam_stft_num_frames': (_i64, [_i64, _i]),
     'dam_stft_db': (_i, [_vp, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _d, _vp, _vp, _i, _i, _d, _d, _i,
-                         _vp, _i, _i64, _vp, _vp]),
+                         _vp, _i, _i64, _i64, _vp, _vp]),
     'dam_gain_mix': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _i,
                           _vp, _vp, _vp]),
     'dam_bus_sum': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _c.POINTER(_c.c_int32), _i, _d, _vp, _vp]),

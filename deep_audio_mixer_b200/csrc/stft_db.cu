@@ -57,9 +57,6 @@ struct StftParams {
     const double* row_gain;
     const float* window;
     const void* twiddle;          // device table, Cx<R>::type [33][34]
-    const void* twiddle_r16;      // device tables of the 16x16x4 kernel (float2): [16][64] | [16][4] | [516]
-    int tma_src;                  // 1: raw float32 samples may be staged by bulk copies (host-evaluated)
-    int elem_bytes;               // bytes per source sample
     int hop;
     long long T;                  // frames per row
     long long tiles_per_row, n_tiles;
@@ -69,6 +66,7 @@ struct StftParams {
     double log_scale_d, floor_db_d;
     void* out;
     long long out_row_stride;
+    long long bin_stride;         // elements between consecutive bins of a plane (>= T; T when dense)
     double* stats;
 };
 
@@ -604,7 +602,7 @@ stft_db_kernel(const StftParams p) {
             }
             __syncthreads();     // all frames are in registers; s_stage may now be overwritten
             if (warp < nf)
-                stage1_frame_pc<OUT, kStats>(xp, reinterpret_cast<float2*>(s_xch) + warp * kXch + lane, out_row + warp, T,
+                stage1_frame_pc<OUT, kStats>(xp, reinterpret_cast<float2*>(s_xch) + warp * kXch + lane, out_row + warp, p.bin_stride,
                                              nq, p, lane, st);
         } else {
             R x[64];
@@ -615,7 +613,7 @@ stft_db_kernel(const StftParams p) {
             }
             __syncthreads();     // all frames are in registers; s_stage may now be overwritten
             if (warp < nf)
-                stage1_frame<R, OUT, kStats>(x, s_xch + warp * kXch + lane, out_row + warp, T, nq, p, lane, st);
+                stage1_frame<R, OUT, kStats>(x, s_xch + warp * kXch + lane, out_row + warp, p.bin_stride, nq, p, lane, st);
         }
         __syncthreads();
 
@@ -625,9 +623,9 @@ stft_db_kernel(const StftParams p) {
             if (t < nf) {
                 if constexpr (kPc)
                     stage2_task_pc<OUT, kStats>(reinterpret_cast<const float2*>(s_xch) + t * kXch + kp * kRow,
-                                                reinterpret_cast<const float2*>(s_tw) + kp * kRow, out_row + t, T, kp, p, st);
+                                                reinterpret_cast<const float2*>(s_tw) + kp * kRow, out_row + t, p.bin_stride, kp, p, st);
                 else
-                    stage2_task<R, OUT, kStats>(s_xch + t * kXch + kp * kRow, s_tw + kp * kRow, out_row + t, T, kp, p, st);
+                    stage2_task<R, OUT, kStats>(s_xch + t * kXch + kp * kRow, s_tw + kp * kRow, out_row + t, p.bin_stride, kp, p, st);
             }
         }
     }
@@ -787,249 +785,14 @@ stft_db_async_kernel(const StftParams p) {
         in_flight = prefetch(tile + gridDim.x);
 
         if (warp < nf)
-            stage1_frame_pc<OUT, kStats>(xp, s_xch + warp * kXch + lane, out_row + warp, T, nq, p, lane, st);
+            stage1_frame_pc<OUT, kStats>(xp, s_xch + warp * kXch + lane, out_row + warp, p.bin_stride, nq, p, lane, st);
         __syncthreads();
 
         // ---- stage 2: thread = (k' = tid / FT in 0..31, frame = tid % FT)
         {
             const int kp = tid / kFT, t = tid % kFT;
             if (t < nf)
-                stage2_task_pc<OUT, kStats, !kTabSmem>(s_xch + t * kXch + kp * kRow, twp + kp * kRow, out_row + t, T, kp, p, st);
-        }
-    }
-    if (kStats) st.flush(p.stats, lane);
-}
-
-// ==========================================================================================
-// Three-stage variant (float32 arithmetic): half the registers per thread, twice the warps per SM.
-// The two-stage kernels above carry a 32-point complex transform (64 data registers) per thread, which
-// pins them at 128 registers and 16 warps per SM; their profile is latency bound (8.4 cycles per issued
-// instruction with four warps per scheduler).  Here a frame of 2048 real samples is transformed as a
-// 1024-point complex transform of z[m] = x[2m] + i x[2m+1] factored 16 x 16 x 4, followed by the
-// real-input split, so no thread ever holds more than 16 complex values: 64 registers, 512 threads per
-// CTA, two CTAs = 32 warps per SM.
-//   m = 64 m1 + 4 m2 + m3,  k = k1 + 16 k2 + 256 k3   (m1, m2, k1, k2 < 16; m3, k3 < 4)
-//   stage 1  thread (frame, j = 4 m2 + m3): 16 windowed sample PAIRS (one 64-bit shared load each,
-//            conflict-free) -> 16-point transform over m1 -> x W_1024^(j k1) -> exchange [k1][68]
-//   stage 2  thread (frame, k1, m3): 16-point transform over m2 -> x W_64^(m3 k2) -> exchange [k][m3]
-//   stage 3  thread (frame, u), u = 1..127: the 4-point transforms of rows u and 256 - u give
-//            Z[u + 256 k3] and Z[1024 - (u + 256 k3)] in the SAME thread, so the split
-//            X[k], X[1024-k] = E +- (-i W_2048^k) D,  E = Z[k] + conj Z[1024-k],  D = Z[k] - conj Z[1024-k]
-//            needs no further exchange: 8 bins per task, dB in registers, lanes = 8 frames x 4 tasks so a
-//            store instruction writes four 32-byte row segments.  u = 0 handles rows 0 and 128 (9 bins).
-// The factor 1/2 of the split is folded into the window table (exact: a power of two).
-constexpr int kR16Threads = 512;
-constexpr int kR16FT = 8;
-constexpr int kR16S1 = 68;          // pitch of an exchange-1 row (float2): half-warp (4 k1 x 4 m3) hits 16 bank pairs
-constexpr int kR16FS = 1090;        // frame stride (float2), = 2 mod 16: 128-bit stage-3 loads of two frames interleave
-constexpr int kR16Tw1 = 16 * 64, kR16Tw2 = 16 * 4, kR16TwN = 516;
-
-__device__ __forceinline__ pk2 pk_cmul(pk2 v, float2 w) {
-    // v * w = (vr wr - vi wi, vi wr + vr wi) = v * (wr, wr) + swap(v) * (-wi, wi)
-    return pk_fma(pk_swap(v), pk_make(-w.y, w.y), pk_mul(v, pk_c(w.x)));
-}
-__device__ __forceinline__ void pk_fft4(const pk2 (&z)[4], pk2 (&Z)[4]) {
-    const pk2 a = pk_add(z[0], z[2]), b = pk_sub(z[0], z[2]);
-    const pk2 c = pk_add(z[1], z[3]), d = pk_sub(z[1], z[3]);
-    Z[0] = pk_add(a, c);
-    Z[2] = pk_sub(a, c);
-    Z[1] = pk_fma(pk_swap(d), pk_make(1.f, -1.f), b);      // b - i d
-    Z[3] = pk_fma(pk_swap(d), pk_make(-1.f, 1.f), b);      // b + i d
-}
-// bins k (-> ok) and 1024 - k (-> omk, skipped when null) from Z1 = Z[k], Z2 = Z[1024 - k]; tw = -i W_2048^k
-template <typename OUT, bool kStats>
-__device__ __forceinline__ void r16_emit(pk2 Z1, pk2 Z2, float2 tw, OUT* ok, OUT* omk, const StftParams& p, StatAcc& st) {
-    const pk2 E = pk_fma(Z2, pk_make(1.f, -1.f), Z1);
-    const pk2 D = pk_fma(Z2, pk_make(-1.f, 1.f), Z1);
-    const pk2 Tm = pk_cmul(D, tw);
-    float re, im;
-    pk_split(pk_add(E, Tm), re, im);
-    const float da = DbOut<float>::eval(re, im, p);
-    store_out<OUT>(ok, (OUT)da);
-    if (kStats) st.add(da);
-    if (omk != nullptr) {
-        pk_split(pk_sub(E, Tm), re, im);
-        const float db = DbOut<float>::eval(re, im, p);
-        store_out<OUT>(omk, (OUT)db);
-        if (kStats) st.add(db);
-    }
-}
-
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
-}
-
-constexpr size_t r16_table_bytes() { return kNfft * sizeof(float) + (size_t)(kR16Tw1 + kR16Tw2 + kR16TwN) * sizeof(float2) + 16; }
-
-template <typename OUT, bool kStats>
-__global__ void __launch_bounds__(kR16Threads, 2)
-stft_db_r16_kernel(const StftParams p) {
-    constexpr int kFT = kR16FT;
-    constexpr int kThreads = kR16Threads;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_win = reinterpret_cast<float*>(smem_raw);                 // [2048], 0.5 * window
-    float2* s_tw1 = reinterpret_cast<float2*>(s_win + kNfft);          // [16][64]  W_1024^(j k1)
-    float2* s_tw2 = s_tw1 + kR16Tw1;                                   // [16][4]   W_64^(m3 k2)
-    float2* s_twN = s_tw2 + kR16Tw2;                                   // [513]     -i W_2048^k
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_twN + kR16TwN);     // 16 bytes
-    float2* s_x = reinterpret_cast<float2*>(bar + 2);                  // [kFT][kR16FS]
-    float* s_stage = reinterpret_cast<float*>(s_x);                    // aliases s_x: [C][(kFT-1)*hop + 2048]
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    for (int i = tid; i < kNfft; i += kThreads) s_win[i] = 0.5f * __ldg(p.window + i);
-    {
-        const float2* tab = reinterpret_cast<const float2*>(p.twiddle_r16);
-        for (int i = tid; i < kR16Tw1 + kR16Tw2 + kR16TwN; i += kThreads) s_tw1[i] = tab[i];
-    }
-    if (tid == 0) mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const int hop = p.hop;
-    const int span_max = (kFT - 1) * hop + kNfft;
-    const long long T = p.T;
-    const long long n = p.n_samples;
-    const int C = p.channels;
-    const unsigned tiles_per_row = (unsigned)p.tiles_per_row, n_tiles = (unsigned)p.n_tiles;
-    // raw float32 samples can go through the TMA unit: one bulk copy per channel issued by one thread
-    // (the generic staging code costs ~200 instructions per warp and tile, a fifth of this kernel)
-    unsigned phase = 0;
-    StatAcc st;
-
-    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned urow = tile / tiles_per_row;
-        const long long row = urow;
-        const long long t0 = (long long)(tile - urow * tiles_per_row) * kFT;
-        const int nf = (int)((T - t0) < kFT ? (T - t0) : kFT);
-        OUT* out_row = reinterpret_cast<OUT*>(p.out) + row * p.out_row_stride + t0;
-        const long long g0 = t0 * hop - kNfft / 2;
-        const int span = (nf - 1) * hop + kNfft;
-        const float* src = reinterpret_cast<const float*>(p.audio) + row_offset(p, row) + g0;
-        const bool tma = p.tma_src && g0 >= 0 && g0 + span <= n && (reinterpret_cast<unsigned long long>(src) & 15ull) == 0;
-
-        fence_proxy_async();  // this thread's reads of s_x (stage 3) are ordered before the TMA writes below
-        __syncthreads();      // previous tile's stage 3 has finished reading s_x (and the tables are loaded)
-        if (tid == 0) {
-            if (tma) {
-                const unsigned bytes = (unsigned)span * 4u;
-                mbar_expect_tx(bar, bytes * (unsigned)C);
-                bulk_g2s(s_stage, src, bytes, bar);
-                if (C == 2) bulk_g2s(s_stage + span_max, src + p.chan_stride, bytes, bar);
-            }
-            // pull the next tile's samples towards L2 while this one is transformed (16-byte aligned interior)
-            const unsigned nt = tile + gridDim.x;
-            if (p.l2_prefetch && nt < n_tiles && p.samp_stride == 1) {
-                const unsigned nrow = nt / tiles_per_row;
-                const long long nt0 = (long long)(nt - nrow * tiles_per_row) * kFT;
-                const int nnf = (int)((T - nt0) < kFT ? (T - nt0) : kFT);
-                long long lo = nt0 * hop - kNfft / 2, hi = lo + (nnf - 1) * hop + kNfft;
-                lo = lo < 0 ? 0 : lo;
-                hi = hi > n ? n : hi;
-                for (int c = 0; c < C; ++c) {
-                    const unsigned long long a0 = reinterpret_cast<unsigned long long>(p.audio) +
-                                                  (unsigned long long)((row_offset(p, nrow) + c * p.chan_stride + lo) * p.elem_bytes);
-                    const unsigned long long a1 = a0 + (unsigned long long)((hi - lo) * p.elem_bytes);
-                    const unsigned long long b0 = (a0 + 15ull) & ~15ull, b1 = a1 & ~15ull;
-                    if (b1 > b0) bulk_prefetch_l2(reinterpret_cast<const void*>(b0), (unsigned)(b1 - b0));
-                }
-            }
-        }
-        if (tma) {
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            if (C == 2) {
-                float4* l4 = reinterpret_cast<float4*>(s_stage);
-                const float4* r4 = reinterpret_cast<const float4*>(s_stage + span_max);
-                for (int v = tid; v < span / 4; v += kThreads) {
-                    float4 a = l4[v];
-                    const float4 b = r4[v];
-                    a.x = (a.x + b.x) * 0.5f; a.y = (a.y + b.y) * 0.5f; a.z = (a.z + b.z) * 0.5f; a.w = (a.w + b.w) * 0.5f;
-                    l4[v] = a;
-                }
-                __syncthreads();
-            }
-        } else {
-            if (p.audio_dtype == DAM_F32)      stage_tile<float, float, float, kThreads>(p, s_stage, row, g0, span, tid);
-            else if (p.audio_dtype == DAM_I16) stage_tile<float, float, short, kThreads>(p, s_stage, row, g0, span, tid);
-            else                               stage_tile<float, double, double, kThreads>(p, s_stage, row, g0, span, tid);
-            __syncthreads();
-        }
-
-        const int f = tid >> 6, r = tid & 63;          // stages 1 and 2: 64 tasks per frame
-        const int fc = f < nf ? f : nf - 1;
-        // ---- stage 1: task (f, j = r)
-        {
-            pk2 z[16];
-            const pk2* fx = reinterpret_cast<const pk2*>(s_stage + fc * hop) + r;
-            const pk2* fw = reinterpret_cast<const pk2*>(s_win) + r;
-#pragma unroll
-            for (int m1 = 0; m1 < 16; ++m1) z[m1] = pk_mul(fx[64 * m1], fw[64 * m1]);
-            __syncthreads();     // every sample pair is in registers; s_stage may be overwritten
-            if (f < nf) {
-                dam_cfft16_pc(z);
-                pk2* dst = reinterpret_cast<pk2*>(s_x) + f * kR16FS + r;
-                const float2* tw = s_tw1 + r;
-                dst[0] = z[0];
-#pragma unroll
-                for (int k1 = 1; k1 < 16; ++k1) dst[k1 * kR16S1] = pk_cmul(z[k1], tw[k1 * 64]);
-            }
-        }
-        __syncthreads();
-        // ---- stage 2: task (f, k1 = r / 4, m3 = r % 4)
-        {
-            pk2 a[16];
-            const int k1 = r >> 2, m3 = r & 3;
-            const pk2* src = reinterpret_cast<const pk2*>(s_x) + fc * kR16FS + k1 * kR16S1 + m3;
-#pragma unroll
-            for (int m2 = 0; m2 < 16; ++m2) a[m2] = src[4 * m2];
-            __syncthreads();     // exchange 1 is consumed; exchange 2 goes to the same buffer
-            if (f < nf) {
-                dam_cfft16_pc(a);
-                pk2* dst = reinterpret_cast<pk2*>(s_x) + f * kR16FS + r;         // (k1 + 16 k2) * 4 + m3 = r + 64 k2
-                const float2* tw = s_tw2 + m3;
-                dst[0] = a[0];
-#pragma unroll
-                for (int k2 = 1; k2 < 16; ++k2) dst[64 * k2] = pk_cmul(a[k2], tw[k2 * 4]);
-            }
-        }
-        __syncthreads();
-        // ---- stage 3: two tasks per thread, lanes = 8 frames x 4 tasks
-        {
-            const int ki = tid & 3, ft = (tid >> 2) & 7;
-            if (ft < nf) {
-                OUT* out_frame = out_row + ft;
-                const unsigned T32 = (unsigned)T;                    // the launcher guarantees 1024 * T < 2^31
-                const size_t S = (size_t)(256u * T32);
-                const ulonglong2* xf = reinterpret_cast<const ulonglong2*>(s_x + ft * kR16FS);      // two complex per element
-#pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {
-                    const int u = 4 * ((tid >> 5) + 16 * pass) + ki;
-                    const int ub = u == 0 ? 128 : 256 - u;
-                    const ulonglong2 a01 = xf[2 * u], a23 = xf[2 * u + 1];
-                    const ulonglong2 b01 = xf[2 * ub], b23 = xf[2 * ub + 1];
-                    const pk2 za[4] = {a01.x, a01.y, a23.x, a23.y};
-                    const pk2 zb[4] = {b01.x, b01.y, b23.x, b23.y};
-                    pk2 ZA[4], ZB[4];
-                    pk_fft4(za, ZA);
-                    pk_fft4(zb, ZB);
-                    OUT* P0 = out_frame + (size_t)((unsigned)u * T32);        // bins u + 256 i      at P0 + i S
-                    OUT* Q0 = out_frame + (size_t)((unsigned)ub * T32);       // bins 256 - u + 256 i at Q0 + i S
-                    const float2* ta = s_twN + u;
-                    const float2* tb = s_twN + ub;
-                    if (u != 0) {
-                        r16_emit<OUT, kStats>(ZA[0], ZB[3], ta[0], P0, Q0 + 3 * S, p, st);            // u,       1024 - u
-                        r16_emit<OUT, kStats>(ZA[1], ZB[2], ta[256], P0 + S, Q0 + 2 * S, p, st);      // u + 256, 768 - u
-                        r16_emit<OUT, kStats>(ZB[0], ZA[3], tb[0], Q0, P0 + 3 * S, p, st);            // 256 - u, 768 + u
-                        r16_emit<OUT, kStats>(ZB[1], ZA[2], tb[256], Q0 + S, P0 + 2 * S, p, st);      // 512 - u, 512 + u
-                    } else {
-                        r16_emit<OUT, kStats>(ZA[0], ZA[0], ta[0], P0, P0 + 4 * S, p, st);            // 0, 1024
-                        r16_emit<OUT, kStats>(ZA[1], ZA[3], ta[256], P0 + S, P0 + 3 * S, p, st);      // 256, 768
-                        r16_emit<OUT, kStats>(ZA[2], ZA[2], ta[512], P0 + 2 * S, (OUT*)nullptr, p, st);   // 512
-                        r16_emit<OUT, kStats>(ZB[0], ZB[3], tb[0], Q0, Q0 + 3 * S, p, st);            // 128, 896
-                        r16_emit<OUT, kStats>(ZB[1], ZB[2], tb[256], Q0 + S, Q0 + 2 * S, p, st);      // 384, 640
-                    }
-                    if (kStats) st.fold();
-                }
-            }
+                stage2_task_pc<OUT, kStats, !kTabSmem>(s_xch + t * kXch + kp * kRow, twp + kp * kRow, out_row + t, p.bin_stride, kp, p, st);
         }
     }
     if (kStats) st.flush(p.stats, lane);
@@ -1128,7 +891,7 @@ stft_db_generic_kernel(const StftParams p, int n_fft, int log2n, int kGenFT) {
     OUT* out_row = reinterpret_cast<OUT*>(p.out) + row * p.out_row_stride + t0;
     for (int i = tid; i < bins * kGenFT; i += kGenThreads) {
         const int f = i / kGenFT, t = i % kGenFT;
-        if (t < nf) out_row[(long long)f * T + t] = (OUT)s_db[i];
+        if (t < nf) out_row[(long long)f * p.bin_stride + t] = (OUT)s_db[i];
     }
     if (p.stats != nullptr) {
         double sm = 0.0, sq = 0.0, cnt = 0.0;
@@ -1167,7 +930,6 @@ int launch_generic(const StftParams& p, int n_fft, cudaStream_t stream) {
 struct TwiddleTables {
     float2* f32 = nullptr;
     double2* f64 = nullptr;
-    float2* r16 = nullptr;         // [16][64] W_1024^(j k1) | [16][4] W_64^(m3 k2) | [516] -i W_2048^k
 };
 
 int get_twiddles(TwiddleTables** out) {
@@ -1228,36 +990,6 @@ int get_twiddles(TwiddleTables** out) {
         DAM_CHECK_CUDA(cudaMemcpy(dd, hd.data(), hd.size() * sizeof(double2), cudaMemcpyHostToDevice));
         t.f32 = df;
         t.f64 = dd;
-        {
-            // exp(-2 pi i num / den), exact on the octants
-            auto cis = [two_pi](long long num, long long den, long double& c, long double& sn) {
-                num %= den;
-                if ((8 * num) % den == 0) {
-                    const int o = (int)(8 * num / den);
-                    const long double h = 0.70710678118654752440084436210484903928L;
-                    const long double cs[8] = {1, h, 0, -h, -1, -h, 0, h};
-                    const long double ss[8] = {0, h, 1, h, 0, -h, -1, -h};
-                    c = cs[o]; sn = -ss[o];
-                } else {
-                    const long double ang = two_pi * (long double)num / (long double)den;
-                    c = cosl(ang); sn = -sinl(ang);
-                }
-            };
-            std::vector<float2> hr(kR16Tw1 + kR16Tw2 + kR16TwN, make_float2(0.f, 0.f));
-            long double c, sn;
-            for (int k1 = 0; k1 < 16; ++k1)
-                for (int j = 0; j < 64; ++j) { cis((long long)j * k1, 1024, c, sn); hr[k1 * 64 + j] = make_float2((float)c, (float)sn); }
-            for (int k2 = 0; k2 < 16; ++k2)
-                for (int m3 = 0; m3 < 4; ++m3) { cis((long long)m3 * k2, 64, c, sn); hr[kR16Tw1 + k2 * 4 + m3] = make_float2((float)c, (float)sn); }
-            for (int k = 0; k <= 512; ++k) {          // -i (c + i sn) = sn - i c
-                cis(k, 2048, c, sn);
-                hr[kR16Tw1 + kR16Tw2 + k] = make_float2((float)sn, (float)(-c));
-            }
-            float2* dr = nullptr;
-            DAM_CHECK_CUDA(cudaMalloc(&dr, hr.size() * sizeof(float2)));
-            DAM_CHECK_CUDA(cudaMemcpy(dr, hr.data(), hr.size() * sizeof(float2), cudaMemcpyHostToDevice));
-            t.r16 = dr;
-        }
     }
     *out = &t;
     return DAM_OK;
@@ -1304,44 +1036,6 @@ int launch(StftParams p, cudaStream_t stream) {
     if (trace) fprintf(stderr, "[dam] stft_db_kernel FT=%d pc=%d f%d smem=%zu occ=%d hop=%d C=%d T=%lld\n", kFT, (int)kPc,
                        (int)sizeof(R) * 8, smem, occ, p.hop, p.channels, (long long)p.T);
     kern<<<(unsigned)grid, kThreads, smem, stream>>>(p);
-    DAM_CHECK_CUDA(cudaGetLastError());
-    return DAM_OK;
-}
-
-template <bool kStats>
-int launch_r16(StftParams p, cudaStream_t stream) {
-    p.tiles_per_row = (p.T + kR16FT - 1) / kR16FT;
-    p.n_tiles = p.tiles_per_row * p.n_rows;
-    DAM_CHECK_ARG(p.n_tiles < 0x7fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
-                  (long long)p.n_tiles);
-    static const int pf_env = [] { const char* e = getenv("DAM_K1_PREFETCH"); return e ? atoi(e) : 1; }();
-    p.l2_prefetch = pf_env;
-    p.elem_bytes = p.audio_dtype == DAM_I16 ? 2 : (p.audio_dtype == DAM_F32 ? 4 : 8);
-    p.tma_src = p.audio_dtype == DAM_F32 && p.channels <= 2 && p.input_scale == 1.0 && p.row_gain == nullptr &&
-                p.samp_stride == 1 && (p.hop & 3) == 0 && (p.channels == 1 || ((p.chan_stride * 4) & 15ll) == 0);
-    const size_t stage = (size_t)p.channels * ((size_t)(kR16FT - 1) * p.hop + kNfft) * sizeof(float);   // raw channels for the TMA path
-    const size_t xch = (size_t)kR16FT * kR16FS * sizeof(float2);
-    const size_t smem = r16_table_bytes() + (stage > xch && p.channels <= 2 ? stage : xch);
-    auto kern = stft_db_r16_kernel<float, kStats>;
-    static std::mutex mu;
-    static bool configured[64] = {};
-    int dev = 0;
-    DAM_CHECK_CUDA(cudaGetDevice(&dev));
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (!configured[dev]) {
-            DAM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            configured[dev] = true;
-        }
-    }
-    int occ = 0;
-    DAM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kR16Threads, smem));
-    DAM_CHECK_ARG(occ > 0, "stft kernel does not fit on an SM (hop=%d needs %zu B shared memory)", p.hop, smem);
-    long long grid = (long long)dam_sm_count() * occ;
-    if (grid > p.n_tiles) grid = p.n_tiles;
-    static const bool trace = getenv("DAM_K1_TRACE") != nullptr;
-    if (trace) fprintf(stderr, "[dam] stft_db_r16_kernel smem=%zu occ=%d hop=%d C=%d T=%lld\n", smem, occ, p.hop, p.channels, (long long)p.T);
-    kern<<<(unsigned)grid, kR16Threads, smem, stream>>>(p);
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }
@@ -1400,7 +1094,8 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
                            double input_scale, const double* row_gain,
                            const float* window, int n_fft, int hop,
                            double amin, double multiplier, int compute_dtype,
-                           void* out, int out_dtype, int64_t out_row_stride, double* stats, void* stream) {
+                           void* out, int out_dtype, int64_t out_row_stride, int64_t out_bin_stride, double* stats,
+                           void* stream) {
     dam_clear_error();
     DAM_CHECK_ARG(audio != nullptr && window != nullptr && out != nullptr, "null pointer argument");
     DAM_CHECK_ARG(audio_dtype == DAM_I16 || audio_dtype == DAM_F32 || audio_dtype == DAM_F64,
@@ -1418,6 +1113,9 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     DAM_CHECK_ARG(hop >= 1 && hop <= n_fft, "hop=%d must be in [1, n_fft]", hop);
     DAM_CHECK_ARG(amin >= 0.0, "amin must be non-negative");
     DAM_CHECK_ARG(out_row_stride >= 0, "out_row_stride must be non-negative");
+    DAM_CHECK_ARG(out_bin_stride == 0 || out_bin_stride >= 1 + n_samples / hop,
+                  "out_bin_stride=%lld is smaller than the %lld frames of a row", (long long)out_bin_stride,
+                  (long long)(1 + n_samples / hop));
     DAM_CHECK_ARG(n_inner >= 0, "n_inner must be non-negative");
     if (n_rows == 0) return DAM_OK;
     DAM_CHECK_ARG(n_samples > n_fft / 2,
@@ -1435,11 +1133,11 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     p.floor_db_d = amin > 0.0 ? multiplier * log10(amin) : -INFINITY;
     p.floor_db = (float)p.floor_db_d;
     p.out = out; p.stats = stats;
-    p.tma_src = 0; p.elem_bytes = 0; p.twiddle_r16 = nullptr;
-    p.out_row_stride = out_row_stride > 0 ? out_row_stride : (long long)(n_fft / 2 + 1) * p.T;
+    p.bin_stride = out_bin_stride > 0 ? out_bin_stride : p.T;
+    p.out_row_stride = out_row_stride > 0 ? out_row_stride : (long long)(n_fft / 2 + 1) * p.bin_stride;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (n_fft != kNfft) {
-        p.twiddle = nullptr; p.twiddle_r16 = nullptr;
+        p.twiddle = nullptr;
         p.tiles_per_row = 0; p.n_tiles = 0; p.l2_prefetch = 0;
         if (compute_dtype == DAM_F32) return launch_generic<float, float>(p, n_fft, s);
         return out_dtype == DAM_F32 ? launch_generic<double, float>(p, n_fft, s) : launch_generic<double, double>(p, n_fft, s);
@@ -1450,11 +1148,6 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     const bool st = stats != nullptr;
     if (compute_dtype == DAM_F32) {
         p.twiddle = tw->f32;
-        p.twiddle_r16 = tw->r16;
-        // DAM_K1_R16=1: the three-stage 64-register kernel (needs an even hop: sample pairs are loaded as 64-bit words)
-        static const int r16_env = [] { const char* e = getenv("DAM_K1_R16"); return e ? atoi(e) : 0; }();
-        if (r16_env > 0 && (hop % 2) == 0 && out_dtype == DAM_F32 && p.T < (1LL << 21))
-            return st ? launch_r16<true>(p, s) : launch_r16<false>(p, s);
         // Frames per tile: 8 (two 8-warp CTAs per SM) by default.  16 (one 16-warp CTA per SM) writes 64-byte
         // row segments: measured +15 % when rows are not sector aligned (T % 8 != 0) at hop >= 1024, -17 %
         // when they are, -4 % at hop 512; it also wastes more of a short row's last tile.  DAM_FT_F32 = 8 | 16
@@ -1463,7 +1156,7 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
         static const bool use_pc = [] { const char* e = getenv("DAM_K1_PC"); return !(e && atoi(e) == 0); }();
         int ft = 8;
         if (ft_env == 8 || ft_env == 16) ft = ft_env;
-        else if (hop >= 1024 && (p.T % 8) != 0 && p.T >= 160) ft = 16;
+        else if (hop >= 1024 && (p.bin_stride % 8) != 0 && p.T >= 160) ft = 16;
         // TMA-staged kernel: measured +7..10 % on mono rows whose length is a multiple of 8 frames (sector-aligned
         // output rows) at hop >= 512, neutral on stereo, and 4..27 % SLOWER on unaligned rows (T = 173, 87), where
         // every 32-byte output segment straddles two sectors and the phase kernel's lock-step CTAs cope better.
@@ -1472,7 +1165,7 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
         static const int async_env = [] { const char* e = getenv("DAM_K1_ASYNC"); return e ? atoi(e) : 1; }();
         const bool async_ok = use_pc && ft == 8 && audio_dtype == DAM_F32 && (channels == 1 || channels == 2) &&
                               input_scale == 1.0 && row_gain == nullptr && samp_stride == 1 && (hop % 4) == 0;
-        const bool async_wins = channels == 1 && (p.T % 8) == 0 && hop >= 512;
+        const bool async_wins = channels == 1 && (p.bin_stride % 8) == 0 && hop >= 512;
         if (async_ok && (async_env >= 2 || (async_env == 1 && async_wins))) {
             const int force = async_env == 2 ? 1 : (async_env == 3 ? 0 : -1);
             const int rc2 = st ? launch_async<true>(p, s, force) : launch_async<false>(p, s, force);
@@ -1486,7 +1179,6 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
         return st ? launch<float, float, true, 8>(p, s) : launch<float, float, false, 8>(p, s);
     }
     p.twiddle = tw->f64;
-    p.twiddle_r16 = nullptr;
     if (out_dtype == DAM_F32) return st ? launch<double, float, true, 8>(p, s) : launch<double, float, false, 8>(p, s);
     return st ? launch<double, double, true, 8>(p, s) : launch<double, double, false, 8>(p, s);
 }

@@ -36,22 +36,36 @@ class SegmentBatchPipeline:
     def n_chunks(self, n_samples: int) -> int:
         return n_samples // self.chunk_samples
 
+    def feature_buffer(self, n_rows: int, n_bus: int = 4, device=None) -> torch.Tensor:
+        """Destination of ``features``: [n_rows, n_bus, F, pitch] float32 with the frame axis padded to a
+        multiple of 8 (32 bytes).  With T = 173 -- the only length model_scalar_2s accepts -- a dense row is
+        692 bytes and 7 of 8 of K1's 8-frame output segments straddle two DRAM sectors (12 % slower, ncu in
+        profiles/); consumers read the [..., :T] view, as non-contiguous as the reference's own features."""
+        F = self.n_fft // 2 + 1
+        T = features.num_frames(self.chunk_samples, self.hop)
+        return torch.empty((n_rows, n_bus, F, features.aligned_pitch(T)), dtype=torch.float32,
+                           device=device if device is not None else self.device)
+
     def features(self, buses: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
-        """buses [B, 4, C, N] float32 -> [B * n_chunks, 4, F, T] float32 (model input layout)."""
+        """buses [B, 4, C, N] float32 -> [B * n_chunks, 4, F, T] float32 (model input layout; a view of a
+        ``feature_buffer`` whose frame axis is padded to the next multiple of 8)."""
         B, S, C, N = buses.shape
         nc = self.n_chunks(N)
         F = self.n_fft // 2 + 1
         T = features.num_frames(self.chunk_samples, self.hop)
         if out is None:
-            out = torch.empty((B * nc, S, F, T), dtype=torch.float32, device=buses.device)
+            out = self.feature_buffer(B * nc, S, buses.device)
+        pitch = out.shape[-1]
+        if tuple(out.shape[:3]) != (B * nc, S, F) or pitch < T or not out.is_contiguous():
+            raise ValueError('features: out must be a contiguous [%d, %d, %d, >=%d] buffer' % (B * nc, S, F, T))
         for s in range(S):
             # rows = (segment, chunk) of bus s: two-level addressing, channels averaged in the kernel
             view = buses[:, s].as_strided((B, nc, C, self.chunk_samples),
                                           (buses.stride(0), self.chunk_samples, buses.stride(2), 1),
                                           buses[:, s].storage_offset())
             features.stft_db(view, self.n_fft, self.hop, channel_axis=-2, out=out[:, s],
-                             out_row_stride=S * F * T)
-        return out
+                             out_row_stride=S * F * pitch, frame_pitch=pitch)
+        return out[..., :T]
 
     def _ev(self, name):
         if self.timings is not None:

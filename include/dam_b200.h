@@ -78,6 +78,10 @@ const char* dam_last_error(void);
  *                output requires compute_dtype F64); plane r starts at out + r*out_row_stride
  *                elements (0 = densely packed, (n_fft/2+1)*T).  A stride of S*F*T lets one call
  *                per stem fill a [chunks, S, F, T] model input in place.
+ *   out_bin_stride  elements between consecutive bins of a plane (0 = T, dense).  A multiple of 8
+ *                (32 bytes) keeps every 8-frame output segment inside one DRAM sector: with T = 173
+ *                the dense layout straddles sectors for 7 of 8 bins and the kernel runs 12 % slower;
+ *                the caller then views the result as out[..., :T].
  *   stats        optional device double[3]: sum, sum of squares and count of the dB values
  *                written are ATOMICALLY ADDED (caller zeroes it); NULL = skip.
  */
@@ -88,7 +92,8 @@ int dam_stft_db(const void* audio, int audio_dtype, int channels,
                 double input_scale, const double* row_gain,
                 const float* window, int n_fft, int hop,
                 double amin, double multiplier, int compute_dtype,
-                void* out, int out_dtype, int64_t out_row_stride, double* stats, void* stream);
+                void* out, int out_dtype, int64_t out_row_stride, int64_t out_bin_stride, double* stats,
+                void* stream);
 
 /*
  * K2: zero-order-hold gain masks applied to stems + stem sum (time domain).

@@ -300,6 +300,8 @@ for rows, ch, n, hop in ((7, 1, 88200, 512), (5, 2, 88200, 512), (4, 1, 176400, 
     h.update(out.cpu().numpy().tobytes()); h.update(stats.cpu().numpy().tobytes()[16:])
     out = F.stft_db(x, hop=hop, **kw)
     h.update(out.cpu().numpy().tobytes())
+    out = F.stft_db(x, hop=hop, frame_pitch=F.aligned_pitch(1 + n // hop), **kw)       # sector-aligned rows
+    h.update(out.contiguous().cpu().numpy().tobytes())
 print('DIGEST', h.hexdigest())
 '''
 
@@ -319,3 +321,32 @@ def test_async_and_phase_kernels_are_bit_identical(cuda_device):
         assert r.returncode == 0, r.stderr[-2000:]
         digests[mode] = [l for l in r.stdout.splitlines() if l.startswith('DIGEST')][0]
     assert len(set(digests.values())) == 1, digests
+
+
+@pytest.mark.parametrize('n,hop,ch', [(88200, 512, 1), (88200, 512, 2), (88200, 1024, 1), (176400, 1024, 1), (30001, 512, 1)])
+def test_frame_pitch_padded_rows(cuda_device, n, hop, ch):
+    """out_bin_stride: rows padded to a multiple of 8 frames hold the same values as the dense layout, the
+    padding is never written, and nothing lands outside the buffer."""
+    T = 1 + n // hop
+    pitch = F.aligned_pitch(T)
+    assert pitch % 8 == 0 and 0 <= pitch - T < 8
+    g = torch.Generator(device='cuda').manual_seed(3)
+    x = torch.randn((4, ch, n) if ch > 1 else (4, n), device='cuda', generator=g) * 0.3
+    kw = {'channel_axis': -2} if ch > 1 else {}
+    dense = F.stft_db(x, hop=hop, **kw)
+    view = F.stft_db(x, hop=hop, frame_pitch=pitch, **kw)
+    assert view.shape == dense.shape and view.stride(-2) == pitch
+    assert torch.equal(view, dense)
+    guard = 1024
+    buf = torch.full((guard + 4 * 1025 * pitch + guard,), float('nan'), device='cuda')
+    body = buf[guard:guard + 4 * 1025 * pitch]
+    got = F.stft_db(x, hop=hop, frame_pitch=pitch, out=body, **kw)
+    torch.cuda.synchronize()
+    assert torch.isnan(buf[:guard]).all() and torch.isnan(buf[-guard:]).all()
+    planes = body.reshape(4, 1025, pitch)
+    assert torch.equal(planes[..., :T], dense)
+    if pitch > T:
+        assert torch.isnan(planes[..., T:]).all()
+    assert torch.equal(got, dense)
+    with pytest.raises(ValueError):
+        F.stft_db(x, hop=hop, frame_pitch=T - 1, **kw)

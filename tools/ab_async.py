@@ -66,7 +66,6 @@ def main():
     modes = [('phase', {'DAM_K1_ASYNC': '0'}), ('phase ft8', {'DAM_K1_ASYNC': '0', 'DAM_FT_F32': '8'}),
              ('phase ft16', {'DAM_K1_ASYNC': '0', 'DAM_FT_F32': '16'}),
              ('default', {}),
-             ('r16 three-stage', {'DAM_K1_R16': '1'}),
              ('async tab-smem ft8', {'DAM_K1_ASYNC': '2', 'DAM_FT_F32': '8'}),
              ('async tab-global ft8', {'DAM_K1_ASYNC': '3', 'DAM_FT_F32': '8'})]
     for name, env in modes:

@@ -568,10 +568,6 @@ def main():
     summary.append('// dam_cfft32_pc: %d packed ops (one 32-point complex transform, packed complex registers)' % nops)
     parts.append('// In-place forward complex DFT of 32 points; z[k] = (re, im) packed.\n'
                  '__device__ __forceinline__ void dam_cfft32_pc(pk2 (&z)[32]) {\n    %s\n}\n' % '\n    '.join(lines))
-    lines, nops = build_pc_cfft(16)
-    summary.append('// dam_cfft16_pc: %d packed ops (one 16-point complex transform, packed complex registers)' % nops)
-    parts.append('// In-place forward complex DFT of 16 points; z[k] = (re, im) packed.\n'
-                 '__device__ __forceinline__ void dam_cfft16_pc(pk2 (&z)[16]) {\n    %s\n}\n' % '\n    '.join(lines))
     lines, nops = build_pc_rfft(64)
     summary.append('// dam_rfft64_pc: %d packed ops (64 real samples, packed complex registers)' % nops)
     parts.append('// 64 real samples as 32 packed pairs xp[m] = (x[2m], x[2m+1]) -> y0n = (Y[0], Y[32]) and s[k] = 2*Y[k] (packed complex), k = 1..31.\n'
