@@ -32,6 +32,10 @@ SIGNATURES = {
     'dam_gated_loudness': (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i64, _d, _vp, _vp]),
     'dam_kweight_segments': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _c.POINTER(_d), _vp, _i64, _vp, _vp,
                                   _c.c_size_t, _vp]),
+    'dam_scale': (_i, [_vp, _i, _i64, _d, _vp, _i, _vp]),
+    'dam_kweight_num_blocks': (_i64, [_i64, _d, _d, _d]),
+    'dam_kweight_blocks_workspace_bytes': (_c.c_size_t, [_i64, _i64, _d, _d, _d]),
+    'dam_kweight_blocks': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _d, _c.POINTER(_d), _d, _d, _vp, _vp, _c.c_size_t, _vp]),
 }
 
 

@@ -17,6 +17,7 @@
 #include "dam_common.cuh"
 
 #include <math.h>
+#include <algorithm>
 #include <mutex>
 #include <string.h>
 #include <vector>
@@ -517,6 +518,112 @@ extern "C" int dam_gated_loudness(const double* seg_sumsq, int64_t n_signals, in
     p.last = reinterpret_cast<const long long*>(block_last);
     p.inv_len = inv_block_len; p.out = lufs_out;
     gated_loudness_kernel<<<(unsigned)n_signals, kGateBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// dam_kweight_blocks: K-weighting + mean square per 400 ms gating block in one call.
+// The block geometry is evaluated on the host with pyloudnorm's own floating-point expressions
+//   T = n / rate;  num_blocks = int(round((T - T_g) / (T_g * step)) + 1),  step = 1 - overlap
+//   l_j = int(T_g * (j * step) * rate),  u_j = int(T_g * (j * step + 1) * rate)
+// (meter.py:69-78 of pyloudnorm 0.1.0), turned into disjoint segments for dam_kweight_segments, and
+// a small kernel adds the run of segments of every block.
+namespace {
+
+struct BlockGeometry {
+    std::vector<long long> bounds, first, last;
+    long long n_blocks = 0, n_seg = 0;
+};
+
+bool block_geometry(int64_t n, double rate, double T_g, double overlap, BlockGeometry* g) {
+    if (n <= 0 || rate <= 0 || T_g <= 0 || overlap < 0 || overlap >= 1) return false;
+    const double step = 1.0 - overlap;
+    const double T = (double)n / rate;
+    if ((double)n < T_g * rate) return false;
+    const long long nb = (long long)(nearbyint((T - T_g) / (T_g * step)) + 1);
+    if (nb < 1) return false;
+    std::vector<long long> lo(nb), hi(nb);
+    for (long long j = 0; j < nb; ++j) {
+        lo[j] = (long long)(T_g * ((double)j * step) * rate);
+        hi[j] = (long long)(T_g * ((double)j * step + 1) * rate);
+        if (hi[j] > n) hi[j] = n;
+    }
+    g->bounds = lo;
+    g->bounds.insert(g->bounds.end(), hi.begin(), hi.end());
+    std::sort(g->bounds.begin(), g->bounds.end());
+    g->bounds.erase(std::unique(g->bounds.begin(), g->bounds.end()), g->bounds.end());
+    g->first.resize(nb); g->last.resize(nb);
+    for (long long j = 0; j < nb; ++j) {
+        g->first[j] = std::lower_bound(g->bounds.begin(), g->bounds.end(), lo[j]) - g->bounds.begin();
+        g->last[j] = std::lower_bound(g->bounds.begin(), g->bounds.end(), hi[j]) - g->bounds.begin();
+    }
+    g->n_blocks = nb;
+    g->n_seg = (long long)g->bounds.size() - 1;
+    return g->n_seg >= 1;
+}
+
+inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+__global__ void block_sum_kernel(const double* __restrict__ seg, long long n_seg, const long long* __restrict__ first,
+                                 const long long* __restrict__ last, long long n_blocks, double inv_len,
+                                 double* __restrict__ z) {
+    const long long r = blockIdx.y;
+    const double* s = seg + r * n_seg;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n_blocks; j += (long long)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (long long k = first[j]; k < last[j]; ++k) acc += s[k];
+        z[r * n_blocks + j] = acc * inv_len;
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t dam_kweight_num_blocks(int64_t n_samples, double rate, double block_seconds, double overlap) {
+    BlockGeometry g;
+    return block_geometry(n_samples, rate, block_seconds, overlap, &g) ? (int64_t)g.n_blocks : 0;
+}
+
+extern "C" size_t dam_kweight_blocks_workspace_bytes(int64_t n_rows, int64_t n_samples, double rate,
+                                                      double block_seconds, double overlap) {
+    BlockGeometry g;
+    if (n_rows <= 0 || !block_geometry(n_samples, rate, block_seconds, overlap, &g)) return 0;
+    return align16(dam_kweight_workspace_bytes(n_rows, n_samples)) + align16((g.bounds.size() + 2 * g.n_blocks) * sizeof(long long)) +
+           align16((size_t)n_rows * g.n_seg * sizeof(double));
+}
+
+extern "C" int dam_kweight_blocks(const void* x, int dtype, int64_t n_rows, int64_t n_samples,
+                                  int64_t row_stride, int64_t samp_stride, double rate,
+                                  const double* coeffs_host, double block_seconds, double overlap,
+                                  double* z_out, void* workspace, size_t workspace_bytes, void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(x && coeffs_host && z_out && workspace, "null pointer argument");
+    BlockGeometry g;
+    DAM_CHECK_ARG(block_geometry(n_samples, rate, block_seconds, overlap, &g),
+                  "audio must be longer than the gating block (n=%lld, rate=%g, block=%g s)", (long long)n_samples, rate,
+                  block_seconds);
+    const size_t need = dam_kweight_blocks_workspace_bytes(n_rows, n_samples, rate, block_seconds, overlap);
+    DAM_CHECK_ARG(workspace_bytes >= need, "workspace too small: need %zu bytes", need);
+    DAM_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+    const size_t kw_bytes = align16(dam_kweight_workspace_bytes(n_rows, n_samples));
+    long long* d_geo = reinterpret_cast<long long*>(w + kw_bytes);
+    const size_t geo_count = g.bounds.size() + 2 * (size_t)g.n_blocks;
+    double* d_seg = reinterpret_cast<double*>(w + kw_bytes + align16(geo_count * sizeof(long long)));
+    std::vector<long long> host(g.bounds);
+    host.insert(host.end(), g.first.begin(), g.first.end());
+    host.insert(host.end(), g.last.begin(), g.last.end());
+    // pageable source: the runtime stages it before returning, so `host` may go out of scope
+    DAM_CHECK_CUDA(cudaMemcpyAsync(d_geo, host.data(), geo_count * sizeof(long long), cudaMemcpyHostToDevice, st));
+    DAM_CHECK_CUDA(cudaMemsetAsync(d_seg, 0, (size_t)n_rows * g.n_seg * sizeof(double), st));
+    const int rc = dam_kweight_segments(x, dtype, n_rows, n_samples, row_stride, samp_stride, coeffs_host,
+                                        reinterpret_cast<const int64_t*>(d_geo), g.n_seg, d_seg, workspace, kw_bytes, stream);
+    if (rc != DAM_OK) return rc;
+    const long long* d_first = d_geo + g.bounds.size();
+    const long long* d_last = d_first + g.n_blocks;
+    dim3 grid((unsigned)((g.n_blocks + 127) / 128), (unsigned)n_rows);
+    block_sum_kernel<<<grid, 128, 0, st>>>(d_seg, g.n_seg, d_first, d_last, g.n_blocks, 1.0 / (block_seconds * rate), z_out);
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }

@@ -647,3 +647,44 @@ extern "C" int dam_row_reduce(const void* x, int dtype, int64_t n_rows, int64_t 
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }
+
+// dam_scale: one signal times a HOST scalar: pyln.normalize.loudness with a gain the caller already
+// holds, MeanLoudnessModel / RandomModel per-stem gains, peak normalisation with a known peak.
+namespace {
+template <typename TI, typename TO, int V>
+__global__ void __launch_bounds__(kBlock) scale_scalar_kernel(const TI* __restrict__ x, long long n, double gain,
+                                                              TO* __restrict__ out) {
+    const long long nvec = (n + V - 1) / V;
+    for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
+        const Vec<TI, V> xv = load_vec<TI, V>(x + v * V);
+        Vec<TO, V> y;
+#pragma unroll
+        for (int j = 0; j < V; ++j) y.v[j] = (TO)((double)xv.v[j] * gain);
+        store_vec<TO, V>(out + v * V, y);
+    }
+}
+}  // namespace
+
+extern "C" int dam_scale(const void* x, int dtype, int64_t n, double gain, void* out, int out_dtype, void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(x && out, "null pointer argument");
+    DAM_CHECK_ARG((dtype == DAM_F32 || dtype == DAM_F64) && (out_dtype == DAM_F32 || out_dtype == DAM_F64),
+                  "dtypes must be F32 or F64");
+    DAM_CHECK_ARG(n >= 0, "negative size");
+    if (n == 0) return DAM_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool vec_ok = (n % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 32 == 0) && (reinterpret_cast<uintptr_t>(out) % 32 == 0);
+    const int grid = grid_for(vec_ok ? n / 4 : n, 8);
+#define DAM_SCALE1(TI, TO)                                                                              \
+    do {                                                                                               \
+        if (vec_ok) scale_scalar_kernel<TI, TO, 4><<<grid, kBlock, 0, st>>>((const TI*)x, n, gain, (TO*)out); \
+        else scale_scalar_kernel<TI, TO, 1><<<grid, kBlock, 0, st>>>((const TI*)x, n, gain, (TO*)out);        \
+    } while (0)
+    if (dtype == DAM_F32 && out_dtype == DAM_F32) DAM_SCALE1(float, float);
+    else if (dtype == DAM_F32) DAM_SCALE1(float, double);
+    else if (out_dtype == DAM_F32) DAM_SCALE1(double, float);
+    else DAM_SCALE1(double, double);
+#undef DAM_SCALE1
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}

@@ -82,6 +82,28 @@ class Meter:
         csum = np.concatenate([np.zeros((R, 1)), np.cumsum(seg.cpu().numpy(), axis=1)], axis=1)
         return (csum[:, last] - csum[:, first]) / (self.block_size * self.rate)
 
+    def block_energies_device(self, rows: torch.Tensor) -> torch.Tensor:
+        """rows [R, N] CUDA -> z [R, num_blocks] float64 on the device through the one-call entry point
+        dam_kweight_blocks (the library evaluates pyloudnorm's block geometry itself); asynchronous."""
+        if not rows.is_cuda:
+            raise ValueError('block_energies_device needs a CUDA tensor')
+        R, n = rows.shape
+        if n < self.block_size * self.rate:
+            raise ValueError('Audio must have length greater than the block size.')
+        dev = rows.device
+        lib = _lib.lib()
+        nb = lib.dam_kweight_num_blocks(n, float(self.rate), float(self.block_size), 0.75)
+        ws_bytes = lib.dam_kweight_blocks_workspace_bytes(R, n, float(self.rate), float(self.block_size), 0.75)
+        ws = torch.empty(ws_bytes // 8 + 2, dtype=torch.float64, device=dev)
+        z = torch.empty((R, nb), dtype=torch.float64, device=dev)
+        coeffs = (ctypes.c_double * 10)(*self._coeffs)
+        with torch.cuda.device(dev):
+            rc = lib.dam_kweight_blocks(_lib.ptr(rows), _lib.dtype_code(rows.dtype), R, n, rows.stride(0), rows.stride(1),
+                                        float(self.rate), coeffs, float(self.block_size), 0.75, _lib.ptr(z), _lib.ptr(ws),
+                                        ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, 'dam_kweight_blocks')
+        return z
+
     def _segment_sums(self, rows: torch.Tensor):
         R, n = rows.shape
         dev = rows.device

@@ -130,12 +130,25 @@ def scale_rows(x: torch.Tensor, factor, divide: bool = False, out_dtype=None) ->
     return out.reshape(x.shape)
 
 
+def scale(x: torch.Tensor, gain: float, out_dtype=None) -> torch.Tensor:
+    """x * gain for a host scalar gain (C entry point dam_scale): float64 product rounded to out_dtype.
+    No upload of the factor, so the call never touches the host allocator."""
+    _check_cuda(x, 'x')
+    xc = x if x.is_contiguous() else x.contiguous()
+    out_dtype = out_dtype or x.dtype
+    out = torch.empty(xc.shape, dtype=out_dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().dam_scale(_lib.ptr(xc), _lib.dtype_code(x.dtype), xc.numel(), float(gain), _lib.ptr(out),
+                                  _lib.dtype_code(out_dtype), _lib.stream_ptr())
+    _lib.check(rc, 'dam_scale')
+    return out
+
+
 def normalize_loudness(data: torch.Tensor, input_loudness: float, target_loudness: float,
                        out_dtype=None) -> torch.Tensor:
     """pyloudnorm.normalize.loudness: data * 10**((target - input)/20) (evaluation.py:64)."""
     gain = float(np.power(10.0, (target_loudness - input_loudness) / 20.0))
-    flat = data.reshape(1, -1) if data.is_contiguous() else data.contiguous().reshape(1, -1)
-    return scale_rows(flat, [gain], out_dtype=out_dtype or data.dtype).reshape(data.shape)
+    return scale(data, gain, out_dtype=out_dtype or data.dtype)
 
 
 def peak_normalize(x: torch.Tensor) -> torch.Tensor:

@@ -171,6 +171,11 @@ int dam_db_sum(const float* x, int64_t B, int64_t S, int64_t P, float* out, void
 int dam_scale_rows(const void* x, int dtype, int64_t n_rows, int64_t n, int64_t row_stride,
                    const double* factor, int divide, void* out, int out_dtype, void* stream);
 
+/* One signal times a HOST scalar: out[i] = x[i] * gain in float64, rounded to out_dtype (the scalar-gain form of
+ * K5: pyln.normalize.loudness with a known gain, evaluation.py:64; MeanLoudnessModel / RandomModel stem gains,
+ * models/baselines/mean_loudness_model.py:10-20, random_model.py:10-14). */
+int dam_scale(const void* x, int dtype, int64_t n, double gain, void* out, int out_dtype, void* stream);
+
 /*
  * Row reductions used by the normalisations: absmax[r] = max |x[r,:]| and sumsq[r] = sum x[r,:]^2
  * in float64 (either pointer may be NULL).  Results are ACCUMULATED (atomic max / add); caller
@@ -202,6 +207,25 @@ int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, int64_t n_sam
                          int64_t row_stride, int64_t samp_stride,
                          const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,
                          double* seg_sumsq, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * K-weighting + mean square of every 400 ms gating block in ONE call: z_out[r, j] of
+ * pyloudnorm.Meter.integrated_loudness (meter.py:69-78 of pyloudnorm 0.1.0) for n_rows signals.  The block
+ * geometry (num_blocks = int(round((T - T_g)/(T_g*step)) + 1), bounds int(T_g*(j*step)*rate) ...) is
+ * evaluated on the host in double precision exactly as pyloudnorm does, mapped onto disjoint segments for
+ * dam_kweight_segments, and the segments of each block are added on the device.
+ *   rate, block_seconds, overlap   44100, 0.4 and 0.75 in the reference.
+ *   z_out        DEVICE double[n_rows, dam_kweight_num_blocks(...)].
+ *   workspace    DEVICE scratch of dam_kweight_blocks_workspace_bytes(...) bytes, 16-byte aligned.
+ * Fails with DAM_ERR_INVALID when the audio is shorter than one block (pyloudnorm raises ValueError).
+ */
+int64_t dam_kweight_num_blocks(int64_t n_samples, double rate, double block_seconds, double overlap);
+size_t dam_kweight_blocks_workspace_bytes(int64_t n_rows, int64_t n_samples, double rate,
+                                          double block_seconds, double overlap);
+int dam_kweight_blocks(const void* x, int dtype, int64_t n_rows, int64_t n_samples,
+                       int64_t row_stride, int64_t samp_stride, double rate,
+                       const double* coeffs_host, double block_seconds, double overlap,
+                       double* z_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Gating and LUFS of BS.1770 on the device, from the segment sums of dam_kweight_segments:

@@ -58,3 +58,20 @@ def test_batch_of_stems_and_gating(cuda_device):
     with pytest.raises(ValueError):
         meter.integrated_loudness(np.zeros((1000, 2)))
     assert meter.integrated_loudness(np.zeros((44100, 2))) == -np.inf
+
+
+@pytest.mark.parametrize('n,rate', [(44100 * 3 + 17, 44100), (48000 * 2, 48000), (17640, 44100), (44100 * 11, 44100)])
+def test_kweight_blocks_one_call_entry_point(cuda_device, n, rate):
+    """dam_kweight_blocks (block geometry evaluated inside the library) == the oracle's block energies."""
+    from oracle import loudness as OL
+    from deep_audio_mixer_b200.loudness import Meter
+    rng = np.random.default_rng(n)
+    x = rng.normal(scale=0.2, size=(3, n))
+    z = Meter(rate).block_energies_device(torch.from_numpy(x).cuda()).cpu().numpy()
+    ref = np.stack([OL.block_energies(x[r][:, None], rate)[0] for r in range(3)])
+    assert z.shape == ref.shape
+    assert np.allclose(z, ref, rtol=1e-9, atol=1e-18), np.abs(z / ref - 1).max()
+    z2 = Meter(rate).block_energies(torch.from_numpy(x).cuda())
+    assert np.allclose(z, z2, rtol=1e-12, atol=0)
+    with pytest.raises(Exception):
+        Meter(rate).block_energies_device(torch.zeros(1, int(0.3 * rate), device='cuda', dtype=torch.float64))

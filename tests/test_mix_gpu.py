@@ -163,3 +163,18 @@ def test_no_writes_outside_outputs(cuda_device):
     assert np.array_equal(y.cpu().numpy(), view.cpu().numpy() * np.array([[2.0], [3.0], [4.0], [5.0]]))
     am, sq = mixing.row_reduce(view)
     assert np.array_equal(am.cpu().numpy(), np.abs(view.cpu().numpy()).max(axis=1))
+
+
+def test_scale_scalar_entry_point(cuda_device):
+    """dam_scale: host scalar gain, float64 product rounded to the output type (odd sizes and views too)."""
+    for n in (1, 7, 4096, 100003):
+        for dt in (torch.float32, torch.float64):
+            x = torch.randn(n, device='cuda', dtype=dt)
+            got = mixing.scale(x, 0.3183098861837907)
+            ref = (x.double() * 0.3183098861837907).to(dt)
+            assert torch.equal(got, ref)
+        x = torch.randn(2, n, device='cuda')
+        got = mixing.scale(x, -2.5, out_dtype=torch.float64)
+        assert got.dtype == torch.float64 and torch.equal(got, x.double() * -2.5)
+    y = mixing.normalize_loudness(torch.ones(2, 1000, device='cuda', dtype=torch.float64), -23.0, -20.0)
+    assert torch.allclose(y, torch.full_like(y, 10 ** (3 / 20)), rtol=0, atol=1e-15)
