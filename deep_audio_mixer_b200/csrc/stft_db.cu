@@ -450,14 +450,14 @@ __device__ __forceinline__ void stage2_task(const typename Cx<R>::type* src, con
 
     // bins k'+64q (q < 16) walk up from row k'; mirrors 2048-k'-64q (q >= 16) walk down from row
     // 1024-k'.  k' = 0 owns only q <= 16 (bins 0, 64, ..., 1024).
-    const long long stride = 64 * T;
-    OUT* o_lo = out_frame + kp * T;
-    OUT* o_hi = out_frame + (kNfft / 2 - kp) * T;
+    const int sb = (int)(64 * T * (long long)sizeof(OUT));      // one IMAD.WIDE per store (see stage2_task_pc)
+    char* o_lo = reinterpret_cast<char*>(out_frame + kp * T);
+    char* o_hi = reinterpret_cast<char*>(out_frame + (kNfft / 2 - kp) * T);
     const bool mirror_ok = kp != 0;
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
         const bool valid = q <= 16 ? true : mirror_ok;
-        OUT* o = q < 16 ? o_lo + q * stride : o_hi - (q - 16) * stride;
+        OUT* o = reinterpret_cast<OUT*>(q < 16 ? o_lo + (long long)q * (long long)sb : o_hi + (long long)(16 - q) * (long long)sb);
         const typename DbOut<R>::type db = DbOut<R>::eval(sr[q], si[q], p);
         if (valid) store_out<OUT>(o, (OUT)db);
         if (kStats && valid) st.add((float)db);
@@ -505,14 +505,15 @@ __device__ __forceinline__ void stage2_task_pc(const float2* src, const float2* 
         asm volatile("" ::: "memory");
     }
     dam_cfft32_pc(z);
-    const long long stride = 64 * T;
-    OUT* o_lo = out_frame + kp * T;
-    OUT* o_hi = out_frame + (kNfft / 2 - kp) * T;
+    // one IMAD.WIDE per store: base + (compile-time q) * (32-bit byte stride); the launcher keeps 64 rows < 2 GiB
+    const int sb = (int)(64 * T * (long long)sizeof(OUT));
+    char* o_lo = reinterpret_cast<char*>(out_frame + kp * T);
+    char* o_hi = reinterpret_cast<char*>(out_frame + (kNfft / 2 - kp) * T);
     const bool mirror_ok = kp != 0;
 #pragma unroll
     for (int q = 0; q < 32; ++q) {
         const bool valid = q <= 16 ? true : mirror_ok;
-        OUT* o = q < 16 ? o_lo + q * stride : o_hi - (q - 16) * stride;
+        OUT* o = reinterpret_cast<OUT*>(q < 16 ? o_lo + (long long)q * (long long)sb : o_hi + (long long)(16 - q) * (long long)sb);
         float re, im;
         pk_split(z[q], re, im);
         const float db = DbOut<float>::eval(re, im, p);
@@ -1113,6 +1114,8 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     DAM_CHECK_ARG(hop >= 1 && hop <= n_fft, "hop=%d must be in [1, n_fft]", hop);
     DAM_CHECK_ARG(amin >= 0.0, "amin must be non-negative");
     DAM_CHECK_ARG(out_row_stride >= 0, "out_row_stride must be non-negative");
+    DAM_CHECK_ARG((out_bin_stride > 0 ? out_bin_stride : 1 + n_samples / hop) < (1LL << 22),
+                  "rows of more than 4M frames are not supported (split the signal)");
     DAM_CHECK_ARG(out_bin_stride == 0 || out_bin_stride >= 1 + n_samples / hop,
                   "out_bin_stride=%lld is smaller than the %lld frames of a row", (long long)out_bin_stride,
                   (long long)(1 + n_samples / hop));
