@@ -83,19 +83,29 @@ __device__ __forceinline__ long long row_offset(const StftParams& p, long long r
 // division by C -- a multiply by 1/C when C is a power of two, which is bit-identical), row gain.
 // Loads are issued in batches so every thread keeps several global requests in flight; interior,
 // unit-stride, 16-byte-aligned tiles use 128-bit loads and vector shared-memory stores.
-template <typename SRC> struct VecOf { static constexpr int kN = 16 / sizeof(SRC); };
+template <typename SRC, int VB> struct VecOf { static constexpr int kN = VB / (int)sizeof(SRC); };
 
-template <typename P, typename SRC>
-__device__ __forceinline__ void unpack16(const uint4& raw, P (&v)[VecOf<SRC>::kN]) {
+// VB-byte (16 or 8) read-only vector load; an 8-byte load fills the low half
+template <int VB>
+__device__ __forceinline__ uint4 ldg_vec(const void* ptr, int v) {
+    if (VB == 16) return __ldg(reinterpret_cast<const uint4*>(ptr) + v);
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(ptr) + v);
+    return make_uint4(t.x, t.y, 0u, 0u);
+}
+
+template <typename P, typename SRC, int N>
+__device__ __forceinline__ void unpack_vec(const uint4& raw, P (&v)[N]) {
     const SRC* e = reinterpret_cast<const SRC*>(&raw);
 #pragma unroll
-    for (int j = 0; j < VecOf<SRC>::kN; ++j) v[j] = (P)e[j];
+    for (int j = 0; j < N; ++j) v[j] = (P)e[j];
 }
 
 template <typename R, int V>
 __device__ __forceinline__ void store_vec(R* dst, const R (&v)[V]) {
     constexpr int kBytes = V * (int)sizeof(R);
-    if (kBytes == 8) {
+    if (kBytes == 4) {
+        *reinterpret_cast<unsigned*>(dst) = *reinterpret_cast<const unsigned*>(v);
+    } else if (kBytes == 8) {
         *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(v);
     } else {
 #pragma unroll
@@ -124,11 +134,127 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+// Interior tile of unit-stride channels (mono or planar), every channel VB-byte aligned.  Returns the
+// number of samples staged (a multiple of the vector length; the caller finishes the tail).
+template <typename R, typename P, typename SRC, int kThreads, int VB>
+__device__ __forceinline__ int stage_planar(const StftParams& p, const Prologue<P>& pro, R* __restrict__ s_stage,
+                                            const SRC* __restrict__ src, int span, int tid) {
+    constexpr int V = VecOf<SRC, VB>::kN;
+    constexpr int U = 4;                         // vector loads in flight per thread and channel
+    const int C = p.channels;
+    const int nvec = span / V;
+    if (VB == 16 && sizeof(R) == sizeof(SRC) && sizeof(P) == sizeof(SRC) && C == 1 && pro.unit_scale && !pro.has_gain) {
+        // plain copy (same type, mono, no scaling): asynchronous 16-byte global->shared copies
+        for (int v = tid; v < nvec; v += kThreads) cp_async16(s_stage + v * V, src + v * V);
+        cp_async_wait_all();
+    } else if (C == 2 && pro.unit_scale && !pro.has_gain) {
+        // stereo source, no scaling (the inference path with the mono shim): both channels of
+        // six vectors in flight per thread, (L + R) * 0.5 == numpy's float mean over two channels
+        constexpr int U2 = 6;
+        const SRC* s1 = src + p.chan_stride;
+        for (int v0 = tid; v0 < nvec; v0 += kThreads * U2) {
+            uint4 r0[U2], r1[U2];
+#pragma unroll
+            for (int u = 0; u < U2; ++u) {
+                const int v = v0 + u * kThreads;
+                r0[u] = v < nvec ? ldg_vec<VB>(src, v) : make_uint4(0, 0, 0, 0);
+                r1[u] = v < nvec ? ldg_vec<VB>(s1, v) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < U2; ++u) {
+                const int v = v0 + u * kThreads;
+                if (v < nvec) {
+                    P a[V], c[V];
+                    R r[V];
+                    unpack_vec<P, SRC, V>(r0[u], a);
+                    unpack_vec<P, SRC, V>(r1[u], c);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) r[j] = (R)((a[j] + c[j]) * (P)0.5);
+                    store_vec<R, V>(s_stage + v * V, r);
+                }
+            }
+        }
+    } else {
+        for (int v0 = tid; v0 < nvec; v0 += kThreads * U) {
+            P acc[U][V];
+            uint4 raw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int v = v0 + u * kThreads;
+                raw[u] = v < nvec ? ldg_vec<VB>(src, v) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                unpack_vec<P, SRC, V>(raw[u], acc[u]);
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc[u][j] = pro.load(acc[u][j]);
+            }
+            for (int c = 1; c < C; ++c) {
+                const SRC* sc = src + c * p.chan_stride;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int v = v0 + u * kThreads;
+                    raw[u] = v < nvec ? ldg_vec<VB>(sc, v) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    P t[V];
+                    unpack_vec<P, SRC, V>(raw[u], t);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[u][j] += pro.load(t[j]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int v = v0 + u * kThreads;
+                if (v < nvec) {
+                    R r[V];
+#pragma unroll
+                    for (int j = 0; j < V; ++j) r[j] = (R)pro.finish(acc[u][j]);
+                    store_vec<R, V>(s_stage + v * V, r);
+                }
+            }
+        }
+    }
+    return nvec * V;
+}
+
+// Interior tile of an INTERLEAVED stereo source (L R L R ..., the frame order of a WAV file and of
+// soundfile.read): a VB-byte vector holds VB / (2 sizeof(SRC)) frames; L + R in the source precision, then
+// the same mean / gain as the planar path.
+template <typename R, typename P, typename SRC, int kThreads, int VB>
+__device__ __forceinline__ int stage_interleaved2(const Prologue<P>& pro, R* __restrict__ s_stage,
+                                                  const SRC* __restrict__ src, int span, int tid) {
+    constexpr int VE = VecOf<SRC, VB>::kN;       // elements per vector
+    constexpr int F = VE / 2;                    // frames per vector
+    constexpr int U = 6;
+    const int nvec = span / F;
+    for (int v0 = tid; v0 < nvec; v0 += kThreads * U) {
+        uint4 raw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int v = v0 + u * kThreads;
+            raw[u] = v < nvec ? ldg_vec<VB>(src, v) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int v = v0 + u * kThreads;
+            if (v < nvec) {
+                P e[VE];
+                R r[F];
+                unpack_vec<P, SRC, VE>(raw[u], e);
+#pragma unroll
+                for (int j = 0; j < F; ++j) r[j] = (R)pro.finish(pro.load(e[2 * j]) + pro.load(e[2 * j + 1]));
+                store_vec<R, F>(s_stage + v * F, r);
+            }
+        }
+    }
+    return nvec * F;
+}
+
 template <typename R, typename P, typename SRC, int kThreads>
 __device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ s_stage, long long row,
                                            long long g0, int span, int tid) {
-    constexpr int V = VecOf<SRC>::kN;
-    constexpr int U = 4;                         // vector loads in flight per thread and channel
     const SRC* __restrict__ base = reinterpret_cast<const SRC*>(p.audio) + row_offset(p, row);
     const long long n = p.n_samples;
     const int C = p.channels;
@@ -142,87 +268,23 @@ __device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ 
     pro.inv_c = ((C & (C - 1)) == 0) ? (P)1 / (P)C : (P)0;
 
     int done = 0;
-    const bool interior = g0 >= 0 && g0 + span <= n && p.samp_stride == 1;
-    if (interior) {
+    const bool interior = g0 >= 0 && g0 + span <= n;
+    if (interior && p.samp_stride == 1) {
+        // unit-stride channels: 16-byte vectors when every channel start is 16-byte aligned, else 8-byte
+        // vectors (PCM16 rows of an odd number of 8-byte groups, e.g. 220500 samples, alternate)
         const SRC* src = base + g0;
-        const bool aligned = ((reinterpret_cast<unsigned long long>(src) & 15ull) == 0) &&
-                             (C == 1 || ((p.chan_stride * (long long)sizeof(SRC)) & 15ll) == 0);
-        if (aligned) {
-            const int nvec = span / V;
-            if (sizeof(R) == sizeof(SRC) && sizeof(P) == sizeof(SRC) && C == 1 && pro.unit_scale && !pro.has_gain) {
-                // plain copy (same type, mono, no scaling): asynchronous 16-byte global->shared copies
-                for (int v = tid; v < nvec; v += kThreads) cp_async16(s_stage + v * V, src + v * V);
-                cp_async_wait_all();
-            } else if (C == 2 && pro.unit_scale && !pro.has_gain) {
-                // stereo source, no scaling (the inference path with the mono shim): both channels of
-                // six vectors in flight per thread, (L + R) * 0.5 == numpy's float mean over two channels
-                constexpr int U2 = 6;
-                const uint4* s0 = reinterpret_cast<const uint4*>(src);
-                const uint4* s1 = reinterpret_cast<const uint4*>(src + p.chan_stride);
-                for (int v0 = tid; v0 < nvec; v0 += kThreads * U2) {
-                    uint4 r0[U2], r1[U2];
-#pragma unroll
-                    for (int u = 0; u < U2; ++u) {
-                        const int v = v0 + u * kThreads;
-                        r0[u] = v < nvec ? __ldg(s0 + v) : make_uint4(0, 0, 0, 0);
-                        r1[u] = v < nvec ? __ldg(s1 + v) : make_uint4(0, 0, 0, 0);
-                    }
-#pragma unroll
-                    for (int u = 0; u < U2; ++u) {
-                        const int v = v0 + u * kThreads;
-                        if (v < nvec) {
-                            P a[V], c[V];
-                            R r[V];
-                            unpack16<P, SRC>(r0[u], a);
-                            unpack16<P, SRC>(r1[u], c);
-#pragma unroll
-                            for (int j = 0; j < V; ++j) r[j] = (R)((a[j] + c[j]) * (P)0.5);
-                            store_vec<R, V>(s_stage + v * V, r);
-                        }
-                    }
-                }
-            } else
-            for (int v0 = tid; v0 < nvec; v0 += kThreads * U) {
-                P acc[U][V];
-                uint4 raw[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int v = v0 + u * kThreads;
-                    raw[u] = v < nvec ? __ldg(reinterpret_cast<const uint4*>(src) + v) : make_uint4(0, 0, 0, 0);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    unpack16<P, SRC>(raw[u], acc[u]);
-#pragma unroll
-                    for (int j = 0; j < V; ++j) acc[u][j] = pro.load(acc[u][j]);
-                }
-                for (int c = 1; c < C; ++c) {
-                    const uint4* sc = reinterpret_cast<const uint4*>(src + c * p.chan_stride);
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int v = v0 + u * kThreads;
-                        raw[u] = v < nvec ? __ldg(sc + v) : make_uint4(0, 0, 0, 0);
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        P t[V];
-                        unpack16<P, SRC>(raw[u], t);
-#pragma unroll
-                        for (int j = 0; j < V; ++j) acc[u][j] += pro.load(t[j]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int v = v0 + u * kThreads;
-                    if (v < nvec) {
-                        R r[V];
-#pragma unroll
-                        for (int j = 0; j < V; ++j) r[j] = (R)pro.finish(acc[u][j]);
-                        store_vec<R, V>(s_stage + v * V, r);
-                    }
-                }
-            }
-            done = nvec * V;
+        const unsigned long long bits = reinterpret_cast<unsigned long long>(src) |
+                                        (C == 1 ? 0ull : (unsigned long long)(p.chan_stride * (long long)sizeof(SRC)));
+        if ((bits & 15ull) == 0) done = stage_planar<R, P, SRC, kThreads, 16>(p, pro, s_stage, src, span, tid);
+        else if constexpr (sizeof(SRC) <= 4) {
+            if ((bits & 7ull) == 0) done = stage_planar<R, P, SRC, kThreads, 8>(p, pro, s_stage, src, span, tid);
+        }
+    } else if (interior && C == 2 && p.samp_stride == 2 && p.chan_stride == 1) {
+        const SRC* src = base + 2 * g0;
+        const unsigned long long bits = reinterpret_cast<unsigned long long>(src);
+        if ((bits & 15ull) == 0) done = stage_interleaved2<R, P, SRC, kThreads, 16>(pro, s_stage, src, span, tid);
+        else if constexpr (sizeof(SRC) <= 4) {
+            if ((bits & 7ull) == 0) done = stage_interleaved2<R, P, SRC, kThreads, 8>(pro, s_stage, src, span, tid);
         }
     }
     // general path: edges (reflection), strided or unaligned sources, vector tail

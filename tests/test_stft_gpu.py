@@ -350,3 +350,36 @@ def test_frame_pitch_padded_rows(cuda_device, n, hop, ch):
     assert torch.equal(got, dense)
     with pytest.raises(ValueError):
         F.stft_db(x, hop=hop, frame_pitch=T - 1, **kw)
+
+
+@pytest.mark.parametrize('n', [30000, 30004, 30002, 30001])
+def test_pcm16_and_interleaved_staging_tiers(cuda_device, n):
+    """The staging paths of the WAV-order / PCM16 ingest: 16-byte vectors, the 8-byte tier
+    (rows whose byte length is 8 mod 16, e.g. 220500 PCM16 samples), interleaved stereo in int16 / float32 /
+    float64, and the scalar fall-back for odd offsets -- all must stage exactly the values numpy computes."""
+    x = synthetic.make_song(40 + n % 7, 3, n, kind='music', dtype=np.float32)           # [3, 2, n]
+    q = synthetic.quantise_int16(x)                                                       # [3, 2, n] int16
+    as_float = q.astype(np.float32) / np.float32(32768.0)
+    # PCM16 mono rows (row r starts at byte 2 n r: 16-, 8- or 2-byte aligned depending on n)
+    ref_mono = oracle(as_float[:, 0].astype(np.float64))
+    got = run(np.ascontiguousarray(q[:, 0]), compute_dtype=torch.float64)
+    assert np.max(np.abs(got - ref_mono)) <= 1e-4
+    # stereo: numpy float32 mean of the two scaled channels, planar and interleaved must agree bit for bit
+    mean32 = np.mean(as_float, axis=1)
+    ref_st = oracle(mean32.astype(np.float64))
+    got_planar = run(q, channel_axis=-2, compute_dtype=torch.float64)
+    got_inter = run(np.ascontiguousarray(q.transpose(0, 2, 1)), channel_axis=-1, compute_dtype=torch.float64)
+    assert np.max(np.abs(got_planar - ref_st)) <= 1e-4
+    assert np.array_equal(got_planar, got_inter)
+    # float32 and float64 interleaved (librosa / soundfile layouts)
+    ref32 = oracle(np.mean(x, axis=1).astype(np.float64))
+    got32 = run(np.ascontiguousarray(x.transpose(0, 2, 1)), channel_axis=-1, compute_dtype=torch.float64)
+    assert np.max(np.abs(got32 - ref32)) <= 1e-4
+    x64 = x.astype(np.float64)
+    ref64 = oracle(np.mean(x64, axis=1))
+    got64 = run(np.ascontiguousarray(x64.transpose(0, 2, 1)), channel_axis=-1)
+    assert np.max(np.abs(got64 - ref64)) <= 1e-4
+    # float32 arithmetic on the interleaved PCM16 source == on the planar one
+    a = run(q, channel_axis=-2)
+    b = run(np.ascontiguousarray(q.transpose(0, 2, 1)), channel_axis=-1)
+    assert np.array_equal(a, b)

@@ -36,8 +36,8 @@ def timed(fn, reps=10, warm=3):
     return a.elapsed_time(b) / reps
 
 
-def k1_case(rows, n, hop, dtype=torch.float32, compute=None, channels=1, label=''):
-    shape = (rows, channels, n) if channels > 1 else (rows, n)
+def k1_case(rows, n, hop, dtype=torch.float32, compute=None, channels=1, label='', interleaved=False):
+    shape = ((rows, n, channels) if interleaved else (rows, channels, n)) if channels > 1 else (rows, n)
     if dtype == torch.int16:
         x = (torch.randn(shape, device='cuda') * 3000).clamp(-32768, 32767).to(torch.int16)
     else:
@@ -47,7 +47,7 @@ def k1_case(rows, n, hop, dtype=torch.float32, compute=None, channels=1, label='
     out = torch.empty(rows, 1025, T, device='cuda', dtype=compute)
     kw = dict(hop=hop, compute_dtype=compute, out_dtype=compute, out=out)
     if channels > 1:
-        kw['channel_axis'] = -2
+        kw['channel_axis'] = -1 if interleaved else -2
     ms = timed(lambda: F.stft_db(x, **kw))
     byts = x.numel() * x.element_size() + out.numel() * out.element_size()
     stem_s = rows * n / SR
@@ -87,7 +87,11 @@ def main():
     res['config3'] = [k1_case(rows, 220500, 1024, torch.float32, label='fp32 mono, fp32 FFT'),
                       k1_case(rows, 220500, 1024, torch.int16, label='PCM16 mono, fp32 FFT'),
                       k1_case(rows // 2, 220500, 1024, torch.float64, label='fp64 mono, fp64 FFT (training-path dtype)'),
-                      k1_case(rows, 220500, 1024, torch.float32, channels=2, label='fp32 stereo planar, fp32 FFT')]
+                      k1_case(rows, 220500, 1024, torch.float32, channels=2, label='fp32 stereo planar, fp32 FFT'),
+                      k1_case(rows, 220500, 1024, torch.int16, channels=2, label='PCM16 stereo planar, fp32 FFT'),
+                      k1_case(rows, 220500, 1024, torch.int16, channels=2, interleaved=True, label='PCM16 stereo INTERLEAVED (WAV frame order), fp32 FFT'),
+                      k1_case(rows, 220500, 1024, torch.float32, channels=2, interleaved=True, label='fp32 stereo interleaved, fp32 FFT'),
+                      k1_case(rows // 2, 220500, 1024, torch.float64, channels=2, interleaved=True, label='fp64 stereo interleaved (soundfile.read layout), fp64 FFT')]
 
     # ---- config 2 / 4 shapes of K1 alone
     res['k1_shapes'] = [k1_case(1280, 88200, 512, torch.float32, channels=2, label='config 2: stereo, 2 s @ hop 512 (T=173)'),
