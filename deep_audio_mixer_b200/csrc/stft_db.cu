@@ -57,9 +57,6 @@ struct StftParams {
     const double* row_gain;
     const float* window;
     const void* twiddle;          // device table, Cx<R>::type [33][34]
-    const void* twiddle_r16;      // tables of the three-stage float64 kernel (double2): [16][64] | [16][4] | [516]
-    int tma_src;                  // 1: raw float64 samples may be staged by bulk copies (host-evaluated)
-    int elem_bytes;               // bytes per source sample
     int hop;
     long long T;                  // frames per row
     long long tiles_per_row, n_tiles;
@@ -865,233 +862,6 @@ stft_db_async_kernel(const StftParams p) {
 }
 
 // ==========================================================================================
-// Three-stage float64 kernel.  The two-stage float64 kernel carries a 32-point complex transform in double
-// precision per thread (128 data registers): 255 registers, ONE 8-warp CTA per SM, two warps per scheduler
-// -- it is latency bound with the FP64 pipe 30 % busy.  Here a frame of 2048 real samples is a 1024-point
-// complex transform of z[m] = x[2m] + i x[2m+1] factored 16 x 16 x 4, then the real-input split, so a thread
-// holds at most 16 complex values: 128 registers, one 16-warp CTA per SM (twice the warps).
-//   m = 64 m1 + 4 m2 + m3,  k = k1 + 16 k2 + 256 k3   (m1, m2, k1, k2 < 16; m3, k3 < 4)
-//   stage 1  thread (frame, j = 4 m2 + m3): 16 windowed sample PAIRS (one 128-bit shared load each) ->
-//            16-point transform over m1 -> x W_1024^(j k1) -> exchange [k1][68]
-//   stage 2  thread (frame, k1, m3): 16-point transform over m2 -> x W_64^(m3 k2) -> exchange [k][m3]
-//   stage 3  thread (frame, u), u = 1..127: 4-point transforms of rows u and 256 - u give Z[u + 256 k3] and
-//            Z[1024 - (u + 256 k3)] in the SAME thread, so the split
-//            X[k], X[1024-k] = E +- (-i W_2048^k) D,  E = Z[k] + conj Z[1024-k],  D = Z[k] - conj Z[1024-k]
-//            needs no further exchange: 8 bins per task, dB in registers, lanes = 8 frames x 4 tasks so a
-//            store instruction writes four row segments.  u = 0 handles rows 0 and 128 (9 bins).
-// The factor 1/2 of the split is folded into the window table (exact).  The float32 form of this kernel
-// was measured and dropped (shared-memory bound at the speed of the two-stage kernel); in float64
-// the two-stage kernel is so starved of warps that the extra exchange pays.
-constexpr int kR16Threads = 512;
-constexpr int kR16FT = 8;
-constexpr int kR16S1 = 68;          // pitch of an exchange-1 row (complex): a quarter-warp (2 k1 x 4 m3) hits 8 bank groups
-constexpr int kR16FS = 1090;        // frame stride (complex)
-constexpr int kR16Tw1 = 16 * 64, kR16Tw2 = 16 * 4, kR16TwN = 516;
-
-__device__ __forceinline__ double2 cmul_d(double2 v, double2 w) {
-    return make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
-}
-// 4-point forward transform, natural order
-__device__ __forceinline__ void fft4_d(const double2 (&z)[4], double2 (&Z)[4]) {
-    const double2 a = make_double2(z[0].x + z[2].x, z[0].y + z[2].y), b = make_double2(z[0].x - z[2].x, z[0].y - z[2].y);
-    const double2 c = make_double2(z[1].x + z[3].x, z[1].y + z[3].y), d = make_double2(z[1].x - z[3].x, z[1].y - z[3].y);
-    Z[0] = make_double2(a.x + c.x, a.y + c.y);
-    Z[2] = make_double2(a.x - c.x, a.y - c.y);
-    Z[1] = make_double2(b.x + d.y, b.y - d.x);      // b - i d
-    Z[3] = make_double2(b.x - d.y, b.y + d.x);      // b + i d
-}
-// bins k (-> ok) and 1024 - k (-> omk, skipped when null) from Z1 = Z[k], Z2 = Z[1024 - k]; tw = -i W_2048^k
-template <typename OUT, bool kStats>
-__device__ __forceinline__ void r16_emit(double2 Z1, double2 Z2, double2 tw, OUT* ok, OUT* omk, const StftParams& p,
-                                         StatAcc& st) {
-    const double2 E = make_double2(Z1.x + Z2.x, Z1.y - Z2.y);
-    const double2 D = make_double2(Z1.x - Z2.x, Z1.y + Z2.y);
-    const double2 Tm = cmul_d(D, tw);
-    const double da = DbOut<double>::eval(E.x + Tm.x, E.y + Tm.y, p);
-    store_out<OUT>(ok, (OUT)da);
-    if (kStats) st.add((float)da);
-    if (omk != nullptr) {
-        const double db = DbOut<double>::eval(E.x - Tm.x, E.y - Tm.y, p);
-        store_out<OUT>(omk, (OUT)db);
-        if (kStats) st.add((float)db);
-    }
-}
-
-constexpr size_t r16_table_bytes() {
-    return kNfft * sizeof(double) + (size_t)(kR16Tw1 + kR16Tw2 + kR16TwN) * sizeof(double2) + 16;
-}
-
-template <typename OUT, bool kStats>
-__global__ void __launch_bounds__(kR16Threads, 1)
-stft_db_r16d_kernel(const StftParams p) {
-    constexpr int kFT = kR16FT;
-    constexpr int kThreads = kR16Threads;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_win = reinterpret_cast<double*>(smem_raw);               // [2048], 0.5 * window
-    double2* s_tw1 = reinterpret_cast<double2*>(s_win + kNfft);        // [16][64]  W_1024^(j k1)
-    double2* s_tw2 = s_tw1 + kR16Tw1;                                  // [16][4]   W_64^(m3 k2)
-    double2* s_twN = s_tw2 + kR16Tw2;                                  // [513]     -i W_2048^k
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_twN + kR16TwN);     // 16 bytes
-    double2* s_x = reinterpret_cast<double2*>(bar + 2);                // [kFT][kR16FS]
-    double* s_stage = reinterpret_cast<double*>(s_x);                  // aliases s_x: [C][(kFT-1)*hop + 2048]
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    for (int i = tid; i < kNfft; i += kThreads) s_win[i] = 0.5 * (double)__ldg(p.window + i);
-    {
-        const double2* tab = reinterpret_cast<const double2*>(p.twiddle_r16);
-        for (int i = tid; i < kR16Tw1 + kR16Tw2 + kR16TwN; i += kThreads) s_tw1[i] = tab[i];
-    }
-    if (tid == 0) mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const int hop = p.hop;
-    const int span_max = (kFT - 1) * hop + kNfft;
-    const long long T = p.T;
-    const long long n = p.n_samples;
-    const int C = p.channels;
-    const unsigned tiles_per_row = (unsigned)p.tiles_per_row, n_tiles = (unsigned)p.n_tiles;
-    unsigned phase = 0;
-    StatAcc st;
-
-    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned urow = tile / tiles_per_row;
-        const long long row = urow;
-        const long long t0 = (long long)(tile - urow * tiles_per_row) * kFT;
-        const int nf = (int)((T - t0) < kFT ? (T - t0) : kFT);
-        OUT* out_row = reinterpret_cast<OUT*>(p.out) + row * p.out_row_stride + t0;
-        const long long g0 = t0 * hop - kNfft / 2;
-        const int span = (nf - 1) * hop + kNfft;
-        // raw float64 samples of an interior, 16-byte aligned tile go through the TMA unit (one bulk copy per
-        // channel issued by one thread); everything else through the generic staging code
-        const double* src = reinterpret_cast<const double*>(p.audio) + row_offset(p, row) + g0;
-        const bool tma = p.tma_src && g0 >= 0 && g0 + span <= n && (reinterpret_cast<unsigned long long>(src) & 15ull) == 0;
-
-        fence_proxy_async();  // this thread's reads of s_x (stage 3) are ordered before the TMA writes below
-        __syncthreads();      // previous tile's stage 3 has finished reading s_x (and the tables are loaded)
-        if (tma) {
-            if (tid == 0) {
-                const unsigned bytes = (unsigned)span * 8u;
-                mbar_expect_tx(bar, bytes * (unsigned)C);
-                bulk_g2s(s_stage, src, bytes, bar);
-                if (C == 2) bulk_g2s(s_stage + span_max, src + p.chan_stride, bytes, bar);
-            }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            if (C == 2) {
-                double2* l2 = reinterpret_cast<double2*>(s_stage);
-                const double2* r2 = reinterpret_cast<const double2*>(s_stage + span_max);
-                for (int v = tid; v < span / 2; v += kThreads) {
-                    double2 a = l2[v];
-                    const double2 b = r2[v];
-                    a.x = (a.x + b.x) * 0.5; a.y = (a.y + b.y) * 0.5;       // numpy's float64 mean over two channels
-                    l2[v] = a;
-                }
-                __syncthreads();
-            }
-        } else {
-            if (p.audio_dtype == DAM_F32)      stage_tile<double, float, float, kThreads>(p, s_stage, row, g0, span, tid);
-            else if (p.audio_dtype == DAM_I16) stage_tile<double, float, short, kThreads>(p, s_stage, row, g0, span, tid);
-            else                               stage_tile<double, double, double, kThreads>(p, s_stage, row, g0, span, tid);
-            __syncthreads();
-        }
-        if (p.l2_prefetch) {
-            const unsigned nt = tile + gridDim.x;
-            if (nt < n_tiles) {
-                const unsigned nrow = nt / tiles_per_row;
-                const long long nt0 = (long long)(nt - nrow * tiles_per_row) * kFT;
-                const int nnf = (int)((T - nt0) < kFT ? (T - nt0) : kFT);
-                prefetch_tile<kThreads>(p, nrow, nt0 * hop - kNfft / 2, (nnf - 1) * hop + kNfft, p.elem_bytes, tid);
-            }
-        }
-
-        const int f = tid >> 6, r = tid & 63;          // stages 1 and 2: 64 tasks per frame
-        const int fc = f < nf ? f : nf - 1;
-        // ---- stage 1: task (f, j = r)
-        {
-            double re[16], im[16];
-            const double2* fx = reinterpret_cast<const double2*>(s_stage + fc * hop) + r;
-            const double2* fw = reinterpret_cast<const double2*>(s_win) + r;
-#pragma unroll
-            for (int m1 = 0; m1 < 16; ++m1) {
-                const double2 x = fx[64 * m1], w = fw[64 * m1];
-                re[m1] = x.x * w.x;
-                im[m1] = x.y * w.y;
-            }
-            __syncthreads();     // every sample pair is in registers; s_stage may be overwritten
-            if (f < nf) {
-                dam_cfft16<double>(re, im);
-                double2* dst = s_x + f * kR16FS + r;
-                const double2* tw = s_tw1 + r;
-                dst[0] = make_double2(re[0], im[0]);
-#pragma unroll
-                for (int k1 = 1; k1 < 16; ++k1) dst[k1 * kR16S1] = cmul_d(make_double2(re[k1], im[k1]), tw[k1 * 64]);
-            }
-        }
-        __syncthreads();
-        // ---- stage 2: task (f, k1 = r / 4, m3 = r % 4)
-        {
-            double re[16], im[16];
-            const int k1 = r >> 2, m3 = r & 3;
-            const double2* src2 = s_x + fc * kR16FS + k1 * kR16S1 + m3;
-#pragma unroll
-            for (int m2 = 0; m2 < 16; ++m2) {
-                const double2 a = src2[4 * m2];
-                re[m2] = a.x;
-                im[m2] = a.y;
-            }
-            __syncthreads();     // exchange 1 is consumed; exchange 2 goes to the same buffer
-            if (f < nf) {
-                dam_cfft16<double>(re, im);
-                double2* dst = s_x + f * kR16FS + r;         // (k1 + 16 k2) * 4 + m3 = r + 64 k2
-                const double2* tw = s_tw2 + m3;
-                dst[0] = make_double2(re[0], im[0]);
-#pragma unroll
-                for (int k2 = 1; k2 < 16; ++k2) dst[64 * k2] = cmul_d(make_double2(re[k2], im[k2]), tw[k2 * 4]);
-            }
-        }
-        __syncthreads();
-        // ---- stage 3: two tasks per thread, lanes = 8 frames x 4 tasks
-        {
-            const int ki = tid & 3, ft = (tid >> 2) & 7;
-            if (ft < nf) {
-                OUT* out_frame = out_row + ft;
-                const size_t BS = (size_t)p.bin_stride;
-                const size_t S = 256 * BS;
-                const double2* xf = s_x + ft * kR16FS;
-#pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-                    const int u = 4 * ((tid >> 5) + 16 * pass) + ki;
-                    const int ub = u == 0 ? 128 : 256 - u;
-                    const double2 za[4] = {xf[4 * u], xf[4 * u + 1], xf[4 * u + 2], xf[4 * u + 3]};
-                    const double2 zb[4] = {xf[4 * ub], xf[4 * ub + 1], xf[4 * ub + 2], xf[4 * ub + 3]};
-                    double2 ZA[4], ZB[4];
-                    fft4_d(za, ZA);
-                    fft4_d(zb, ZB);
-                    OUT* P0 = out_frame + (size_t)u * BS;         // bins u + 256 i       at P0 + i S
-                    OUT* Q0 = out_frame + (size_t)ub * BS;        // bins 256 - u + 256 i at Q0 + i S
-                    const double2* ta = s_twN + u;
-                    const double2* tb = s_twN + ub;
-                    if (u != 0) {
-                        r16_emit<OUT, kStats>(ZA[0], ZB[3], ta[0], P0, Q0 + 3 * S, p, st);            // u,       1024 - u
-                        r16_emit<OUT, kStats>(ZA[1], ZB[2], ta[256], P0 + S, Q0 + 2 * S, p, st);      // u + 256, 768 - u
-                        r16_emit<OUT, kStats>(ZB[0], ZA[3], tb[0], Q0, P0 + 3 * S, p, st);            // 256 - u, 768 + u
-                        r16_emit<OUT, kStats>(ZB[1], ZA[2], tb[256], Q0 + S, P0 + 2 * S, p, st);      // 512 - u, 512 + u
-                    } else {
-                        r16_emit<OUT, kStats>(ZA[0], ZA[0], ta[0], P0, P0 + 4 * S, p, st);            // 0, 1024
-                        r16_emit<OUT, kStats>(ZA[1], ZA[3], ta[256], P0 + S, P0 + 3 * S, p, st);      // 256, 768
-                        r16_emit<OUT, kStats>(ZA[2], ZA[2], ta[512], P0 + 2 * S, (OUT*)nullptr, p, st);   // 512
-                        r16_emit<OUT, kStats>(ZB[0], ZB[3], tb[0], Q0, Q0 + 3 * S, p, st);            // 128, 896
-                        r16_emit<OUT, kStats>(ZB[1], ZB[2], tb[256], Q0 + S, Q0 + 2 * S, p, st);      // 384, 640
-                    }
-                    if (kStats) st.fold();
-                }
-            }
-        }
-    }
-    if (kStats) st.flush(p.stats, lane);
-}
-
-// ==========================================================================================
 // Generic window sizes (power of two, 64..8192 except 2048): a plain shared-memory radix-2 transform,
 // one CTA per (row, tile of 8 frames).  The reference only ever uses window_size = 2048
 // (data/dataset.py:132), so this path exists for API completeness (window_size is a runtime argument
@@ -1223,7 +993,6 @@ int launch_generic(const StftParams& p, int n_fft, cudaStream_t stream) {
 struct TwiddleTables {
     float2* f32 = nullptr;
     double2* f64 = nullptr;
-    double2* r16 = nullptr;        // [16][64] W_1024^(j k1) | [16][4] W_64^(m3 k2) | [516] -i W_2048^k
 };
 
 int get_twiddles(TwiddleTables** out) {
@@ -1284,36 +1053,6 @@ int get_twiddles(TwiddleTables** out) {
         DAM_CHECK_CUDA(cudaMemcpy(dd, hd.data(), hd.size() * sizeof(double2), cudaMemcpyHostToDevice));
         t.f32 = df;
         t.f64 = dd;
-        {
-            // exp(-2 pi i num / den), exact on the octants
-            auto cis = [two_pi](long long num, long long den, long double& c, long double& sn) {
-                num %= den;
-                if ((8 * num) % den == 0) {
-                    const int o = (int)(8 * num / den);
-                    const long double h = 0.70710678118654752440084436210484903928L;
-                    const long double cs[8] = {1, h, 0, -h, -1, -h, 0, h};
-                    const long double ss[8] = {0, h, 1, h, 0, -h, -1, -h};
-                    c = cs[o]; sn = -ss[o];
-                } else {
-                    const long double ang = two_pi * (long double)num / (long double)den;
-                    c = cosl(ang); sn = -sinl(ang);
-                }
-            };
-            std::vector<double2> hr(kR16Tw1 + kR16Tw2 + kR16TwN, make_double2(0.0, 0.0));
-            long double c, sn;
-            for (int k1 = 0; k1 < 16; ++k1)
-                for (int j = 0; j < 64; ++j) { cis((long long)j * k1, 1024, c, sn); hr[k1 * 64 + j] = make_double2((double)c, (double)sn); }
-            for (int k2 = 0; k2 < 16; ++k2)
-                for (int m3 = 0; m3 < 4; ++m3) { cis((long long)m3 * k2, 64, c, sn); hr[kR16Tw1 + k2 * 4 + m3] = make_double2((double)c, (double)sn); }
-            for (int k = 0; k <= 512; ++k) {          // -i (c + i sn) = sn - i c
-                cis(k, 2048, c, sn);
-                hr[kR16Tw1 + kR16Tw2 + k] = make_double2((double)sn, (double)(-c));
-            }
-            double2* dr = nullptr;
-            DAM_CHECK_CUDA(cudaMalloc(&dr, hr.size() * sizeof(double2)));
-            DAM_CHECK_CUDA(cudaMemcpy(dr, hr.data(), hr.size() * sizeof(double2), cudaMemcpyHostToDevice));
-            t.r16 = dr;
-        }
     }
     *out = &t;
     return DAM_OK;
@@ -1360,43 +1099,6 @@ int launch(StftParams p, cudaStream_t stream) {
     if (trace) fprintf(stderr, "[dam] stft_db_kernel FT=%d pc=%d f%d smem=%zu occ=%d hop=%d C=%d T=%lld\n", kFT, (int)kPc,
                        (int)sizeof(R) * 8, smem, occ, p.hop, p.channels, (long long)p.T);
     kern<<<(unsigned)grid, kThreads, smem, stream>>>(p);
-    DAM_CHECK_CUDA(cudaGetLastError());
-    return DAM_OK;
-}
-
-template <typename OUT, bool kStats>
-int launch_r16d(StftParams p, cudaStream_t stream) {
-    p.tiles_per_row = (p.T + kR16FT - 1) / kR16FT;
-    p.n_tiles = p.tiles_per_row * p.n_rows;
-    DAM_CHECK_ARG(p.n_tiles < 0x7fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
-                  (long long)p.n_tiles);
-    static const int pf_env = [] { const char* e = getenv("DAM_K1_PREFETCH"); return e ? atoi(e) : 1; }();
-    p.l2_prefetch = pf_env;
-    p.elem_bytes = p.audio_dtype == DAM_I16 ? 2 : (p.audio_dtype == DAM_F32 ? 4 : 8);
-    p.tma_src = p.audio_dtype == DAM_F64 && p.channels <= 2 && p.input_scale == 1.0 && p.row_gain == nullptr &&
-                p.samp_stride == 1 && (p.hop & 1) == 0 && (p.channels == 1 || ((p.chan_stride * 8) & 15ll) == 0);
-    const size_t stage = (size_t)(p.tma_src ? p.channels : 1) * ((size_t)(kR16FT - 1) * p.hop + kNfft) * sizeof(double);
-    const size_t xch = (size_t)kR16FT * kR16FS * sizeof(double2);
-    const size_t smem = r16_table_bytes() + (stage > xch ? stage : xch);
-    if (smem > 227 * 1024) return 1;          // caller falls back to the two-stage kernel
-    auto kern = stft_db_r16d_kernel<OUT, kStats>;
-    static std::mutex mu;
-    static bool configured[64] = {};
-    int dev = 0;
-    DAM_CHECK_CUDA(cudaGetDevice(&dev));
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (!configured[dev]) {
-            DAM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            configured[dev] = true;
-        }
-    }
-    long long grid = (long long)dam_sm_count();
-    if (grid > p.n_tiles) grid = p.n_tiles;
-    static const bool trace = getenv("DAM_K1_TRACE") != nullptr;
-    if (trace) fprintf(stderr, "[dam] stft_db_r16d_kernel smem=%zu hop=%d C=%d T=%lld tma=%d\n", smem, p.hop, p.channels,
-                       (long long)p.T, p.tma_src);
-    kern<<<(unsigned)grid, kR16Threads, smem, stream>>>(p);
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }
@@ -1496,7 +1198,6 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     p.floor_db_d = amin > 0.0 ? multiplier * log10(amin) : -INFINITY;
     p.floor_db = (float)p.floor_db_d;
     p.out = out; p.stats = stats;
-    p.tma_src = 0; p.elem_bytes = 0; p.twiddle_r16 = nullptr;
     p.bin_stride = out_bin_stride > 0 ? out_bin_stride : p.T;
     p.out_row_stride = out_row_stride > 0 ? out_row_stride : (long long)(n_fft / 2 + 1) * p.bin_stride;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -1543,16 +1244,6 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
         return st ? launch<float, float, true, 8>(p, s) : launch<float, float, false, 8>(p, s);
     }
     p.twiddle = tw->f64;
-    p.twiddle_r16 = tw->r16;
-    // float64: the three-stage kernel (16 warps per SM) unless DAM_K1_R16D=0 or the hop is odd (sample pairs
-    // are loaded as 128-bit words)
-    static const int r16_env = [] { const char* e = getenv("DAM_K1_R16D"); return e ? atoi(e) : 1; }();
-    if (r16_env > 0 && (hop % 2) == 0) {
-        int rc2;
-        if (out_dtype == DAM_F32) rc2 = st ? launch_r16d<float, true>(p, s) : launch_r16d<float, false>(p, s);
-        else rc2 = st ? launch_r16d<double, true>(p, s) : launch_r16d<double, false>(p, s);
-        if (rc2 <= 0) return rc2;
-    }
     if (out_dtype == DAM_F32) return st ? launch<double, float, true, 8>(p, s) : launch<double, float, false, 8>(p, s);
     return st ? launch<double, double, true, 8>(p, s) : launch<double, double, false, 8>(p, s);
 }
