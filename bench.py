@@ -158,6 +158,25 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank (and so the pages of its pinned host buffers, by first touch) to the CPUs NVML reports as
+    local to its GPU: with several ranks the end-to-end leg is bound by host memory / PCIe root placement."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return sorted(use)[:1] + [len(use)]
+    except Exception:            # noqa: BLE001 -- best effort; the bench runs unpinned otherwise
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -171,6 +190,7 @@ def run_ours(args):
         raise SystemExit('bench.py needs a CUDA device: there is no CPU fallback')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     _lib.lib()
@@ -350,6 +370,7 @@ def run_ours(args):
                'h2d_bytes_per_step': int(raw_host.numel() * 4 + m_host.numel() * 4),
                'd2h_bytes_per_step': int(out_host.numel() * 8 + lufs_host.numel() * 8),
                'ms_per_step': med, 'step_ms': [round(v, 3) for v in step_ms], 'statistic': 'median step, max over ranks',
+               'cpu_binding': numa,
                'pcie_ceiling': 'measured on this pool (profiles/r01_pcie_probe.json): 55.6 GB/s H2D alone, 52.5 GB/s with a '
                                'concurrent D2H; this step moves %.2f GB up' % (raw_host.numel() * 4 / 1e9),
                'check': float(lufs_host[0])}
