@@ -78,6 +78,13 @@ __device__ __forceinline__ void store_vec(T* p, const Vec<T, V>& r) {
     }
 }
 
+// Product and sum with SEPARATE roundings (numpy: `track * mask` is a rounded array, then np.sum adds): the
+// intrinsics are never contracted into an FMA, which would change the last bit of the mix.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
 // ------------------------------------------------------------------------------------------
 // K2 gain-mask apply + stem sum
 struct GainMixParams {
@@ -153,8 +160,8 @@ __global__ void __launch_bounds__(kBlock, 4) gain_mix_kernel(const GainMixParams
                         Vec<TO, V> y;
 #pragma unroll
                         for (int j = 0; j < V; ++j) {
-                            const TC prod = (TC)x[u].v[j] * g[u];
-                            acc[j] = (s0 + u) == 0 ? prod : acc[j] + prod;
+                            const TC prod = mul_rn((TC)x[u].v[j], g[u]);
+                            acc[j] = (s0 + u) == 0 ? prod : add_rn(acc[j], prod);
                             y.v[j] = (TO)prod;
                         }
                         if (sout) store_vec<TO, V>(sout + (long long)(s0 + u) * p.n_channels * n, y);
@@ -176,8 +183,8 @@ __global__ void __launch_bounds__(kBlock, 4) gain_mix_kernel(const GainMixParams
                         gd = __ldg(gains + (long long)s * K + k);
                     }
                     const TC g = zero_mask ? TC(0) : (TC)gd;
-                    const TC prod = (TC)x.v[j] * g;
-                    acc[j] = s == 0 ? prod : acc[j] + prod;
+                    const TC prod = mul_rn((TC)x.v[j], g);
+                    acc[j] = s == 0 ? prod : add_rn(acc[j], prod);
                     y.v[j] = (TO)prod;
                 }
                 if (sout) store_vec<TO, V>(sout + (long long)s * p.n_channels * n, y);

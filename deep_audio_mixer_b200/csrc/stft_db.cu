@@ -114,12 +114,17 @@ __device__ __forceinline__ void store_vec(R* dst, const R (&v)[V]) {
     }
 }
 
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+
 template <typename P>
 struct Prologue {
     P scale, gain, inv_c, f_c;
     int C;
     bool unit_scale, has_gain;
-    __device__ __forceinline__ P load(P raw) const { return unit_scale ? raw : raw * scale; }
+    // x * input_scale is rounded on its own (numpy: `x / 32768` is an array before the channels are added);
+    // the intrinsic keeps ptxas from contracting it into the channel sum
+    __device__ __forceinline__ P load(P raw) const { return unit_scale ? raw : mul_rn(raw, scale); }
     __device__ __forceinline__ P finish(P acc) const {
         if (C > 1) acc = (inv_c != (P)0) ? acc * inv_c : acc / f_c;
         return has_gain ? gain * acc : acc;

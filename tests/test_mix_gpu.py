@@ -31,6 +31,13 @@ def test_gain_mix_float64_mask_path_bit_exact(cuda_device, S, C, N, K):
     assert np.array_equal(res['mix'].cpu().numpy(), ref_mix)
     assert np.allclose(res['peak'].cpu().numpy(), np.abs(ref_mix).max(axis=1), rtol=0, atol=0)
     assert np.allclose(res['sumsq'].cpu().numpy(), (ref_mix ** 2).sum(axis=1), rtol=1e-12)
+    # mix only (the pipeline's call): without the per-stem outputs the compiler is free to contract the product
+    # into the sum -- the kernel must still round the product first, like numpy's `track * mask`
+    only = mixing.gain_mix(cuda(stems), gains, want_mix=True)
+    assert np.array_equal(only['mix'].cpu().numpy(), ref_mix)
+    only32 = mixing.gain_mix(cuda(stems), gains[:, :1], hold_single=True, compute_dtype=torch.float32, want_mix=True)
+    ref32 = OM.stem_sum(stems * gains[:, :1, None].astype(np.float32))
+    assert np.array_equal(only32['mix'].cpu().numpy(), ref32)
 
 
 def test_gain_mix_float64_stems_and_unaligned_views(cuda_device):
