@@ -144,6 +144,15 @@ struct TileLoader {
             reg[k] = idx < w_len[r] ? x[w_base[r] + idx * samp_stride] : T(0);
         }
     }
+    // The warp's 32 chunks are full and consecutive in one unit-stride row (all but the ~1/54 warps that
+    // straddle a row end): chunk r starts at q0 + r * kChunk, so the 16 loads of a step are one base pointer
+    // plus compile-time offsets -- no per-element base / length look-ups (they were 6 of the 40 instructions
+    // per sample that made pass C issue bound).
+    __device__ __forceinline__ void load_fast(const T* __restrict__ q0, int sb, int lane) {
+        const T* q = q0 + (lane >> 4) * kChunk + (lane & 15) + sb * kSub;
+#pragma unroll
+        for (int k = 0; k < kSub; ++k) reg[k] = q[k * 2 * kChunk];
+    }
     __device__ __forceinline__ void store(T* __restrict__ tile, int lane) const {
 #pragma unroll
         for (int k = 0; k < kSub; ++k) {
@@ -174,6 +183,16 @@ __device__ __forceinline__ ChunkId publish_chunk(const KwParams& p, long long it
     return id;
 }
 
+// warp-uniform: are this warp's 32 chunks full, consecutive and unit-stride?  q0 = first sample of the warp's first chunk
+template <typename T>
+__device__ __forceinline__ bool warp_fast_path(const KwParams& p, const ChunkId& id, const T* x, const T** q0) {
+    const long long row0 = __shfl_sync(0xffffffffu, id.row, 0);
+    const long long chunk0 = __shfl_sync(0xffffffffu, id.chunk, 0);
+    const bool ok = id.active && id.len == kChunk && id.row == row0 && p.samp_stride == 1;
+    *q0 = x + row0 * p.row_stride + chunk0 * kChunk;
+    return __all_sync(0xffffffffu, ok);
+}
+
 // pass A: zero-state end state of each full chunk (the last chunk's end state is never needed)
 template <typename T>
 __global__ void __launch_bounds__(kBlock) kw_chunk_state_kernel(const KwParams p) {
@@ -194,13 +213,15 @@ __global__ void __launch_bounds__(kBlock) kw_chunk_state_kernel(const KwParams p
         const ChunkId id = publish_chunk(p, item, s_base, s_len);
         __syncwarp();
         TileLoader<T> ld;
-        ld.load(x, w_base, w_len, 0, p.samp_stride, lane);
+        const T* q0;
+        const bool fast = warp_fast_path<T>(p, id, x, &q0);
+        if (fast) ld.load_fast(q0, 0, lane); else ld.load(x, w_base, w_len, 0, p.samp_stride, lane);
         ld.store(w_tile, lane);
         __syncwarp();
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         for (int sb = 0; sb < kChunk / kSub; ++sb) {
             const bool more = sb + 1 < kChunk / kSub;
-            if (more) ld.load(x, w_base, w_len, sb + 1, p.samp_stride, lane);
+            if (more) { if (fast) ld.load_fast(q0, sb + 1, lane); else ld.load(x, w_base, w_len, sb + 1, p.samp_stride, lane); }
             const T* mine = w_tile + (sb & 1) * kBlock * kPitch + lane * kPitch;
 #pragma unroll
             for (int j = 0; j < kSub; ++j) {
@@ -298,7 +319,9 @@ __global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
         const ChunkId id = publish_chunk(p, item, s_base, s_len);
         __syncwarp();
         TileLoader<T> ld;
-        ld.load(x, w_base, w_len, 0, p.samp_stride, lane);
+        const T* q0;
+        const bool fast = warp_fast_path<T>(p, id, x, &q0);
+        if (fast) ld.load_fast(q0, 0, lane); else ld.load(x, w_base, w_len, 0, p.samp_stride, lane);
         const long long i0 = id.chunk * kChunk;
         const long long len = id.len;
         double s[4] = {0, 0, 0, 0};
@@ -324,7 +347,7 @@ __global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
 
         for (int sb = 0; sb < kChunk / kSub; ++sb) {
             const bool more = sb + 1 < kChunk / kSub;
-            if (more) ld.load(x, w_base, w_len, sb + 1, p.samp_stride, lane);
+            if (more) { if (fast) ld.load_fast(q0, sb + 1, lane); else ld.load(x, w_base, w_len, sb + 1, p.samp_stride, lane); }
             const T* mine = w_tile + (sb & 1) * kBlock * kPitch + lane * kPitch;
             const long long base = (long long)sb * kSub;
             if (base < len) {

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kBlock) bus_sum_i16_kernel(const BusParams p, 
                 if (p.group[s] != g) continue;
                 const Vec<short, V> x = load_vec<short, V>(in + s * p.stem_stride + i0);
 #pragma unroll
-                for (int j = 0; j < V; ++j) acc[j] += (float)x.v[j] * scale;
+                for (int j = 0; j < V; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn((float)x.v[j], scale));   // never an FMA
             }
             if (V == 8) {
                 reinterpret_cast<float4*>(outp + (long long)g * p.n_elems + i0)[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
