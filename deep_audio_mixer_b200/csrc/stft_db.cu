@@ -1204,6 +1204,9 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     p.floor_db = (float)p.floor_db_d;
     p.out = out; p.stats = stats;
     p.bin_stride = out_bin_stride > 0 ? out_bin_stride : p.T;
+    DAM_CHECK_ARG(out_row_stride == 0 || out_row_stride >= (int64_t)(n_fft / 2 + 1) * p.bin_stride,
+                  "out_row_stride=%lld is smaller than one plane (%lld elements)", (long long)out_row_stride,
+                  (long long)(n_fft / 2 + 1) * p.bin_stride);
     p.out_row_stride = out_row_stride > 0 ? out_row_stride : (long long)(n_fft / 2 + 1) * p.bin_stride;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (n_fft != kNfft) {

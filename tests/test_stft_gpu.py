@@ -383,3 +383,25 @@ def test_pcm16_and_interleaved_staging_tiers(cuda_device, n):
     a = run(q, channel_axis=-2)
     b = run(np.ascontiguousarray(q.transpose(0, 2, 1)), channel_axis=-1)
     assert np.array_equal(a, b)
+
+
+def test_frame_pitch_other_window_sizes_and_plane_check(cuda_device):
+    """out_bin_stride on the generic-window kernel, and the refusal of planes that would overlap (Python
+    wrapper and C ABI both check)."""
+    import ctypes
+    from deep_audio_mixer_b200 import _lib
+    x = torch.randn(3, 12000, device='cuda')
+    for n_fft, hop in ((1024, 256), (512, 500), (4096, 1024)):
+        dense = F.stft_db(x, n_fft, hop)
+        T = dense.shape[-1]
+        view = F.stft_db(x, n_fft, hop, frame_pitch=F.aligned_pitch(T) + 8)
+        assert view.stride(-2) == F.aligned_pitch(T) + 8 and torch.equal(view, dense)
+    T = 1 + 12000 // 1024
+    out = torch.empty(3 * 1025 * (T + 8), device='cuda')
+    with pytest.raises(ValueError):
+        F.stft_db(x, out=out, out_row_stride=1025 * T, frame_pitch=T + 8)
+    win = F.hann_window(2048, x.device)
+    rc = _lib.lib().dam_stft_db(_lib.ptr(x), _lib.dtype_code(x.dtype), 1, 3, 12000, 12000, 0, 1, 0, 0, 1.0, None,
+                                _lib.ptr(win), 2048, 1024, 1e-5, 20.0, _lib.dtype_code(torch.float32), _lib.ptr(out),
+                                _lib.dtype_code(torch.float32), 1025 * T, T + 8, None, None)
+    assert rc != 0 and b'smaller than one plane' in _lib.lib().dam_last_error()
