@@ -346,9 +346,11 @@ def run_ours(args):
             """Per-step CUDA-event times of run_host (upload + kernels + download each step); the rate is
             quoted on the MEDIAN step (one host-side hiccup -- page migration, another process on the PCIe
             root -- otherwise triples a 5-step sum) and every step time is listed beside it."""
-            for _ in range(3):
+            # warm-up: the caching allocator needs a few steps to grow the pools the three streams recycle
+            # (every cudaMalloc on the way synchronises); fixed count so that all ranks stay in step
+            for _ in range(10):
                 pipe.run_host(src_host, m_host, out_host, lufs_host, streams=streams)
-            torch.cuda.synchronize()
+                torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             times = []

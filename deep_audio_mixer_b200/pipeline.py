@@ -125,7 +125,7 @@ class SegmentBatchPipeline:
         return dict(mix=norm, lufs=lufs, peak=res['peak'], sumsq=res['sumsq'], features=feats, m=m)
 
     def run_host(self, raw_host: torch.Tensor, m_host: torch.Tensor, out_host: torch.Tensor,
-                 lufs_host: torch.Tensor, sub_batch: int = 8, streams=None):
+                 lufs_host: torch.Tensor, sub_batch: int = 4, streams=None):
         """End-to-end form with HOST (pinned) buffers: raw_host [B, S, C, N] float32 -> out_host
         [B, C, N] float64 and lufs_host [B].  The batch is cut into sub-batches; uploads, kernels and
         downloads of consecutive sub-batches overlap on three streams."""
