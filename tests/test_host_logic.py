@@ -29,6 +29,43 @@ def test_library_exports_every_declared_symbol():
     assert lib.dam_kweight_workspace_bytes(2, 1000) == 2 * 4 * 4 * 8
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype in include/dam_b200.h has as many parameters as its ctypes signature, with the same
+    pointer / integer / double kinds in the same order (an ABI drift between header, library and binding
+    would otherwise only show up as garbage on the GPU)."""
+    from deep_audio_mixer_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'dam_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    protos = dict(re.findall(r'\b(dam_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', header, flags=re.S))
+    assert set(protos) == set(_lib.SIGNATURES)
+
+    def kind_of_c(param):
+        param = param.strip()
+        if param in ('void', ''):
+            return None
+        if '*' in param:
+            return 'ptr'
+        if re.match(r'(const\s+)?double\b', param):
+            return 'f64'
+        if re.match(r'(const\s+)?(int64_t|size_t)\b', param):
+            return 'i64'
+        if re.match(r'(const\s+)?int\b', param):
+            return 'i32'
+        raise AssertionError('unclassified parameter: %r' % param)
+
+    def kind_of_ctypes(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, 'contents') or getattr(t, '_type_', None) is not None and \
+                isinstance(getattr(t, '_type_'), type):
+            return 'ptr'
+        return {ctypes.c_double: 'f64', ctypes.c_int64: 'i64', ctypes.c_size_t: 'i64', ctypes.c_int: 'i32',
+                ctypes.c_int32: 'i32'}[t]
+
+    for name, params in protos.items():
+        c_kinds = [k for k in (kind_of_c(q) for q in params.split(',')) if k is not None]
+        py_kinds = [kind_of_ctypes(t) for t in _lib.SIGNATURES[name][1]]
+        assert c_kinds == py_kinds, (name, c_kinds, py_kinds)
+
+
 def test_product_does_not_import_oracle():
     pkg = os.path.join(ROOT, 'deep_audio_mixer_b200')
     for fn in os.listdir(pkg):

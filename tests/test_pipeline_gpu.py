@@ -182,3 +182,25 @@ def test_evaluator_and_baselines(cuda_device):
     assert abs(stats['sum_error'] - OL.loudness_dict_diff(OL.evaluate_loudness(test_tracks, sr), ref_rel)) < 1e-7
     mix = E.produce_mixture(test_tracks, sr=sr)
     assert torch.equal(mix, norm)
+
+
+def test_integration_md_binding_stub_runs(cuda_device):
+    """The ctypes stub INTEGRATION.md shows a reference maintainer (section B) is executed verbatim against the
+    built library, so the document cannot drift from the C ABI."""
+    import os
+    import re
+    from deep_audio_mixer_b200 import _lib, features as F
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, 'INTEGRATION.md')).read()
+    block = re.search(r"```python\n# data/dam_binding.py.*?```", text, re.S).group(0)
+    code = block[len('```python\n'):-3].replace("'/path/to/libdam_b200.so'", repr(_lib.LIB_PATH))
+    ns = {}
+    exec(compile(code, 'INTEGRATION.md', 'exec'), ns)
+    x = torch.randn(3, 44100, device='cuda', dtype=torch.float64)
+    win = torch.hann_window(2048).cuda()
+    got = ns['stft_db'](x, win)
+    assert got.dtype == torch.float64 and torch.equal(got, F.stft_db(x, window=win))
+    x32 = torch.randn(2, 30000, device='cuda')
+    assert torch.equal(ns['stft_db'](x32, win, 2048, 512), F.stft_db(x32, hop=512, window=win))
+    q = (x32 * 3000).to(torch.int16)
+    assert torch.equal(ns['stft_db'](q, win), F.stft_db(q, window=win))
