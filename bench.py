@@ -108,11 +108,12 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def cpu_reference_throughput(n_seg_sample, steps, warmup):
+def cpu_reference_throughput(n_seg_sample, steps, warmup, variants=False):
     """The oracle port (oracle/cpu_reference.py) on the host cores, on a bounded sample of the workload.
     Segments are independent, so they are spread over a thread pool with one worker per core (torch and
     numpy release the GIL in their kernels; measured 2.4x faster than one segment at a time with
-    torch's own intra-op threads)."""
+    torch's own intra-op threads).  ``variants`` adds the other three cells of SURVEY 8(d)'s table (one
+    thread / all cores x float32 / float64 features) on small samples."""
     import concurrent.futures as cf
     import torch
     from oracle import cpu_reference as CR
@@ -126,8 +127,8 @@ def cpu_reference_throughput(n_seg_sample, steps, warmup):
                     for i in range(n_seg_sample)])
     m = synth_m(n_seg_sample * nc)
 
-    def one(b):
-        return CR.segment_step(raw[b], GROUP, m[b * nc:(b + 1) * nc], CHUNK_SAMPLES, HOP, SR)[2]
+    def one(b, dtype=None):
+        return CR.segment_step(raw[b], GROUP, m[b * nc:(b + 1) * nc], CHUNK_SAMPLES, HOP, SR, feature_dtype=dtype)[2]
 
     with cf.ThreadPoolExecutor(max_workers=cores) as ex:
         for _ in range(warmup):
@@ -136,9 +137,25 @@ def cpu_reference_throughput(n_seg_sample, steps, warmup):
         for _ in range(steps):
             list(ex.map(one, range(n_seg_sample)))
         dt = (time.perf_counter() - t0) / steps
+        extra = None
+        if variants:
+            per_seg = N_STEMS * SECONDS
+            extra = {}
+            t0 = time.perf_counter()
+            list(ex.map(lambda b: one(b, np.float64), range(n_seg_sample)))
+            extra['float64_features_all_cores'] = n_seg_sample * per_seg / (time.perf_counter() - t0)
+            for name, dt_ in (('float32_features_1_thread', None), ('float64_features_1_thread', np.float64)):
+                one(0, dt_)
+                t0 = time.perf_counter()
+                for b in range(2):
+                    one(b, dt_)
+                extra[name] = 2 * per_seg / (time.perf_counter() - t0)
     stem_s = n_seg_sample * N_STEMS * SECONDS
-    return stem_s / dt, dt, cores, ('%d of %d segments (%d stem-audio-s) per step, one worker thread per core, '
-                                    'float32 features like the inference path') % (n_seg_sample, N_SEG, stem_s)
+    sample = ('%d of %d segments (%d stem-audio-s) per step, one worker thread per core, '
+              'float32 features like the inference path') % (n_seg_sample, N_SEG, stem_s)
+    if variants:
+        return stem_s / dt, dt, cores, sample, extra
+    return stem_s / dt, dt, cores, sample
 
 
 def run_reference(args):
@@ -409,10 +426,11 @@ def run_ours(args):
         cnn = {'model': 'MixingModelScalar2s (PyTorch/cuDNN fp32, TF32 off, random init)', 'ms_per_batch': cnn_ms,
                'value_with_cnn': stem_s_per_step / ((hot_ms + cnn_ms) * 1e-3), 'unit': UNIT}
         del net
-        # CPU baseline (the oracle port) on this box's host cores, bounded sample
-        v, dt, cores, sample = cpu_reference_throughput(4, 3, 1)
-        cpu_base = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
-                    'ms_per_step': dt * 1e3}
+        # CPU baseline (the oracle port) on this box's host cores, bounded sample; rank 0 at N = 1 only
+        if world == 1:
+            v, dt, cores, sample, extra = cpu_reference_throughput(4, 3, 1, variants=True)
+            cpu_base = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
+                        'ms_per_step': dt * 1e3, 'other_cells_stem_s_per_s': extra}
 
     if rank == 0:
         launches = sum(P.KERNEL_LAUNCHES_PER_BATCH.values()) * args.steps

@@ -30,10 +30,12 @@ def compute_features_torch(audio: np.ndarray, window_size: int = 2048, hop_lengt
 
 
 def segment_step(raw: np.ndarray, group, m: np.ndarray, chunk_samples: int, hop: int, sr: int = 44100,
-                 target: float = -20.0):
+                 target: float = -20.0, feature_dtype=None):
     """One segment [S, C, N] float32 through bus sum -> features -> gains -> mix -> loudness ->
-    normalise.  m [n_chunks, 4] are the head outputs used for the gains.  Returns (features
-    [n_chunks, 4, F, T], normalised mix [C, N] float64, loudness)."""
+    normalise.  m [n_chunks, 4] are the head outputs used for the gains.  ``feature_dtype`` = np.float64
+    featurises in double precision like the training path (data/dataset.py reads float64); the default
+    follows the audio (float32, the inference path).  Returns (features [n_chunks, 4, F, T], normalised
+    mix [C, N] float64, loudness)."""
     S, C, N = raw.shape
     buses = OM.bus_sum(raw, group, 4)                                           # [4, C, N] float32
     n_chunks = N // chunk_samples
@@ -42,7 +44,10 @@ def segment_step(raw: np.ndarray, group, m: np.ndarray, chunk_samples: int, hop:
         per = []
         for s in range(4):
             chunk = buses[s][:, k * chunk_samples:(k + 1) * chunk_samples]
-            per.append(compute_features_torch(np.mean(chunk, axis=0), 2048, hop))
+            mono = np.mean(chunk, axis=0)
+            if feature_dtype is not None:
+                mono = mono.astype(feature_dtype)
+            per.append(compute_features_torch(mono, 2048, hop))
         feats.append(torch.stack(per))
     feats = torch.stack(feats)
     gains = np.power(10.0, 0.5 * m.astype(np.float32)).astype(np.float64)       # [n_chunks, 4]
