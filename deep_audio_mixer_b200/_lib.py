@@ -22,7 +22,7 @@ SIGNATURES = {
                          _vp, _i, _i64, _i64, _vp, _vp]),
     'dam_gain_mix': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _i,
                           _vp, _vp, _vp]),
-    'dam_bus_sum': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _c.POINTER(_c.c_int32), _i, _d, _vp, _vp]),
+    'dam_bus_sum': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _c.POINTER(_c.c_int32), _i, _d, _vp, _vp, _i, _vp]),
     'dam_feature_mix_fwd': (_i, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     'dam_feature_mix_bwd': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     'dam_db_sum': (_i, [_vp, _i64, _i64, _i64, _vp, _vp]),

@@ -2,6 +2,7 @@
 // All of them stream their operands once with 128-bit accesses; grids are sized in multiples of
 // the SM count and grid-stride over the data.
 #include "dam_common.cuh"
+#include <type_traits>
 
 #include <math.h>
 
@@ -241,6 +242,11 @@ struct BusParams {
     int n_bus;
     void* out;
     int group[64];
+    // optional channel-mean output (the mono down-mix K1 would otherwise compute from the stereo bus)
+    void* mono_out;                // [n_batch, n_bus, n_elems / n_channels] or null
+    int n_channels;                // n_elems = n_channels * samples per channel
+    unsigned char order[64];       // stems sorted by bus (stable); bus g owns order[start[g] .. start[g+1])
+    unsigned char start[65];
 };
 
 template <typename T, int V>
@@ -265,6 +271,90 @@ __global__ void __launch_bounds__(kBlock) bus_sum_kernel(const BusParams p) {
     }
 }
 
+
+// Bus sum that also writes the channel mean of every bus (data/dataset.py:181-183 applied to the bus): K1 then
+// reads a mono float32 row through its plain asynchronous staging path instead of averaging two channels per
+// tile.  Arithmetic per sample is exactly K1's: channels added in order in float32, then * 1/C (C a power of
+// two) or / C, so the features are bit-identical (tested).  kI16: PCM16 stems, x * scale first.
+template <int V, bool kI16>
+__global__ void __launch_bounds__(kBlock) bus_sum_mono_kernel(const BusParams p, float scale) {
+    using TS = typename std::conditional<kI16, short, float>::type;
+    const int C = p.n_channels;
+    const long long n = p.n_elems / C;                     // samples per channel
+    const long long nvec = (n + V - 1) / V;
+    const TS* in = reinterpret_cast<const TS*>(p.stems) + (long long)blockIdx.y * p.batch_stride;
+    float* outp = reinterpret_cast<float*>(p.out) + (long long)blockIdx.y * p.n_bus * p.n_elems;
+    float* monop = reinterpret_cast<float*>(p.mono_out) + (long long)blockIdx.y * p.n_bus * n;
+    const float f_c = (float)C;
+    const float inv_c = ((C & (C - 1)) == 0) ? 1.0f / f_c : 0.0f;
+    for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
+        const long long i0 = v * V;
+        for (int g = 0; g < p.n_bus; ++g) {
+            const int s0 = p.start[g], s1 = p.start[g + 1];
+            float mono[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) mono[j] = 0.f;
+            if (C == 2) {
+                // both channels of up to three stems in flight (six independent loads), then the adds in stem order
+                float acc[2][V];
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[c][j] = 0.f;
+                for (int q0 = s0; q0 < s1; q0 += 3) {
+                    Vec<TS, V> x[2][3];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            if (q0 + u < s1) x[c][u] = load_vec<TS, V>(in + (long long)p.order[q0 + u] * p.stem_stride + c * n + i0);
+#pragma unroll
+                    for (int u = 0; u < 3; ++u)
+                        if (q0 + u < s1) {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                                for (int j = 0; j < V; ++j)
+                                    acc[c][j] = kI16 ? __fadd_rn(acc[c][j], __fmul_rn((float)x[c][u].v[j], scale))
+                                                     : acc[c][j] + (float)x[c][u].v[j];
+                        }
+                }
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    Vec<float, V> o;
+#pragma unroll
+                    for (int j = 0; j < V; ++j) o.v[j] = acc[c][j];
+                    store_vec<float, V>(outp + (long long)g * p.n_elems + c * n + i0, o);
+                }
+#pragma unroll
+                for (int j = 0; j < V; ++j) mono[j] = acc[0][j] + acc[1][j];
+            } else {
+                for (int c = 0; c < C; ++c) {
+                    float acc[V];
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+                    for (int q = s0; q < s1; ++q) {
+                        const Vec<TS, V> x = load_vec<TS, V>(in + (long long)p.order[q] * p.stem_stride + c * n + i0);
+#pragma unroll
+                        for (int j = 0; j < V; ++j)
+                            acc[j] = kI16 ? __fadd_rn(acc[j], __fmul_rn((float)x.v[j], scale)) : acc[j] + (float)x.v[j];
+                    }
+                    Vec<float, V> o;
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        o.v[j] = acc[j];
+                        mono[j] = c == 0 ? acc[j] : mono[j] + acc[j];
+                    }
+                    store_vec<float, V>(outp + (long long)g * p.n_elems + c * n + i0, o);
+                }
+            }
+            Vec<float, V> m;
+#pragma unroll
+            for (int j = 0; j < V; ++j) m.v[j] = C == 1 ? mono[j] : (inv_c != 0.f ? mono[j] * inv_c : mono[j] / f_c);
+            store_vec<float, V>(monop + (long long)g * n + i0, m);
+        }
+    }
+}
 
 // PCM16 ingest form of the bus sum: int16 stems are converted with x * scale (1/32768 reproduces what
 // librosa.load yields, exactly) and the buses are accumulated and written in float32, so 16-bit audio
@@ -501,7 +591,8 @@ extern "C" int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_batch,
 
 extern "C" int dam_bus_sum(const void* stems, int dtype, int64_t n_batch, int64_t batch_stride,
                            int64_t n_stems, int64_t n_elems, int64_t stem_stride,
-                           const int32_t* group_host, int n_bus, double input_scale, void* out, void* stream) {
+                           const int32_t* group_host, int n_bus, double input_scale, void* out, void* mono_out,
+                           int n_channels, void* stream) {
     dam_clear_error();
     DAM_CHECK_ARG(stems && group_host && out, "null pointer argument");
     DAM_CHECK_ARG(dtype == DAM_F32 || dtype == DAM_F64 || dtype == DAM_I16, "dtype must be I16, F32 or F64");
@@ -513,12 +604,43 @@ extern "C" int dam_bus_sum(const void* stems, int dtype, int64_t n_batch, int64_
     p.stems = stems; p.n_stems = n_stems; p.n_elems = n_elems; p.stem_stride = stem_stride;
     p.batch_stride = batch_stride;
     p.n_bus = n_bus; p.out = out;
+    p.mono_out = mono_out; p.n_channels = n_channels;
     for (int i = 0; i < 64; ++i) p.group[i] = -1;
     for (int64_t s = 0; s < n_stems; ++s) {
         DAM_CHECK_ARG(group_host[s] >= -1 && group_host[s] < n_bus, "group[%lld]=%d out of range", (long long)s, group_host[s]);
         p.group[s] = group_host[s];
     }
+    {
+        int pos = 0;
+        for (int g = 0; g < n_bus; ++g) {
+            p.start[g] = (unsigned char)pos;
+            for (int64_t s2 = 0; s2 < n_stems; ++s2)
+                if (group_host[s2] == g) p.order[pos++] = (unsigned char)s2;
+        }
+        p.start[n_bus] = (unsigned char)pos;
+    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (mono_out != nullptr) {
+        DAM_CHECK_ARG(dtype == DAM_F32 || dtype == DAM_I16, "the mono output is implemented for F32 and I16 stems");
+        DAM_CHECK_ARG(n_channels >= 1 && n_channels <= 64 && n_elems % n_channels == 0,
+                      "n_channels=%d must divide n_elems=%lld", n_channels, (long long)n_elems);
+        const long long n = n_elems / n_channels;
+        const size_t es = dtype == DAM_F32 ? 4 : 2;
+        const bool vec_ok = (n % 4 == 0) && (stem_stride % 4 == 0) && (batch_stride % 4 == 0) &&
+                            (reinterpret_cast<uintptr_t>(stems) % (4 * es) == 0) &&
+                            (reinterpret_cast<uintptr_t>(out) % 16 == 0) && (reinterpret_cast<uintptr_t>(mono_out) % 16 == 0);
+        const float scale = (float)input_scale;
+        const dim3 grid(grid_for(vec_ok ? n / 4 : n, n_batch >= 8 ? 1 : 8), (unsigned)n_batch);
+        if (dtype == DAM_F32) {
+            if (vec_ok) bus_sum_mono_kernel<4, false><<<grid, kBlock, 0, st>>>(p, 1.0f);
+            else bus_sum_mono_kernel<1, false><<<grid, kBlock, 0, st>>>(p, 1.0f);
+        } else {
+            if (vec_ok) bus_sum_mono_kernel<4, true><<<grid, kBlock, 0, st>>>(p, scale);
+            else bus_sum_mono_kernel<1, true><<<grid, kBlock, 0, st>>>(p, scale);
+        }
+        DAM_CHECK_CUDA(cudaGetLastError());
+        return DAM_OK;
+    }
     if (dtype == DAM_I16) {
         const bool v8 = (n_elems % 8 == 0) && (stem_stride % 8 == 0) && (batch_stride % 8 == 0) &&
                         (reinterpret_cast<uintptr_t>(stems) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);

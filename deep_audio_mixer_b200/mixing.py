@@ -66,11 +66,12 @@ def stem_sum(stems: torch.Tensor, out_dtype=None) -> torch.Tensor:
 
 
 def bus_sum(stems: torch.Tensor, group, n_bus: int = 4, batch_dims: int = 0,
-            input_scale: float = 1.0 / 32768.0) -> torch.Tensor:
+            input_scale: float = 1.0 / 32768.0, want_mono: bool = False):
     """S raw stems -> n_bus buses, summed in stem order in the audio dtype (kernel N2;
     data/medleydb_data_surgery.ipynb:305-332).  stems [S, ...] (or [B, S, ...] with batch_dims=1);
     group[s] in [0, n_bus) or -1 (dropped).  int16 stems (PCM16) are converted with x * input_scale and
-    summed in float32."""
+    summed in float32.  ``want_mono`` (stems [.., S, C, N] float32 / int16) also returns the channel mean
+    of every bus, [.., n_bus, N] float32 -- the mono rows K1 featurises -- as (buses, mono)."""
     _check_cuda(stems, 'stems')
     if batch_dims:
         B, S = stems.shape[0], stems.shape[1]
@@ -85,12 +86,18 @@ def bus_sum(stems: torch.Tensor, group, n_bus: int = 4, batch_dims: int = 0,
     out_dtype = torch.float32 if stems.dtype == torch.int16 else stems.dtype
     out = torch.empty(((B,) if batch_dims else ()) + (n_bus,) + tail, dtype=out_dtype, device=stems.device)
     grp = (ctypes.c_int32 * S)(*[int(v) for v in group])
+    mono, C = None, 1
+    if want_mono:
+        if len(tail) != 2 or stems.dtype not in (torch.float32, torch.int16):
+            raise ValueError('want_mono needs [.., S, C, N] float32 or int16 stems')
+        C = tail[0]
+        mono = torch.empty(((B,) if batch_dims else ()) + (n_bus, tail[1]), dtype=torch.float32, device=stems.device)
     with torch.cuda.device(stems.device):
         rc = _lib.lib().dam_bus_sum(_lib.ptr(flat), _lib.dtype_code(stems.dtype), B, flat.stride(0) if B > 1 else 0,
                                     S, flat.shape[2], flat.stride(1), grp, n_bus, float(input_scale),
-                                    _lib.ptr(out), _lib.stream_ptr())
+                                    _lib.ptr(out), _lib.ptr(mono), C, _lib.stream_ptr())
     _lib.check(rc, 'dam_bus_sum')
-    return out
+    return (out, mono) if want_mono else out
 
 
 def row_reduce(x: torch.Tensor, want_absmax=True, want_sumsq=True):

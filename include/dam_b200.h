@@ -136,10 +136,14 @@ int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_batch, int64_t ba
  *   dtype I16 is the PCM16 ingest form: samples are converted with x * input_scale (1/32768
  *   reproduces librosa.load exactly; N1 of SURVEY 8f) and the buses are float32; input_scale is
  *   ignored for F32 / F64.
+ *   mono_out, n_channels: optional [n_batch, n_bus, n_elems / n_channels] float32 (F32 / I16 stems): the
+ *   channel mean of every bus (_stereo_to_mono, data/dataset.py:181-183), n_elems being n_channels planar
+ *   channels.  dam_stft_db then reads mono rows; the arithmetic (channels added in order in float32, then
+ *   * 1/C or / C) is the one dam_stft_db applies itself, so the features are bit-identical.  NULL = skip.
  */
 int dam_bus_sum(const void* stems, int dtype, int64_t n_batch, int64_t batch_stride,
                 int64_t n_stems, int64_t n_elems, int64_t stem_stride,
-                const int32_t* group_host, int n_bus, double input_scale, void* out, void* stream);
+                const int32_t* group_host, int n_bus, double input_scale, void* out, void* mono_out, int n_channels, void* stream);
 
 /*
  * K3: the models' tail  masked[b] = sum_i m[b,i] * x[b,i]  (dB maps times raw head outputs) and

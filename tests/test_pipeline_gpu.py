@@ -204,3 +204,35 @@ def test_integration_md_binding_stub_runs(cuda_device):
     assert torch.equal(ns['stft_db'](x32, win, 2048, 512), F.stft_db(x32, hop=512, window=win))
     q = (x32 * 3000).to(torch.int16)
     assert torch.equal(ns['stft_db'](q, win), F.stft_db(q, window=win))
+
+
+def test_bus_sum_mono_output_feeds_k1_with_the_same_bits(cuda_device):
+    """The bus-sum kernel's optional channel-mean output: equal to the float32 mean of the stereo bus, and the
+    features K1 computes from it (asynchronous mono path) equal those it computes from the stereo bus."""
+    from deep_audio_mixer_b200 import features as F, mixing, pipeline as P
+    group = (0, 1, 1, 2, 2, 3, 3, 3)
+    g = torch.Generator(device='cuda').manual_seed(21)
+    for dt, n in ((torch.float32, 88200 * 2 + 1000), (torch.float32, 88200 + 3), (torch.int16, 88200 * 2)):
+        if dt == torch.int16:
+            raw = torch.randint(-8000, 8000, (3, 8, 2, n), device='cuda', generator=g, dtype=torch.int32).to(dt)
+        else:
+            raw = torch.randn((3, 8, 2, n), device='cuda', generator=g) * 0.2
+        buses = mixing.bus_sum(raw, group, 4, batch_dims=1)
+        b2, mono = mixing.bus_sum(raw, group, 4, batch_dims=1, want_mono=True)
+        assert torch.equal(b2, buses)
+        assert torch.equal(mono, (buses[:, :, 0] + buses[:, :, 1]) * 0.5)
+        pipe = P.SegmentBatchPipeline(8, group, 88200, 512)
+        assert torch.equal(pipe.features(mono), pipe.features(buses))
+    pipe = P.SegmentBatchPipeline(8, group, 88200, 512)
+    raw = torch.randn((2, 8, 2, 88200 * 3), device='cuda', generator=g) * 0.2
+    m = torch.rand((6, 4), device='cuda', generator=g) - 0.7
+    a = pipe.run(raw, m)
+    pipe.mono_features = False
+    b = pipe.run(raw, m)
+    for k in ('mix', 'lufs', 'peak', 'features'):
+        assert torch.equal(a[k], b[k]), k
+    # three channels: the divide form of the mean
+    raw3 = torch.randn((2, 4, 3, 5000), device='cuda', generator=g)
+    b3, m3 = mixing.bus_sum(raw3, [0, 0, 1, 1], 2, batch_dims=1, want_mono=True)
+    b3h = b3.cpu().numpy()                                       # numpy divides; torch multiplies by 1/3
+    assert np.array_equal(m3.cpu().numpy(), ((b3h[:, :, 0] + b3h[:, :, 1]) + b3h[:, :, 2]) / np.float32(3.0))
