@@ -432,6 +432,9 @@ def run_ours(args):
             v, dt, cores, sample, extra = cpu_reference_throughput(4, 3, 1, variants=True)
             cpu_base = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
                         'ms_per_step': dt * 1e3, 'other_cells_stem_s_per_s': extra}
+        else:
+            cpu_base = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+                        'sample': 'not timed at N > 1 (the CPU leg runs on rank 0 of the N = 1 run only)'}
 
     if rank == 0:
         launches = sum(P.KERNEL_LAUNCHES_PER_BATCH.values()) * args.steps
