@@ -292,7 +292,8 @@ from deep_audio_mixer_b200 import features as F
 g = torch.Generator(device='cuda').manual_seed(5)
 h = hashlib.sha1()
 for rows, ch, n, hop in ((7, 1, 88200, 512), (5, 2, 88200, 512), (4, 1, 176400, 1024), (6, 1, 89600, 512),
-                         (3, 2, 89600, 512), (9, 1, 220500, 1024), (2, 1, 30001, 512), (3, 1, 44100, 256)):
+                         (3, 2, 89600, 512), (9, 1, 220500, 1024), (2, 1, 30001, 512), (3, 1, 44100, 256),
+                         (1, 1, 1326080, 1024), (5, 1, 3584, 512), (300, 1, 7680, 512)):
     x = torch.randn((rows, ch, n) if ch > 1 else (rows, n), device='cuda', generator=g) * 0.2
     kw = {'channel_axis': -2} if ch > 1 else {}
     stats = torch.zeros(3, dtype=torch.float64, device='cuda')
