@@ -17,6 +17,10 @@ _vp, _i, _i64, _d = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_double
 SIGNATURES = {
     'dam_version': (_c.c_char_p, []),
     'dam_last_error': (_c.c_char_p, []),
+    'dam_init': (_i, []),
+    'dam_launch_count': (_i64, []),
+    'dam_last_stft_kernel': (_c.c_char_p, []),
+    'dam_kweight_init': (_i, [_c.POINTER(_d)]),
     'dam_stft_num_frames': (_i64, [_i64, _i]),
     'dam_stft_db': (_i, [_vp, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _d, _vp, _vp, _i, _i, _d, _d, _i,
                          _vp, _i, _i64, _i64, _vp, _vp]),

@@ -1,6 +1,7 @@
 // Library-level entry points: version, thread-local error text, device info cache.
 #include "dam_common.cuh"
 
+#include <atomic>
 #include <mutex>
 #include <string>
 
@@ -16,6 +17,13 @@ void dam_set_error(const char* fmt, ...) {
 }
 
 void dam_clear_error() { g_last_error.clear(); }
+
+static std::atomic<long long> g_launches{0};
+void dam_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" int64_t dam_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern const char* dam_k1_last_kernel_name;          // stft_db.cu / stft_tma.cu
+extern "C" const char* dam_last_stft_kernel(void) { return dam_k1_last_kernel_name; }
 
 int dam_sm_count() {
     static std::mutex mu;

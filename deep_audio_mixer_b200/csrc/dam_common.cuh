@@ -30,6 +30,10 @@ void dam_clear_error();
         }                                                                           \
     } while (0)
 
+// Every kernel launch of the library is counted (dam_launch_count) so that callers report launches from what
+// was dispatched, not from a table.
+void dam_note_launch();
+
 // Number of SMs of the current device (cached per device).
 int dam_sm_count();
 

@@ -96,8 +96,14 @@ int get_tables(const Coeffs& c, KwTables** out) {
         for (int i = 0; i < 4; ++i) t->ML[i * 4 + j] = s[i];
     }
     (void)M;
-    DAM_CHECK_CUDA(cudaMalloc(&t->G, G.size() * sizeof(double)));
-    DAM_CHECK_CUDA(cudaMemcpy(t->G, G.data(), G.size() * sizeof(double), cudaMemcpyHostToDevice));
+    cudaError_t e = cudaMalloc(&t->G, G.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(t->G, G.data(), G.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(t->G);
+        delete t;
+        dam_set_error("building the K-weighting response table failed: %s", cudaGetErrorString(e));
+        return DAM_ERR_CUDA;
+    }
     cache[dev].push_back(t);
     *out = t;
     return DAM_OK;
@@ -453,6 +459,21 @@ extern "C" size_t dam_kweight_workspace_bytes(int64_t n_rows, int64_t n_samples)
     return (size_t)n_rows * (size_t)n_chunks * 4 * sizeof(double);
 }
 
+// Builds the per-device response table of one filter-coefficient set (the only allocation + synchronous copy of
+// the loudness kernels).  dam_kweight_* does the same on first use of a coefficient set; call this first when
+// that first use would sit inside a CUDA-graph stream capture.
+extern "C" int dam_kweight_init(const double* coeffs_host) {
+    dam_clear_error();
+    DAM_CHECK_ARG(coeffs_host != nullptr, "null pointer argument");
+    Coeffs c;
+    for (int s = 0; s < 2; ++s) {
+        c.b0[s] = coeffs_host[s * 5 + 0]; c.b1[s] = coeffs_host[s * 5 + 1]; c.b2[s] = coeffs_host[s * 5 + 2];
+        c.a1[s] = coeffs_host[s * 5 + 3]; c.a2[s] = coeffs_host[s * 5 + 4];
+    }
+    KwTables* t = nullptr;
+    return get_tables(c, &t);
+}
+
 extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, int64_t n_samples,
                                     int64_t row_stride, int64_t samp_stride,
                                     const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,
@@ -516,13 +537,13 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
     long long grid_ll = (long long)dam_sm_count() * (occ > 0 ? occ : 1);
     if (grid_ll > n_items) grid_ll = n_items;
     const unsigned grid = (unsigned)grid_ll;
-    if (dtype == DAM_F32) kw_chunk_state_kernel<float><<<grid, kBlock, kw_smem_bytes<float>(), st>>>(p);
-    else kw_chunk_state_kernel<double><<<grid, kBlock, kw_smem_bytes<double>(), st>>>(p);
+    if (dtype == DAM_F32) { kw_chunk_state_kernel<float><<<grid, kBlock, kw_smem_bytes<float>(), st>>>(p); dam_note_launch(); }
+    else { kw_chunk_state_kernel<double><<<grid, kBlock, kw_smem_bytes<double>(), st>>>(p); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
-    kw_scan_kernel<<<(unsigned)n_rows, kScanBlock, 0, st>>>(p);
+    { kw_scan_kernel<<<(unsigned)n_rows, kScanBlock, 0, st>>>(p); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
-    if (dtype == DAM_F32) kw_apply_kernel<float><<<grid, kBlock, kw_smem_bytes<float>(), st>>>(p);
-    else kw_apply_kernel<double><<<grid, kBlock, kw_smem_bytes<double>(), st>>>(p);
+    if (dtype == DAM_F32) { kw_apply_kernel<float><<<grid, kBlock, kw_smem_bytes<float>(), st>>>(p); dam_note_launch(); }
+    else { kw_apply_kernel<double><<<grid, kBlock, kw_smem_bytes<double>(), st>>>(p); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }
@@ -540,7 +561,7 @@ extern "C" int dam_gated_loudness(const double* seg_sumsq, int64_t n_signals, in
     p.first = reinterpret_cast<const long long*>(block_first);
     p.last = reinterpret_cast<const long long*>(block_last);
     p.inv_len = inv_block_len; p.out = lufs_out;
-    gated_loudness_kernel<<<(unsigned)n_signals, kGateBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    { gated_loudness_kernel<<<(unsigned)n_signals, kGateBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }
@@ -646,7 +667,7 @@ extern "C" int dam_kweight_blocks(const void* x, int dtype, int64_t n_rows, int6
     const long long* d_first = d_geo + g.bounds.size();
     const long long* d_last = d_first + g.n_blocks;
     dim3 grid((unsigned)((g.n_blocks + 127) / 128), (unsigned)n_rows);
-    block_sum_kernel<<<grid, 128, 0, st>>>(d_seg, g.n_seg, d_first, d_last, g.n_blocks, 1.0 / (block_seconds * rate), z_out);
+    { block_sum_kernel<<<grid, 128, 0, st>>>(d_seg, g.n_seg, d_first, d_last, g.n_blocks, 1.0 / (block_seconds * rate), z_out); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }

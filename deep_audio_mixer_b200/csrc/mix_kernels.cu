@@ -224,10 +224,10 @@ int launch_gain_mix(const GainMixParams& p, bool vec_ok, cudaStream_t st) {
         if (per_plane < 1) per_plane = 1;
         if (per_plane > max_blocks) per_plane = max_blocks;
         dim3 grid((unsigned)per_plane, (unsigned)p.n_channels, (unsigned)p.n_batch);
-        gain_mix_kernel<TS, TC, TO, V><<<grid, kBlock, 0, st>>>(p);
+        { gain_mix_kernel<TS, TC, TO, V><<<grid, kBlock, 0, st>>>(p); dam_note_launch(); }
     } else {
         dim3 grid(grid_for(p.n_samples, 8), (unsigned)p.n_channels, (unsigned)p.n_batch);
-        gain_mix_kernel<TS, TC, TO, 1><<<grid, kBlock, 0, st>>>(p);
+        { gain_mix_kernel<TS, TC, TO, 1><<<grid, kBlock, 0, st>>>(p); dam_note_launch(); }
     }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
@@ -632,11 +632,11 @@ extern "C" int dam_bus_sum(const void* stems, int dtype, int64_t n_batch, int64_
         const float scale = (float)input_scale;
         const dim3 grid(grid_for(vec_ok ? n / 4 : n, n_batch >= 8 ? 1 : 8), (unsigned)n_batch);
         if (dtype == DAM_F32) {
-            if (vec_ok) bus_sum_mono_kernel<4, false><<<grid, kBlock, 0, st>>>(p, 1.0f);
-            else bus_sum_mono_kernel<1, false><<<grid, kBlock, 0, st>>>(p, 1.0f);
+            if (vec_ok) { bus_sum_mono_kernel<4, false><<<grid, kBlock, 0, st>>>(p, 1.0f); dam_note_launch(); }
+            else { bus_sum_mono_kernel<1, false><<<grid, kBlock, 0, st>>>(p, 1.0f); dam_note_launch(); }
         } else {
-            if (vec_ok) bus_sum_mono_kernel<4, true><<<grid, kBlock, 0, st>>>(p, scale);
-            else bus_sum_mono_kernel<1, true><<<grid, kBlock, 0, st>>>(p, scale);
+            if (vec_ok) { bus_sum_mono_kernel<4, true><<<grid, kBlock, 0, st>>>(p, scale); dam_note_launch(); }
+            else { bus_sum_mono_kernel<1, true><<<grid, kBlock, 0, st>>>(p, scale); dam_note_launch(); }
         }
         DAM_CHECK_CUDA(cudaGetLastError());
         return DAM_OK;
@@ -645,8 +645,8 @@ extern "C" int dam_bus_sum(const void* stems, int dtype, int64_t n_batch, int64_
         const bool v8 = (n_elems % 8 == 0) && (stem_stride % 8 == 0) && (batch_stride % 8 == 0) &&
                         (reinterpret_cast<uintptr_t>(stems) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
         const float scale = (float)input_scale;
-        if (v8) bus_sum_i16_kernel<8><<<dim3(grid_for((n_elems + 7) / 8, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p, scale);
-        else bus_sum_i16_kernel<1><<<dim3(grid_for(n_elems, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p, scale);
+        if (v8) { bus_sum_i16_kernel<8><<<dim3(grid_for((n_elems + 7) / 8, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p, scale); dam_note_launch(); }
+        else { bus_sum_i16_kernel<1><<<dim3(grid_for(n_elems, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p, scale); dam_note_launch(); }
         DAM_CHECK_CUDA(cudaGetLastError());
         return DAM_OK;
     }
@@ -655,11 +655,11 @@ extern "C" int dam_bus_sum(const void* stems, int dtype, int64_t n_batch, int64_
                         (reinterpret_cast<uintptr_t>(stems) % (4 * es) == 0) &&
                         (reinterpret_cast<uintptr_t>(out) % (4 * es) == 0);
     if (dtype == DAM_F32) {
-        if (vec_ok) bus_sum_kernel<float, 4><<<dim3(grid_for((n_elems + 3) / 4, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p);
-        else bus_sum_kernel<float, 1><<<dim3(grid_for(n_elems, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p);
+        if (vec_ok) { bus_sum_kernel<float, 4><<<dim3(grid_for((n_elems + 3) / 4, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p); dam_note_launch(); }
+        else { bus_sum_kernel<float, 1><<<dim3(grid_for(n_elems, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p); dam_note_launch(); }
     } else {
-        if (vec_ok) bus_sum_kernel<double, 4><<<dim3(grid_for((n_elems + 3) / 4, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p);
-        else bus_sum_kernel<double, 1><<<dim3(grid_for(n_elems, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p);
+        if (vec_ok) { bus_sum_kernel<double, 4><<<dim3(grid_for((n_elems + 3) / 4, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p); dam_note_launch(); }
+        else { bus_sum_kernel<double, 1><<<dim3(grid_for(n_elems, n_batch >= 8 ? 1 : 8), (unsigned)n_batch), kBlock, 0, st>>>(p); dam_note_launch(); }
     }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
@@ -682,10 +682,10 @@ extern "C" int dam_feature_mix_fwd(const float* x, const float* m, int64_t B, in
     const bool vec_ok = (P % 4 == 0) && aligned16(x) && aligned16(out);
     if (vec_ok) {
         dim3 grid(grid_for((P + 3) / 4, 2), (unsigned)B);
-        feature_mix_fwd_kernel<4><<<grid, kBlock, 0, st>>>(x, m, S, P, out);
+        { feature_mix_fwd_kernel<4><<<grid, kBlock, 0, st>>>(x, m, S, P, out); dam_note_launch(); }
     } else {
         dim3 grid(grid_for(P, 2), (unsigned)B);
-        feature_mix_fwd_kernel<1><<<grid, kBlock, 0, st>>>(x, m, S, P, out);
+        { feature_mix_fwd_kernel<1><<<grid, kBlock, 0, st>>>(x, m, S, P, out); dam_note_launch(); }
     }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
@@ -703,10 +703,10 @@ extern "C" int dam_feature_mix_bwd(const float* x, const float* m, const float* 
     const bool vec_ok = (P % 4 == 0) && aligned16(x) && aligned16(grad_out) && (!grad_x || aligned16(grad_x));
     if (vec_ok) {
         dim3 grid(grid_for((P + 3) / 4, 2) > 64 ? 64 : grid_for((P + 3) / 4, 2), (unsigned)B);
-        feature_mix_bwd_kernel<4><<<grid, kBlock, 0, st>>>(x, m, grad_out, S, P, grad_m, grad_x);
+        { feature_mix_bwd_kernel<4><<<grid, kBlock, 0, st>>>(x, m, grad_out, S, P, grad_m, grad_x); dam_note_launch(); }
     } else {
         dim3 grid(grid_for(P, 2) > 64 ? 64 : grid_for(P, 2), (unsigned)B);
-        feature_mix_bwd_kernel<1><<<grid, kBlock, 0, st>>>(x, m, grad_out, S, P, grad_m, grad_x);
+        { feature_mix_bwd_kernel<1><<<grid, kBlock, 0, st>>>(x, m, grad_out, S, P, grad_m, grad_x); dam_note_launch(); }
     }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
@@ -721,10 +721,10 @@ extern "C" int dam_db_sum(const float* x, int64_t B, int64_t S, int64_t P, float
     const bool vec_ok = (P % 4 == 0) && aligned16(x) && aligned16(out);
     if (vec_ok) {
         dim3 grid(grid_for((P + 3) / 4, 2), (unsigned)B);
-        db_sum_kernel<4><<<grid, kBlock, 0, st>>>(x, S, P, out);
+        { db_sum_kernel<4><<<grid, kBlock, 0, st>>>(x, S, P, out); dam_note_launch(); }
     } else {
         dim3 grid(grid_for(P, 2), (unsigned)B);
-        db_sum_kernel<1><<<grid, kBlock, 0, st>>>(x, S, P, out);
+        { db_sum_kernel<1><<<grid, kBlock, 0, st>>>(x, S, P, out); dam_note_launch(); }
     }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
@@ -746,6 +746,7 @@ extern "C" int dam_scale_rows(const void* x, int dtype, int64_t n_rows, int64_t 
     do {                                                                                                          \
         if (vec_ok) scale_rows_kernel<TI, TO, 4><<<grid, kBlock, 0, st>>>((const TI*)x, n, row_stride, factor, divide, (TO*)out); \
         else scale_rows_kernel<TI, TO, 1><<<grid, kBlock, 0, st>>>((const TI*)x, n, row_stride, factor, divide, (TO*)out);        \
+        dam_note_launch();                                                                                                        \
     } while (0)
     if (dtype == DAM_F32 && out_dtype == DAM_F32) DAM_SCALE(float, float);
     else if (dtype == DAM_F32) DAM_SCALE(float, double);
@@ -767,11 +768,11 @@ extern "C" int dam_row_reduce(const void* x, int dtype, int64_t n_rows, int64_t 
     const bool vec_ok = (row_stride % 4 == 0) && (reinterpret_cast<uintptr_t>(x) % 32 == 0);
     dim3 grid(grid_for(vec_ok ? (n + 3) / 4 : n, 4), (unsigned)n_rows);
     if (dtype == DAM_F32) {
-        if (vec_ok) row_reduce_kernel<float, 4><<<grid, kBlock, 0, st>>>((const float*)x, n, row_stride, absmax, sumsq);
-        else row_reduce_kernel<float, 1><<<grid, kBlock, 0, st>>>((const float*)x, n, row_stride, absmax, sumsq);
+        if (vec_ok) { row_reduce_kernel<float, 4><<<grid, kBlock, 0, st>>>((const float*)x, n, row_stride, absmax, sumsq); dam_note_launch(); }
+        else { row_reduce_kernel<float, 1><<<grid, kBlock, 0, st>>>((const float*)x, n, row_stride, absmax, sumsq); dam_note_launch(); }
     } else {
-        if (vec_ok) row_reduce_kernel<double, 4><<<grid, kBlock, 0, st>>>((const double*)x, n, row_stride, absmax, sumsq);
-        else row_reduce_kernel<double, 1><<<grid, kBlock, 0, st>>>((const double*)x, n, row_stride, absmax, sumsq);
+        if (vec_ok) { row_reduce_kernel<double, 4><<<grid, kBlock, 0, st>>>((const double*)x, n, row_stride, absmax, sumsq); dam_note_launch(); }
+        else { row_reduce_kernel<double, 1><<<grid, kBlock, 0, st>>>((const double*)x, n, row_stride, absmax, sumsq); dam_note_launch(); }
     }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
@@ -808,6 +809,7 @@ extern "C" int dam_scale(const void* x, int dtype, int64_t n, double gain, void*
     do {                                                                                               \
         if (vec_ok) scale_scalar_kernel<TI, TO, 4><<<grid, kBlock, 0, st>>>((const TI*)x, n, gain, (TO*)out); \
         else scale_scalar_kernel<TI, TO, 1><<<grid, kBlock, 0, st>>>((const TI*)x, n, gain, (TO*)out);        \
+        dam_note_launch();                                                                                    \
     } while (0)
     if (dtype == DAM_F32 && out_dtype == DAM_F32) DAM_SCALE1(float, float);
     else if (dtype == DAM_F32) DAM_SCALE1(float, double);

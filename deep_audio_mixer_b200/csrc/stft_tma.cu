@@ -1,0 +1,377 @@
+// K1, TMA-staged kernel (float32 arithmetic, float32 or PCM16 source, mono / planar stereo / interleaved stereo).
+//
+// Same transform as stft_db_kernel (stft_db.cu: two-stage 64 x 32 decomposition of the 2048-point frame,
+// packed-complex codelets, dB epilogue in registers), with everything around the transform stripped down:
+//
+// * Every tile of 8 frames -- interior or at a row end -- arrives through the TMA unit: one thread hands the RAW
+//   bytes of the next tile (float32 or int16, one contiguous run per channel plane, or the interleaved frames)
+//   to cp.async.bulk while both transform stages of the current tile run.  The in-range part of a row-end tile
+//   is copied and the reflected samples (center=True, pad_mode='reflect' of torch.stft, reference
+//   data/dataset.py:145-149) are filled in by a short shared->shared pass.
+// * PCM16 and stereo sources are converted in place, once per tile, by a two-phase shared->registers->shared
+//   pass that reproduces the numpy prologue of the reference bit for bit (x / 32768 in float32 is exact; the
+//   channel mean of two channels is (L + R) * 0.5): N1 of SURVEY section 8(f) -- the bytes of a WAV file go
+//   straight from HBM to shared memory, 2 bytes per sample.
+// * The tile walk needs no division: (row, tile-in-row) advance by a per-launch constant step.
+// * The window table sits TRANSPOSED in shared memory (wt[b][a] = w[32 a + b], 68 floats per lane), so a stage-1
+//   thread reads its 64 window values with 16 conflict-free 128-bit loads instead of 64 scalar ones.
+// * The bin pitch of the output plane is a template parameter for the common shapes (88, 176, 216 frames), so
+//   the 1025 stores of a frame use immediate offsets.
+//
+// Results are bit-identical to the phase kernel (tests/test_stft_gpu.py).
+#include "stft_common.cuh"
+
+namespace {
+
+constexpr int kFT = 8;                      // frames per tile = warps per CTA
+constexpr int kThreads = 32 * kFT;
+constexpr int kXch = XchStride<float, 8>::v;
+constexpr int kWtStride = 68;               // floats per lane of the transposed window table
+constexpr int kRawSlack = 64;               // bytes behind a raw run for the 16-byte rounding of a skewed copy
+// Samples staged in front of a tile's first frame.  When n_samples is a multiple of hop the last frame of a row is
+// centred on x[n] and its reflected half reaches back to x[c - 1025], one sample before the frame itself: if that
+// frame opens its tile the sample would not be staged.  Eight samples keep every copy 16-byte aligned.
+constexpr int kPre = 8;
+
+__host__ __device__ inline int span_max_of(int hop) { return (kFT - 1) * hop + kNfft + kPre; }
+// bytes of one raw region: holds span_max float32 samples, or both int16 planes of a stereo tile
+__host__ __device__ inline int region_bytes_of(int hop) { return span_max_of(hop) * 4 + 2 * kRawSlack; }
+
+inline size_t tma_smem_bytes(int hop, int mode, bool tab_smem) {
+    const size_t tables = tab_smem ? (size_t)32 * kWtStride * sizeof(float) + (size_t)kKp * kRow * sizeof(float2) + kNyqTab * sizeof(float) : 0;
+    const size_t xch = (size_t)kFT * kXch * sizeof(float2);
+    const int regions = (mode == TMA_F32_PLANAR2 || mode == TMA_F32_INTER2) ? 2 : 1;
+    return tables + xch + (size_t)regions * region_bytes_of(hop) + 32;
+}
+
+// offset-binary trick: int16 v -> float32 v exactly, two samples per 32-bit word
+//   bits(0x4B000000 | u16) = 2^23 + u16;  with u16 = v ^ 0x8000 (offset binary) the value is 2^23 + 32768 + v
+__device__ __forceinline__ void cvt2_i16(unsigned word, float& lo, float& hi) {
+    const unsigned w = word ^ 0x80008000u;
+    lo = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)) - 8421376.0f;
+    hi = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)) - 8421376.0f;
+}
+
+// threadIdx.x through a volatile asm: values derived from it cannot be hoisted out of the tile loop (ptxas otherwise
+// keeps the per-thread item indices / addresses of the conversion pass live across both transform stages and
+// spills them around the codelets)
+__device__ __forceinline__ int tid_now() {
+    int t;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    return t;
+}
+
+struct ConvArgs {
+    float scale;
+    bool unit;
+    __device__ __forceinline__ float in(float v) const { return unit ? v : __fmul_rn(v, scale); }
+    __device__ __forceinline__ float mean2(float l, float r) const { return (in(l) + in(r)) * 0.5f; }
+};
+
+// In-place conversion of one raw tile to float32 mono samples s[0, span): all loads, a barrier, all stores.
+// One instantiation per source mode, so that each is a straight run of loads, one barrier and a straight run of
+// stores (a single body switching on the mode per item made ptxas spill around BOTH transform codelets).
+template <int kMode, int kMaxIt>
+__device__ __forceinline__ void convert_tile_mode(const unsigned char* raw, const unsigned char* raw2, float* s,
+                                                  int span, const ConvArgs& cv, int tid) {
+    const int n_items = span >> 2;                       // 4 output samples per item
+    constexpr bool kTwo = kMode == TMA_F32_PLANAR2 || kMode == TMA_F32_INTER2;
+    uint4 a[kMaxIt], b[kTwo ? kMaxIt : 1];
+    // loads are unconditional (items past the end re-read item 0): registers assigned under a predicate are
+    // live from the top of the tile loop as far as ptxas is concerned
+#pragma unroll
+    for (int k = 0; k < kMaxIt; ++k) {
+        const int it0 = tid + k * kThreads;
+        const int it = it0 < n_items ? it0 : 0;
+        if (kMode == TMA_I16_MONO) {
+            const uint2 t = *reinterpret_cast<const uint2*>(raw + 8 * it);
+            a[k] = make_uint4(t.x, t.y, 0, 0);
+        } else if (kMode == TMA_I16_PLANAR2) {
+            const uint2 t = *reinterpret_cast<const uint2*>(raw + 8 * it);
+            const uint2 u = *reinterpret_cast<const uint2*>(raw2 + 8 * it);
+            a[k] = make_uint4(t.x, t.y, u.x, u.y);
+        } else if (kMode == TMA_I16_INTER2) {
+            a[k] = *reinterpret_cast<const uint4*>(raw + 16 * it);
+        } else if (kMode == TMA_F32_PLANAR2) {
+            a[k] = *reinterpret_cast<const uint4*>(raw + 16 * it);
+            b[kTwo ? k : 0] = *reinterpret_cast<const uint4*>(raw2 + 16 * it);
+        } else {
+            a[k] = *reinterpret_cast<const uint4*>(raw + 32 * it);
+            b[kTwo ? k : 0] = *reinterpret_cast<const uint4*>(raw + 32 * it + 16);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kMaxIt; ++k) {
+        const int it = tid + k * kThreads;
+        if (it < n_items) {
+            float4 o;
+            if (kMode == TMA_I16_MONO) {
+                float v0, v1, v2, v3;
+                cvt2_i16(a[k].x, v0, v1); cvt2_i16(a[k].y, v2, v3);
+                o = make_float4(cv.in(v0), cv.in(v1), cv.in(v2), cv.in(v3));
+            } else if (kMode == TMA_I16_PLANAR2) {
+                float l0, l1, l2, l3, r0, r1, r2, r3;
+                cvt2_i16(a[k].x, l0, l1); cvt2_i16(a[k].y, l2, l3); cvt2_i16(a[k].z, r0, r1); cvt2_i16(a[k].w, r2, r3);
+                o = make_float4(cv.mean2(l0, r0), cv.mean2(l1, r1), cv.mean2(l2, r2), cv.mean2(l3, r3));
+            } else if (kMode == TMA_I16_INTER2) {
+                float l0, r0, l1, r1, l2, r2, l3, r3;
+                cvt2_i16(a[k].x, l0, r0); cvt2_i16(a[k].y, l1, r1); cvt2_i16(a[k].z, l2, r2); cvt2_i16(a[k].w, l3, r3);
+                o = make_float4(cv.mean2(l0, r0), cv.mean2(l1, r1), cv.mean2(l2, r2), cv.mean2(l3, r3));
+            } else if (kMode == TMA_F32_PLANAR2) {
+                const uint4 c = b[kTwo ? k : 0];
+                o = make_float4(cv.mean2(__uint_as_float(a[k].x), __uint_as_float(c.x)), cv.mean2(__uint_as_float(a[k].y), __uint_as_float(c.y)),
+                                cv.mean2(__uint_as_float(a[k].z), __uint_as_float(c.z)), cv.mean2(__uint_as_float(a[k].w), __uint_as_float(c.w)));
+            } else {
+                const uint4 c = b[kTwo ? k : 0];
+                o = make_float4(cv.mean2(__uint_as_float(a[k].x), __uint_as_float(a[k].y)), cv.mean2(__uint_as_float(a[k].z), __uint_as_float(a[k].w)),
+                                cv.mean2(__uint_as_float(c.x), __uint_as_float(c.y)), cv.mean2(__uint_as_float(c.z), __uint_as_float(c.w)));
+            }
+            *reinterpret_cast<float4*>(s + 4 * it) = o;
+        }
+    }
+}
+
+template <int kMaxIt>
+__device__ __forceinline__ void convert_tile(int mode, const unsigned char* raw, const unsigned char* raw2, float* s,
+                                             int span, const ConvArgs& cv, int tid) {
+    switch (mode) {
+        case TMA_I16_MONO:    convert_tile_mode<TMA_I16_MONO, kMaxIt>(raw, raw2, s, span, cv, tid); break;
+        case TMA_I16_PLANAR2: convert_tile_mode<TMA_I16_PLANAR2, kMaxIt>(raw, raw2, s, span, cv, tid); break;
+        case TMA_I16_INTER2:  convert_tile_mode<TMA_I16_INTER2, kMaxIt>(raw, raw2, s, span, cv, tid); break;
+        case TMA_F32_PLANAR2: convert_tile_mode<TMA_F32_PLANAR2, kMaxIt>(raw, raw2, s, span, cv, tid); break;
+        default:              convert_tile_mode<TMA_F32_INTER2, kMaxIt>(raw, raw2, s, span, cv, tid); break;
+    }
+}
+
+// geometry of one tile
+struct Tile {
+    int nf, span, lo, hi;        // frames, samples staged, in-range part [lo, hi) of the staged span
+    long long g0;                // first staged sample (may be negative)
+};
+__device__ __forceinline__ Tile tile_of(unsigned tin, int hop, int T, long long n) {
+    Tile t;
+    const int f0 = (int)tin * kFT;
+    t.nf = (T - f0) < kFT ? (T - f0) : kFT;
+    t.g0 = (long long)f0 * hop - kNfft / 2 - kPre;
+    t.span = (t.nf - 1) * hop + kNfft + kPre;
+    t.lo = t.g0 < 0 ? (int)(-t.g0) : 0;
+    const long long rem = n - t.g0;
+    t.hi = rem < (long long)t.span ? (int)rem : t.span;
+    return t;
+}
+
+template <bool kStats, bool kTabSmem, int kPitch, int kMaxIt>
+__global__ void __launch_bounds__(kThreads, 2)
+stft_db_tma_kernel(const StftParams p) {
+    using OUT = float;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_wt = reinterpret_cast<float*>(smem_raw);                                     // [32][68]   (kTabSmem)
+    float2* s_tw = reinterpret_cast<float2*>(s_wt + (kTabSmem ? 32 * kWtStride : 0));     // [33][34]   (kTabSmem)
+    float* s_nq = reinterpret_cast<float*>(s_tw + (kTabSmem ? kKp * kRow : 0));           // [8][32]    (kTabSmem)
+    float2* s_xch = reinterpret_cast<float2*>(s_nq + (kTabSmem ? kNyqTab : 0));           // [kFT][kXch]
+    unsigned char* s_region = reinterpret_cast<unsigned char*>(s_xch + kFT * kXch);       // raw tile / float32 samples
+    const int hop = p.hop;
+    const int mode = p.tma_mode;
+    const int region_bytes = region_bytes_of(hop);
+    const int regions = (mode == TMA_F32_PLANAR2 || mode == TMA_F32_INTER2) ? 2 : 1;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_region + (size_t)regions * region_bytes);
+    volatile int* s_skew = reinterpret_cast<volatile int*>(bar + 1);                      // [2], by tile parity
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (kTabSmem) {
+        for (int i = tid; i < kNfft; i += kThreads) s_wt[(i & 31) * kWtStride + (i >> 5)] = __ldg(p.window + i);
+        const float2* tw = reinterpret_cast<const float2*>(p.twiddle);
+        for (int i = tid; i < kKp * kRow; i += kThreads) s_tw[i] = tw[i];
+        nyq_table_init<float>(s_nq, tid);
+    }
+    const float* nq = kTabSmem ? s_nq : reinterpret_cast<const float*>(p.twiddle) + 2 * kKp * kRow;
+    if (tid == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const int T = (int)p.T;
+    const long long n = p.n_samples;
+    const unsigned tpr = (unsigned)p.tiles_per_row, n_rows = (unsigned)p.n_rows;
+    const float2* twp = kTabSmem ? s_tw : reinterpret_cast<const float2*>(p.twiddle);
+    const int eb = mode >= TMA_I16_MONO ? 2 : 4;                                           // bytes per source element
+    const int frame_bytes = (mode == TMA_F32_INTER2 || mode == TMA_I16_INTER2) ? 2 * eb : eb;
+    // second plane of a planar stereo tile: behind the first int16 plane inside the region, or the second region
+    const int plane2_off = mode == TMA_I16_PLANAR2 ? span_max_of(hop) * 2 + kRawSlack : region_bytes;
+    ConvArgs cv;
+    cv.scale = (float)p.input_scale;
+    cv.unit = p.input_scale == 1.0;
+    StatAcc st;
+
+    // Thread 0 hands the in-range bytes of tile (r, tin) to the TMA unit.  A source run that is not 16-byte
+    // aligned is copied from the aligned address below it; the skew (bytes) is left in s_skew[parity].
+    auto issue = [&](unsigned r, unsigned tin, unsigned parity) {
+        const Tile t = tile_of(tin, hop, T, n);
+        const long long elem = row_offset(p, (long long)r) + (t.g0 + t.lo) * (frame_bytes / eb);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.audio) + elem * eb;
+        const unsigned skew = (unsigned)(reinterpret_cast<unsigned long long>(src) & 15ull);
+        const unsigned bytes = ((unsigned)(t.hi - t.lo) * (unsigned)frame_bytes + skew + 15u) & ~15u;
+        unsigned char* dst = s_region + (size_t)t.lo * frame_bytes;
+        s_skew[parity] = (int)skew;
+        const bool planar2 = mode == TMA_F32_PLANAR2 || mode == TMA_I16_PLANAR2;
+        mbar_expect_tx(bar, planar2 ? 2u * bytes : bytes);
+        bulk_g2s(dst, src - skew, bytes, bar);
+        if (planar2) bulk_g2s(dst + plane2_off, src - skew + p.chan_stride * eb, bytes, bar);
+    };
+
+    // tile walk: (row, tin) advance by (step_rows, step_tiles) = gridDim.x in mixed radix
+    unsigned row = blockIdx.x / tpr, tin = blockIdx.x - row * tpr;
+    unsigned parity = 0;
+    if (tid == 0 && row < n_rows) issue(row, tin, 0);
+
+    while (row < n_rows) {
+        unsigned nrow = row + p.step_rows, ntin = tin + p.step_tiles;
+        if (ntin >= tpr) { ntin -= tpr; ++nrow; }
+        const Tile t = tile_of(tin, hop, T, n);
+        const int nf = t.nf;
+        OUT* out_row = reinterpret_cast<OUT*>(p.out) + (long long)row * p.out_row_stride + (int)tin * kFT;
+
+        mbar_wait(bar, parity);                                   // the raw bytes of this tile have landed
+        const int skew = s_skew[parity];
+        float* s_x = reinterpret_cast<float*>(s_region);          // float32 mono samples of the tile, s_x[i] = x[g0 + i]
+        if (mode == TMA_F32_MONO) {
+            s_x = reinterpret_cast<float*>(s_region + skew);
+        } else {
+            convert_tile<kMaxIt>(mode, s_region + skew, s_region + skew + plane2_off, s_x, t.span, cv, tid_now());
+            fence_proxy_async();                                  // generic writes before the next TMA write to the region
+            __syncthreads();
+        }
+        if (t.lo > 0 || t.hi < t.span) {
+            // row end: reflected samples from the in-range part (x[-k] = x[k], x[n-1+k] = x[n-1-k])
+            const int tv = tid_now();
+            for (int i = tv; i < t.lo; i += kThreads) s_x[i] = s_x[2 * t.lo - i];
+            for (int i = t.hi + tv; i < t.span; i += kThreads) s_x[i] = s_x[2 * t.hi - 2 - i];
+            fence_proxy_async();
+            __syncthreads();
+        }
+
+        // ---- stage 1 loads: warp = frame, lane = b; xp[m] = (x[64m + b] w[64m + b], x[64m + 32 + b] w[64m + 32 + b])
+        pk2 xp[32];
+        {
+            const float* f = s_x + kPre + (warp < nf ? warp : nf - 1) * hop + lane;
+            if (kTabSmem) {
+                const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(s_wt + lane * kWtStride);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const ulonglong2 w = w2[j];
+                    xp[2 * j] = pk_mul(pk_make(f[128 * j], f[128 * j + 32]), w.x);
+                    xp[2 * j + 1] = pk_mul(pk_make(f[128 * j + 64], f[128 * j + 96]), w.y);
+                }
+            } else {
+                const float* w = p.window + lane;
+#pragma unroll
+                for (int m = 0; m < 32; ++m)
+                    xp[m] = pk_mul(pk_make(f[64 * m], f[64 * m + 32]), pk_make(__ldg(w + 64 * m), __ldg(w + 64 * m + 32)));
+            }
+        }
+        __syncthreads();         // every frame is in registers (and stage 2 of the previous tile is done)
+
+        if (tid == 0 && nrow < n_rows) issue(nrow, ntin, parity ^ 1u);
+
+        if (warp < nf)
+            stage1_frame_pc<OUT, kStats>(xp, s_xch + warp * kXch + lane, out_row + warp, p.bin_stride, nq, p, lane, st);
+        __syncthreads();
+
+        // ---- stage 2: thread = (k' = tid / FT in 0..31, frame = tid % FT)
+        {
+            const int kp = tid / kFT, fr = tid % kFT;
+            if (fr < nf)
+                stage2_task_pc<OUT, kStats, !kTabSmem, kPitch>(s_xch + fr * kXch + kp * kRow, twp + kp * kRow, out_row + fr,
+                                                               p.bin_stride, kp, p, st);
+        }
+        row = nrow; tin = ntin; parity ^= 1u;
+    }
+    if (kStats) st.flush(p.stats, lane);
+}
+
+template <bool kStats, bool kTabSmem, int kPitch, int kMaxIt>
+int launch_one(const StftParams& p, size_t smem, unsigned grid, cudaStream_t stream) {
+    auto kern = stft_db_tma_kernel<kStats, kTabSmem, kPitch, kMaxIt>;
+    static std::mutex mu;
+    static bool configured[64] = {};
+    int dev = 0;
+    DAM_CHECK_CUDA(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!configured[dev]) {
+            DAM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            DAM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            configured[dev] = true;
+        }
+    }
+    { kern<<<grid, kThreads, smem, stream>>>(p); dam_note_launch(); }
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
+
+template <bool kTabSmem, int kMaxIt>
+int launch_pitch(const StftParams& p, size_t smem, unsigned grid, cudaStream_t stream) {
+    if (p.stats != nullptr) return launch_one<true, kTabSmem, 0, kMaxIt>(p, smem, grid, stream);
+    switch ((int)p.bin_stride) {
+        case 88:  return launch_one<false, kTabSmem, 88, kMaxIt>(p, smem, grid, stream);
+        case 176: return launch_one<false, kTabSmem, 176, kMaxIt>(p, smem, grid, stream);
+        case 216: return launch_one<false, kTabSmem, 216, kMaxIt>(p, smem, grid, stream);
+        default:  return launch_one<false, kTabSmem, 0, kMaxIt>(p, smem, grid, stream);
+    }
+}
+
+}  // namespace
+
+const char* dam_k1_last_kernel_name = "";
+
+int dam_k1_launch_tma(StftParams p, cudaStream_t stream, int force_tab) {
+    // ---- does the shape qualify?  (anything else runs the phase kernel, same results)
+    const int hop = p.hop;
+    if (hop % 8 != 0 || hop < 64 || hop > 1024) return 1;
+    if (p.row_gain != nullptr) return 1;
+    if (p.n_samples < 2 * kNfft || p.T >= (1 << 24)) return 1;
+    const bool f32 = p.audio_dtype == DAM_F32, i16 = p.audio_dtype == DAM_I16;
+    if (!f32 && !i16) return 1;
+    const int eb = f32 ? 4 : 2;
+    int mode;
+    if (p.channels == 1 && p.samp_stride == 1) mode = f32 ? TMA_F32_MONO : TMA_I16_MONO;
+    else if (p.channels == 2 && p.samp_stride == 1) mode = f32 ? TMA_F32_PLANAR2 : TMA_I16_PLANAR2;
+    else if (p.channels == 2 && p.samp_stride == 2 && p.chan_stride == 1) mode = f32 ? TMA_F32_INTER2 : TMA_I16_INTER2;
+    else return 1;
+    if (mode == TMA_F32_MONO && p.input_scale != 1.0) return 1;      // no conversion pass to apply the scale in
+    // alignment of every row start: the conversion pass reads 8-byte (PCM16 mono / planar) or 16-byte vectors from
+    // (16-byte aligned address + skew), float32 mono rows are read element-wise and only need their natural 4 bytes
+    const long long align = mode == TMA_F32_MONO ? 4 : ((mode == TMA_I16_MONO || mode == TMA_I16_PLANAR2) ? 8 : 16);
+    const unsigned long long base = reinterpret_cast<unsigned long long>(p.audio);
+    if (base % align != 0 || (p.row_stride * eb) % align != 0) return 1;
+    if (p.n_inner > 0 && (p.outer_stride * eb) % align != 0) return 1;
+    if ((mode == TMA_F32_PLANAR2 || mode == TMA_I16_PLANAR2) && (p.chan_stride * eb) % 16 != 0) return 1;
+    // the in-range part of a row-end tile must end on a conversion vector (4 frames)
+    if (mode != TMA_F32_MONO && p.n_samples % 4 != 0) return 1;
+
+    p.tma_mode = mode;
+    p.tiles_per_row = (p.T + kFT - 1) / kFT;
+    p.n_tiles = p.tiles_per_row * p.n_rows;
+    DAM_CHECK_ARG(p.n_tiles < 0x7fffffffLL && p.n_rows < 0x7fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
+                  (long long)p.n_tiles);
+    p.l2_prefetch = 0;
+    for (int tab = 1; tab >= 0; --tab) {
+        if (force_tab >= 0 && tab != force_tab) continue;
+        const size_t smem = tma_smem_bytes(hop, mode, tab != 0);
+        if (2 * (smem + 1024) > 228 * 1024) continue;                // two CTAs per SM or not at all
+        long long grid = (long long)dam_sm_count() * 2;
+        if (grid > p.n_tiles) grid = p.n_tiles;
+        p.step_rows = (unsigned)(grid / p.tiles_per_row);
+        p.step_tiles = (unsigned)(grid % p.tiles_per_row);
+        static const bool trace = getenv("DAM_K1_TRACE") != nullptr;
+        if (trace) fprintf(stderr, "[dam] stft_db_tma_kernel mode=%d tables=%s smem=%zu hop=%d pitch=%lld T=%lld\n", mode,
+                           tab ? "smem" : "global", smem, hop, (long long)p.bin_stride, (long long)p.T);
+        dam_k1_last_kernel_name = tab ? "stft_db_tma_kernel<tables in shared memory>" : "stft_db_tma_kernel<tables in global memory>";
+        // conversion items per thread: span_max / 4 / 256 rounded up = 10 at hop 1024, the largest hop accepted
+        static_assert(((kFT - 1) * 1024 + kNfft + kPre + 3) / 4 <= 10 * kThreads, "kMaxIt");
+        return tab ? launch_pitch<true, 10>(p, smem, (unsigned)grid, stream) : launch_pitch<false, 10>(p, smem, (unsigned)grid, stream);
+    }
+    return 1;
+}

@@ -11,8 +11,11 @@
  *   - Unless a name ends in _host, every data pointer is a DEVICE pointer owned by the caller
  *     (e.g. torch.Tensor.data_ptr()); the call is asynchronous and ordered on `stream`
  *     (a cudaStream_t passed as void*; NULL = the legacy default stream).
- *   - No allocation, no ownership transfer, no exceptions across the boundary.  The only global
- *     state is a per-device constant table (FFT twiddles) created on first use, under a mutex.
+ *   - No ownership transfer, no exceptions across the boundary.  The only global state are per-device
+ *     constant tables (FFT twiddles; the K-weighting response table of each filter-coefficient set),
+ *     created under a mutex with one cudaMalloc + synchronous cudaMemcpy on FIRST USE.  Nothing else
+ *     allocates.  Call dam_init() / dam_kweight_init() beforehand if the first use would otherwise sit
+ *     inside a CUDA-graph stream capture (an allocation there invalidates the capture).
  *   - Return value: DAM_OK (0) or a negative dam_status; dam_last_error() returns a
  *     thread-local human-readable message for the last failing call on this thread.
  *   - Strides are in ELEMENTS of the tensor's dtype, sizes in elements, never bytes.
@@ -44,6 +47,12 @@ typedef enum dam_dtype {
 const char* dam_version(void);
 /* Message for the last error raised on the calling thread ("" if none). */
 const char* dam_last_error(void);
+/* Create the constant tables of K1 on the CURRENT device now (see Conventions). */
+int dam_init(void);
+/* Number of kernels this library has launched in this process (all devices, all threads). */
+int64_t dam_launch_count(void);
+/* Name of the K1 kernel variant the last dam_stft_db call dispatched ("" before the first call). */
+const char* dam_last_stft_kernel(void);
 
 /*
  * K1: fused framing + reflect padding + window + real FFT + |.| + dB, batched over rows.
@@ -207,6 +216,8 @@ int dam_row_reduce(const void* x, int dtype, int64_t n_rows, int64_t n, int64_t 
  *                16-byte aligned.
  */
 size_t dam_kweight_workspace_bytes(int64_t n_rows, int64_t n_samples);
+/* Build the response table of one coefficient set (HOST double[10], as below) on the current device now. */
+int dam_kweight_init(const double* coeffs_host);
 int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, int64_t n_samples,
                          int64_t row_stride, int64_t samp_stride,
                          const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,

@@ -1,6 +1,8 @@
 """Oracle: ITU-R BS.1770-4 integrated loudness as pyloudnorm computes it (TEST INFRASTRUCTURE).
 
-PARITY UNPINNED.  The arithmetic lives in the third-party package ``pyloudnorm`` (imported at
+PARITY: no reference vector exists ("unpinned" by the reference), corroborated against the
+installed ``torchaudio.functional.loudness`` to 1e-9 LU (tests/test_oracle_golden.py::
+test_loudness_matches_torchaudio).  The arithmetic lives in the third-party package ``pyloudnorm`` (imported at
 /root/reference/data/dataset.py:5, evaluation.py:7, models/baselines/mean_loudness_model.py:1,
 data/listening_test_data_preparation.py:4).  It is not vendored in the reference, not installed
 in this image, and the reference pins no version (no requirements file; the 2020 commit dates

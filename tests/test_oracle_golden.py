@@ -181,3 +181,35 @@ def test_bus_sum_and_normalise():
     assert np.allclose(y, st[0] * 10 ** (3 / 20))
     p = OM.peak_normalize(st[0])
     assert np.allclose(np.abs(p).max(axis=1), 1.0)
+
+
+def _loudness_cases(sr=44100):
+    cases = {}
+    for kind in ('white', 'music', 'tonal', 'pink'):
+        cases[kind] = synthetic.make_song(7, 1, sr * 6, kind=kind, dtype=np.float64)[0].T      # [N, 2]
+    g = cases['music'].copy()
+    g[sr * 2:sr * 4] *= 1e-5                     # a near-silent stretch: blocks under the -70 LUFS absolute gate
+    cases['abs_gated'] = g
+    q = cases['white'].copy() * 0.003
+    q[:sr] *= 300                                # 50 dB level step: the quiet part falls under the relative gate
+    cases['rel_gated'] = q
+    cases['mono'] = cases['pink'][:, :1]
+    return cases
+
+
+def test_loudness_matches_torchaudio():
+    """Independent pin for oracle/loudness.py: torchaudio.functional.loudness (installed here; its docstring
+    states it follows pyloudnorm's implementation of ITU-R BS.1770-4) on seven signal classes, two of
+    which exercise the absolute and the relative gate.  Agreement is at rounding level (~1e-14 LU)."""
+    torch = pytest.importorskip('torch')
+    torchaudio = pytest.importorskip('torchaudio')
+    sr = 44100
+    for name, x in _loudness_cases(sr).items():
+        ours = OL.integrated_loudness(x, sr)
+        theirs = float(torchaudio.functional.loudness(torch.from_numpy(np.ascontiguousarray(x.T)), sr))
+        assert abs(ours - theirs) <= 1e-9, (name, ours, theirs)
+    # the gated cases really gate: the ungated mean of the block energies reads differently
+    for name in ('abs_gated', 'rel_gated'):
+        z = OL.block_energies(_loudness_cases(sr)[name], sr)
+        ungated = -0.691 + 10 * np.log10(np.sum(z.mean(axis=1)))
+        assert abs(ungated - OL.gated_loudness(z)) > 0.05, name
