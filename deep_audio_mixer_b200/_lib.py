@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdam_b200.so')
+# DAM_LIB_VARIANT=<name> loads libdam_b200_<name>.so (built by `build.py --variant`): kernel A/B runs only
+LIB_PATH = os.path.join(_HERE, 'libdam_b200%s.so' % ('_' + os.environ['DAM_LIB_VARIANT'] if os.environ.get('DAM_LIB_VARIANT') else ''))
 
 DAM_I16, DAM_F32, DAM_F64 = 0, 1, 2
 

@@ -83,6 +83,32 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines, source: str = 'stft_tma.cu') -> str:
+    """A/B build: libdam_b200_<name>.so = the shipped objects with `source` recompiled under extra -D flags.
+    Loaded with DAM_LIB_VARIANT=<name> (see _lib.py); never the default library."""
+    build_library()
+    nvcc = _nvcc()
+    obj = os.path.join(BUILD, source.replace('.cu', '_%s.o' % name))
+    cmd = [nvcc] + NVCC_FLAGS + ['-D' + d for d in defines] + ['-c', os.path.join(CSRC, source), '-o', obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError('nvcc failed on %s (%s)' % (source, name))
+    sys.stderr.write(''.join(l + '\n' for l in (r.stdout + r.stderr).splitlines() if 'spill' in l and ' 0 bytes spill stores' not in l))
+    objs = [os.path.join(BUILD, s.replace('.cu', '.o')) for s in SOURCES if s != source] + [obj]
+    lib = os.path.join(HERE, 'libdam_b200_%s.so' % name)
+    r = subprocess.run([nvcc, '-shared', '-o', lib] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart'],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError('link failed')
+    return lib
+
+
 if __name__ == '__main__':
-    path = build_library(force='--force' in sys.argv, verbose='--verbose' in sys.argv)
-    print(path)
+    if '--variant' in sys.argv:
+        i = sys.argv.index('--variant')
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        path = build_library(force='--force' in sys.argv, verbose='--verbose' in sys.argv)
+        print(path)

@@ -322,6 +322,33 @@ __device__ __forceinline__ void stage_tile(const StftParams& p, R* __restrict__ 
     }
 }
 
+// ---- mbarrier / bulk-copy (TMA) primitives ---------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes),
+                 "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+
 // L2 prefetch of the samples the NEXT tile of this CTA will stage (no registers, no smem).
 template <int kThreads>
 __device__ __forceinline__ void prefetch_tile(const StftParams& p, long long row, long long g0, int span,
@@ -424,7 +451,7 @@ template <typename OUT> __device__ __forceinline__ void store_out(OUT* o, OUT v)
 // the distinct bins) and go straight to global memory (out_frame = &out[row][0][t]).
 template <typename R, typename OUT, bool kStats>
 __device__ __forceinline__ void nyq_bins(R y32, OUT* out_frame, long long T, const R* nq,
-                                         const StftParams& p, int lane, StatAcc& st) {
+                                         const StftParams& p, int lane, StatAcc& st, bool active = true) {
     nq += lane;
     R vr = y32 * nq[0], vi = y32 * nq[32];
 #pragma unroll
@@ -447,7 +474,7 @@ __device__ __forceinline__ void nyq_bins(R y32, OUT* out_frame, long long T, con
         }
     }
     const typename DbOut<R>::type db = DbOut<R>::eval(vr, vi, p);
-    if ((lane & 1) == 0) {
+    if ((lane & 1) == 0 && active) {
         const int bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);
         store_out<OUT>(out_frame + (long long)bin * T, (OUT)db);
         if (kStats) st.add((float)db);
@@ -552,9 +579,14 @@ __device__ __forceinline__ void stage1_frame_pc(pk2 (&xp)[32], float2* dst, OUT*
 
 // kPitch > 0: the bin pitch of the output plane (elements) is a compile-time constant, so the 32 stores of a task
 // are two base registers plus immediate offsets (STG [R.64 + imm]) instead of one IMAD.WIDE each.
+// xch_free (optional): an mbarrier on which lane 0 of the warp arrives as soon as the warp has consumed its
+// exchange rows, so that the next tile's stage 1 may overwrite them while this task is still transforming.
+// active = false: the task runs on a duplicate of a valid frame (ragged last tile) and stores nothing.
 template <typename OUT, bool kStats, bool kGlobalTw = false, int kPitch = 0>
 __device__ __forceinline__ void stage2_task_pc(const float2* src, const float2* tw, OUT* out_frame, long long T, int kp,
-                                               const StftParams& p, StatAcc& st) {
+                                               const StftParams& p, StatAcc& st, unsigned long long* xch_free = nullptr,
+                                               bool active = true, const float* nq = nullptr, float y32 = 0.f,
+                                               OUT* nyq_frame = nullptr, bool nyq_active = false) {
     pk2 z[32];
     const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(src);     // two complex values per 128-bit load
     const float4* w4 = reinterpret_cast<const float4*>(tw);
@@ -573,10 +605,17 @@ __device__ __forceinline__ void stage2_task_pc(const float2* src, const float2* 
         }
         asm volatile("" ::: "memory");
     }
+    if (xch_free != nullptr) {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(xch_free);
+    }
     dam_cfft32_pc(z);
+    // bins 32 + 64 q of the frame this WARP transformed in stage 1 (Y_b[32] kept in a register): the shuffle chain
+    // is issued here so that its latency hides behind the epilogue below (same basic block, no divergence)
+    if (nq != nullptr) nyq_bins<float, OUT, kStats>(y32, nyq_frame, T, nq, p, (int)(threadIdx.x & 31), st, nyq_active);
     // bins k'+64q (q < 16) walk up from row k'; mirrors 2048-k'-64q (q >= 16) walk down from row 1024-k'.
     // k' = 0 owns only q <= 16 (bins 0, 64, ..., 1024).
-    const bool mirror_ok = kp != 0;
+    const bool mirror_ok = kp != 0 && active;
     if (kPitch > 0) {
         OUT* o_lo = out_frame + kp * kPitch;
         OUT* o_hi = out_frame + (kNfft / 2 - kp) * kPitch;
@@ -594,7 +633,7 @@ __device__ __forceinline__ void stage2_task_pc(const float2* src, const float2* 
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int q = q0 + u;
-                const bool valid = q <= 16 ? true : mirror_ok;
+                const bool valid = q <= 16 ? active : mirror_ok;
                 OUT* o = q < 16 ? o_lo + q * (64 * kPitch) : o_hi - (q - 16) * (64 * kPitch);
                 if (valid) store_out<OUT>(o, (OUT)db[u]);
                 if (kStats && valid) st.add(db[u]);
@@ -617,7 +656,7 @@ __device__ __forceinline__ void stage2_task_pc(const float2* src, const float2* 
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int q = q0 + u;
-                const bool valid = q <= 16 ? true : mirror_ok;
+                const bool valid = q <= 16 ? active : mirror_ok;
                 OUT* o = reinterpret_cast<OUT*>(q < 16 ? o_lo + (long long)q * (long long)sb : o_hi + (long long)(16 - q) * (long long)sb);
                 if (valid) store_out<OUT>(o, (OUT)db[u]);
                 if (kStats && valid) st.add(db[u]);
@@ -626,28 +665,5 @@ __device__ __forceinline__ void stage2_task_pc(const float2* src, const float2* 
     }
     if (kStats) st.fold();
 }
-
-// ---- mbarrier / bulk-copy (TMA) primitives ---------------------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-    unsigned ok;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes),
-                 "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 }  // namespace

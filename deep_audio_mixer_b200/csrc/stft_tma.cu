@@ -21,6 +21,14 @@
 // Results are bit-identical to the phase kernel (tests/test_stft_gpu.py).
 #include "stft_common.cuh"
 
+// A/B switches (tools/ab_variants.py builds one library per setting; the defaults are what ships)
+#ifndef DAM_TMA_SPLIT
+#define DAM_TMA_SPLIT 1        // 1: split-phase mbarrier hand-over of the staging / exchange buffers, 0: __syncthreads
+#endif
+#ifndef DAM_TMA_NYQ_LATE
+#define DAM_TMA_NYQ_LATE 1     // 1: cross-lane DFT of Y_b[32] behind the stage-2 transform, 0: at the end of stage 1
+#endif
+
 namespace {
 
 constexpr int kFT = 8;                      // frames per tile = warps per CTA
@@ -41,7 +49,7 @@ inline size_t tma_smem_bytes(int hop, int mode, bool tab_smem) {
     const size_t tables = tab_smem ? (size_t)32 * kWtStride * sizeof(float) + (size_t)kKp * kRow * sizeof(float2) + kNyqTab * sizeof(float) : 0;
     const size_t xch = (size_t)kFT * kXch * sizeof(float2);
     const int regions = (mode == TMA_F32_PLANAR2 || mode == TMA_F32_INTER2) ? 2 : 1;
-    return tables + xch + (size_t)regions * region_bytes_of(hop) + 32;
+    return tables + xch + (size_t)regions * region_bytes_of(hop) + 48;
 }
 
 // offset-binary trick: int16 v -> float32 v exactly, two samples per 32-bit word
@@ -144,6 +152,76 @@ __device__ __forceinline__ void convert_tile(int mode, const unsigned char* raw,
     }
 }
 
+
+// ---- stage 2 of the TMA kernel, in two parts so that the dB epilogue of one tile can be interleaved with the
+// stage-1 loads of the next (both are light on the FMA pipe and heavy on the LSU / MUFU / store path) ----------
+template <bool kStats, bool kGlobalTw>
+__device__ __forceinline__ void stage2_transform(pk2 (&z)[32], const float2* src, const float2* tw, unsigned long long* xch_free) {
+    const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(src);     // two complex values per 128-bit load
+    const float4* w4 = reinterpret_cast<const float4*>(tw);
+#pragma unroll
+    for (int grp = 0; grp < 4; ++grp) {
+        ulonglong2 v[4];
+        float4 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { v[u] = s2[grp * 4 + u]; w[u] = kGlobalTw ? __ldg(w4 + grp * 4 + u) : w4[grp * 4 + u]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int b2 = grp * 4 + u;
+            z[2 * b2] = pk_fma(pk_swap(v[u].x), pk_make(-w[u].y, w[u].y), pk_mul(v[u].x, pk_c(w[u].x)));
+            z[2 * b2 + 1] = pk_fma(pk_swap(v[u].y), pk_make(-w[u].w, w[u].w), pk_mul(v[u].y, pk_c(w[u].z)));
+        }
+        asm volatile("" ::: "memory");
+    }
+    if (xch_free != nullptr) {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(xch_free);  // this warp's exchange rows may be overwritten
+    }
+    dam_cfft32_pc(z);
+}
+
+// dB + store of bin slot q of a task (q < 16: bin k' + 64 q, q >= 16: mirror bin 2048 - k' - 64 q)
+template <bool kStats, int kPitch>
+struct Epilogue {
+    float* o_lo;
+    float* o_hi;
+    int sb;
+    bool lo_ok, hi_ok;
+    __device__ __forceinline__ void init(float* out_frame, long long T, int kp, bool active) {
+        const long long pitch = kPitch > 0 ? (long long)kPitch : T;
+        o_lo = out_frame + kp * pitch;
+        o_hi = out_frame + (kNfft / 2 - kp) * pitch;
+        sb = (int)(64 * pitch * (long long)sizeof(float));
+        lo_ok = active;
+        hi_ok = active && kp != 0;
+    }
+    __device__ __forceinline__ void put(int q, pk2 zq, const StftParams& p, StatAcc& st) const {
+        float re, im;
+        pk_split(zq, re, im);
+        const float db = DbOut<float>::eval(re, im, p);
+        const bool valid = q <= 16 ? lo_ok : hi_ok;
+        float* o;
+        if (kPitch > 0) o = q < 16 ? o_lo + q * (64 * kPitch) : o_hi - (q - 16) * (64 * kPitch);
+        else o = reinterpret_cast<float*>(q < 16 ? reinterpret_cast<char*>(o_lo) + (long long)q * (long long)sb
+                                                 : reinterpret_cast<char*>(o_hi) + (long long)(16 - q) * (long long)sb);
+        if (valid) *o = db;
+        if (kStats && valid) st.add(db);
+    }
+};
+
+// stage-1 loads of one frame: xp[m] = (x[64m + b] w[64m + b], x[64m + 32 + b] w[64m + 32 + b]), group j = xp[2j], xp[2j+1]
+template <bool kTabSmem>
+__device__ __forceinline__ void load_group(pk2 (&xp)[32], int j, const float* f, const float* s_wt_lane, const float* gw) {
+    if (kTabSmem) {
+        const ulonglong2 w = reinterpret_cast<const ulonglong2*>(s_wt_lane)[j];
+        xp[2 * j] = pk_mul(pk_make(f[128 * j], f[128 * j + 32]), w.x);
+        xp[2 * j + 1] = pk_mul(pk_make(f[128 * j + 64], f[128 * j + 96]), w.y);
+    } else {
+        xp[2 * j] = pk_mul(pk_make(f[128 * j], f[128 * j + 32]), pk_make(__ldg(gw + 128 * j), __ldg(gw + 128 * j + 32)));
+        xp[2 * j + 1] = pk_mul(pk_make(f[128 * j + 64], f[128 * j + 96]), pk_make(__ldg(gw + 128 * j + 64), __ldg(gw + 128 * j + 96)));
+    }
+}
+
 // geometry of one tile
 struct Tile {
     int nf, span, lo, hi;        // frames, samples staged, in-range part [lo, hi) of the staged span
@@ -175,8 +253,10 @@ stft_db_tma_kernel(const StftParams p) {
     const int mode = p.tma_mode;
     const int region_bytes = region_bytes_of(hop);
     const int regions = (mode == TMA_F32_PLANAR2 || mode == TMA_F32_INTER2) ? 2 : 1;
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_region + (size_t)regions * region_bytes);
-    volatile int* s_skew = reinterpret_cast<volatile int*>(bar + 1);                      // [2], by tile parity
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_region + (size_t)regions * region_bytes);   // tile landed
+    unsigned long long* bar_stage = bar + 1;     // 8 arrivals: every warp holds its frame in registers
+    unsigned long long* bar_xch = bar + 2;       // 8 arrivals: every warp has consumed its exchange rows
+    volatile int* s_skew = reinterpret_cast<volatile int*>(bar + 3);                      // [2], by tile parity
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -188,7 +268,11 @@ stft_db_tma_kernel(const StftParams p) {
         nyq_table_init<float>(s_nq, tid);
     }
     const float* nq = kTabSmem ? s_nq : reinterpret_cast<const float*>(p.twiddle) + 2 * kKp * kRow;
-    if (tid == 0) mbar_init(bar, 1);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar_stage, kFT);
+        mbar_init(bar_xch, kFT);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -221,21 +305,11 @@ stft_db_tma_kernel(const StftParams p) {
         if (planar2) bulk_g2s(dst + plane2_off, src - skew + p.chan_stride * eb, bytes, bar);
     };
 
-    // tile walk: (row, tin) advance by (step_rows, step_tiles) = gridDim.x in mixed radix
-    unsigned row = blockIdx.x / tpr, tin = blockIdx.x - row * tpr;
-    unsigned parity = 0;
-    if (tid == 0 && row < n_rows) issue(row, tin, 0);
-
-    while (row < n_rows) {
-        unsigned nrow = row + p.step_rows, ntin = tin + p.step_tiles;
-        if (ntin >= tpr) { ntin -= tpr; ++nrow; }
-        const Tile t = tile_of(tin, hop, T, n);
-        const int nf = t.nf;
-        OUT* out_row = reinterpret_cast<OUT*>(p.out) + (long long)row * p.out_row_stride + (int)tin * kFT;
-
-        mbar_wait(bar, parity);                                   // the raw bytes of this tile have landed
-        const int skew = s_skew[parity];
-        float* s_x = reinterpret_cast<float*>(s_region);          // float32 mono samples of the tile, s_x[i] = x[g0 + i]
+    // Prepares the staged tile (conversion to float32 mono, reflection at a row end) and returns the pointer to its
+    // samples, s_x[i] = x[g0 + i].  Called by all threads after the tile has landed; contains CTA barriers.
+    auto prepare = [&](const Tile& t, unsigned par) -> const float* {
+        const int skew = s_skew[par];
+        float* s_x = reinterpret_cast<float*>(s_region);
         if (mode == TMA_F32_MONO) {
             s_x = reinterpret_cast<float*>(s_region + skew);
         } else {
@@ -251,40 +325,90 @@ stft_db_tma_kernel(const StftParams p) {
             fence_proxy_async();
             __syncthreads();
         }
+        return s_x;
+    };
+    const float* wt_lane = s_wt + lane * kWtStride;
+    const float* gw_lane = p.window + lane;
 
-        // ---- stage 1 loads: warp = frame, lane = b; xp[m] = (x[64m + b] w[64m + b], x[64m + 32 + b] w[64m + 32 + b])
+    // tile walk: (row, tin) advance by (step_rows, step_tiles) = gridDim.x in mixed radix
+    unsigned row = blockIdx.x / tpr, tin = blockIdx.x - row * tpr;
+    unsigned parity = 0;
+    if (tid == 0 && row < n_rows) issue(row, tin, 0);
+
+    while (row < n_rows) {
+        unsigned nrow = row + p.step_rows, ntin = tin + p.step_tiles;
+        if (ntin >= tpr) { ntin -= tpr; ++nrow; }
+        const Tile t = tile_of(tin, hop, T, n);
+        const int nf = t.nf;
+        OUT* out_row = reinterpret_cast<OUT*>(p.out) + (long long)row * p.out_row_stride + (int)tin * kFT;
+
+        mbar_wait(bar, parity);                                   // the raw bytes of this tile have landed
+        const float* s_x = prepare(t, parity);
+
+        // ---- stage 1 loads: warp = frame, lane = b
         pk2 xp[32];
         {
             const float* f = s_x + kPre + (warp < nf ? warp : nf - 1) * hop + lane;
-            if (kTabSmem) {
-                const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(s_wt + lane * kWtStride);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const ulonglong2 w = w2[j];
-                    xp[2 * j] = pk_mul(pk_make(f[128 * j], f[128 * j + 32]), w.x);
-                    xp[2 * j + 1] = pk_mul(pk_make(f[128 * j + 64], f[128 * j + 96]), w.y);
-                }
-            } else {
-                const float* w = p.window + lane;
-#pragma unroll
-                for (int m = 0; m < 32; ++m)
-                    xp[m] = pk_mul(pk_make(f[64 * m], f[64 * m + 32]), pk_make(__ldg(w + 64 * m), __ldg(w + 64 * m + 32)));
-            }
+            for (int j = 0; j < 16; ++j) load_group<kTabSmem>(xp, j, f, wt_lane, gw_lane);
         }
-        __syncthreads();         // every frame is in registers (and stage 2 of the previous tile is done)
 
-        if (tid == 0 && nrow < n_rows) issue(nrow, ntin, parity ^ 1u);
-
-        if (warp < nf)
-            stage1_frame_pc<OUT, kStats>(xp, s_xch + warp * kXch + lane, out_row + warp, p.bin_stride, nq, p, lane, st);
+        // ---- split-phase hand-over of the two shared buffers (no CTA-wide barrier here: the warps drift apart, so
+        // the shared-memory bursts of one overlap the transforms of another)
+        // (a) staged samples: a warp arrives on bar_stage once its frame is in registers; thread 0 waits for all
+        //     eight and only then lets the TMA unit overwrite the region with the next tile
+#if DAM_TMA_SPLIT
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_stage);
+        if (tid == 0 && nrow < n_rows) {
+            mbar_wait(bar_stage, parity);
+            issue(nrow, ntin, parity ^ 1u);
+        }
+#else
         __syncthreads();
+        if (tid == 0 && nrow < n_rows) issue(nrow, ntin, parity ^ 1u);
+#endif
 
-        // ---- stage 2: thread = (k' = tid / FT in 0..31, frame = tid % FT)
+        // ---- stage 1: 64-point real DFT of the lane's samples in registers; the exchange rows are written once
+        // (b) every warp has consumed the rows of the previous tile (arrivals on bar_xch in stage 2; by now every
+        //     warp is past them, so waiting before the transform costs nothing and lets the exchange stores
+        //     interleave with the last butterflies)
+        float y32 = 0.f;
+        if (warp < nf) {
+#if DAM_TMA_SPLIT
+            mbar_wait(bar_xch, parity ^ 1u);
+#endif
+            pk2 y0n, s[32];
+            dam_rfft64_pc(xp, y0n, s);
+            float y0;
+            pk_split(y0n, y0, y32);
+            float2* dst = s_xch + warp * kXch + lane;
+            dst[0] = make_float2(y0, 0.f);                       // row 0: Y[0] (real)
+#pragma unroll
+            for (int k = 1; k < 32; ++k) *reinterpret_cast<pk2*>(dst + k * kRow) = s[k];
+#if !DAM_TMA_NYQ_LATE
+            nyq_bins<float, OUT, kStats>(y32, out_row + warp, p.bin_stride, nq, p, lane, st);
+#endif
+        }
+        __syncthreads();         // stage 1 -> stage 2: all rows of the tile are in the exchange buffer
+
+        // ---- stage 2: thread = (k' = tid / FT in 0..31, frame = tid % FT); lanes past the end of a ragged tile
+        // transform a duplicate of its last frame and store nothing (no divergence around the arrive)
         {
             const int kp = tid / kFT, fr = tid % kFT;
-            if (fr < nf)
-                stage2_task_pc<OUT, kStats, !kTabSmem, kPitch>(s_xch + fr * kXch + kp * kRow, twp + kp * kRow, out_row + fr,
-                                                               p.bin_stride, kp, p, st);
+            pk2 z[32];
+            stage2_transform<kStats, !kTabSmem>(z, s_xch + (fr < nf ? fr : nf - 1) * kXch + kp * kRow, twp + kp * kRow,
+                                                DAM_TMA_SPLIT ? bar_xch : nullptr);
+            // bins 32 + 64 q of the frame this WARP transformed in stage 1 (Y_b[32] kept in a register): the shuffle
+            // chain is issued here so that its latency hides behind the epilogue
+#if DAM_TMA_NYQ_LATE
+            nyq_bins<float, OUT, kStats>(y32, out_row + warp, p.bin_stride, nq, p, lane, st, warp < nf);
+#endif
+            Epilogue<kStats, kPitch> ep;
+            ep.init(out_row + fr, p.bin_stride, kp, fr < nf);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) ep.put(q, z[q], p, st);
+            if (kStats) st.fold();
         }
         row = nrow; tin = ntin; parity ^= 1u;
     }
@@ -357,6 +481,10 @@ int dam_k1_launch_tma(StftParams p, cudaStream_t stream, int force_tab) {
     DAM_CHECK_ARG(p.n_tiles < 0x7fffffffLL && p.n_rows < 0x7fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
                   (long long)p.n_tiles);
     p.l2_prefetch = 0;
+    // Output rows that are not a multiple of 8 frames (32 bytes) make every 8-frame store straddle two sectors; the
+    // variant with its tables in global memory leaves the SM twice the L1 to merge them in and measured 10-15 %
+    // faster there (T = 173 dense: 0.87 vs 1.00 ms, hop 256 T = 345: 0.89 vs 0.98 ms), and slower everywhere else.
+    if (force_tab < 0 && p.bin_stride % 8 != 0) force_tab = 0;
     for (int tab = 1; tab >= 0; --tab) {
         if (force_tab >= 0 && tab != force_tab) continue;
         const size_t smem = tma_smem_bytes(hop, mode, tab != 0);

@@ -79,6 +79,12 @@ def main():
     table = {}
     modes = [('phase', {'DAM_K1_ASYNC': '0'}), ('r1 async', {'DAM_K1_ASYNC': '5'}), ('tma (default)', {}),
              ('tma tab-global', {'DAM_K1_ASYNC': '3'})]
+    # library variants (build.py --variant NAME ...): the default dispatch on each
+    for v in [v for v in os.environ.get('AB_VARIANTS', '').split(',') if v]:
+        modes.append(('lib:' + v, {'DAM_LIB_VARIANT': v}))
+    if os.environ.get('AB_MODES'):
+        keep = os.environ['AB_MODES'].split(',')
+        modes = [m for m in modes if m[0].split()[0] in keep or m[0].startswith('lib:')]
     for name, env in modes:
         e = dict(os.environ)
         e.update(env)
@@ -97,7 +103,7 @@ def main():
                 continue
             c = table[name][i]
             same = '' if ref is None else ('  identical' if c['sha'] == ref[i]['sha'] else '  DIFFERENT OUTPUT')
-            print('   %-16s %7.3f ms  %6.0f GB/s (%.3f of 6549.8)  %.2f M stem-s/s%s' %
+            print('   %-20s %7.3f ms  %6.0f GB/s (%.3f of 6549.8)  %.2f M stem-s/s%s' %
                   (name, c['ms'], c['GBps'], c['GBps'] / 6549.8, c['stem_s_per_s'] / 1e6, same))
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, 'gpurun_out', 'ab_k1.json')
     os.makedirs(os.path.dirname(out), exist_ok=True)
