@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Headline benchmark: stem-audio-seconds per second through STFT -> dB -> gains -> mix (+loudness).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload segments|corpus|train]
+
+--workload segments (default; what the driver runs) is BASELINE.json configs[1]; corpus = configs[2] (bulk
+featurisation of a MedleyDB-shaped corpus, songs LPT-sharded over the ranks, statistics all-reduce) and train =
+configs[3] (ResNet18 data-parallel training epoch, DDP gradient all-reduce) live in tools/bench_workloads.py.
 
 Workload (BASELINE.json configs[1]): model_scalar_2s inference batch of 64 synthetic 8-stem 10 s
 stereo 44.1 kHz segments per GPU: bus sum 8->4, dB-STFT features of every 2 s chunk (hop 512, T=173,
@@ -34,6 +38,11 @@ UNIT = 'stem-audio-s/s'
 WORKLOAD = ('config2: model_scalar_2s inference batch of 64 synthetic 8-stem 10 s stereo 44.1 kHz segments; '
             'bus-sum 8->4 (+ mono down-mix of each bus), 2 s chunks @ hop 512 (T=173), float64 mask/mix, '
             'BS.1770 loudness, -20 LUFS normalise')
+# one dict for BOTH arms (ours and --impl reference): the driver compares them key by key
+CONFIG = {'workload': WORKLOAD, 'segments_per_gpu': N_SEG, 'stems': N_STEMS, 'seconds': SECONDS, 'hop': HOP,
+          'chunk_samples': CHUNK_SAMPLES,
+          'l2': 'inputs (1.8 GB per step) are larger than the 126 MB L2; no explicit flush',
+          'parallelism': 'segments sharded per GPU, no data-path collective'}
 
 
 def synth_m(n_rows, seed=1234 + 2000):
@@ -163,12 +172,13 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    value, dt, cores, sample = cpu_reference_throughput(4, max(1, args.steps), max(1, min(args.warmup, 2)))
+    # every step is the WHOLE per-GPU batch (64 segments, ~0.7 s on 16 cores): same workload and config as our arm
+    value, dt, cores, sample = cpu_reference_throughput(N_SEG, max(1, args.steps), max(1, min(args.warmup, 2)))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'sample': sample},
+        'config': dict(CONFIG),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -234,9 +244,16 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(2):
-        res = step()
+    lib = _lib.lib()
+    res = step()
     torch.cuda.synchronize()
+    # kernels of OUR library per step, counted by the library's launch sites while one step runs eagerly (a graph
+    # replay re-launches exactly these), and the K1 variant the dispatcher picked
+    n0 = lib.dam_launch_count()
+    res = step()
+    torch.cuda.synchronize()
+    launches_per_step = int(lib.dam_launch_count() - n0)
+    k1_kernel = lib.dam_last_stft_kernel().decode()
 
     # The step is ~11 of our kernel launches plus a few tiny torch ops and takes ~2.4 ms on the device,
     # about what Python needs to enqueue it, so the whole step is captured ONCE in a CUDA graph and the
@@ -273,20 +290,21 @@ def run_ours(args):
     else:
         run_step = step
 
-    # warm-up: at least W (>= 3) steps and at least ~0.7 s of continuous load, so clocks/power settle and
-    # nvidia-smi (50 ms period) gets samples under this load before the timed region starts
+    # warm-up: exactly the W steps asked for (>= 3), reported as `warmup`.  Before them, `warmup_extra_steps` keep
+    # the GPU under this load for ~0.7 s so that clocks / power settle and nvidia-smi (50 ms period) has samples of
+    # it; they are reported separately.  (With several ranks the step contains a collective, so every rank must run
+    # the SAME number of steps: a fixed count instead of a time-based one.)
     sampler.mark_begin()
+    n_warm = max(args.warmup, 3)
+    n_extra = 0
     t_w = time.time()
-    n_warm = 0
-    # (with several ranks the step contains a collective, so every rank must run the SAME number of
-    # warm-up steps: a fixed count instead of a time-based one)
-    fixed_warm = max(args.warmup, 3) + 200 if world > 1 else None
-    while (n_warm < fixed_warm) if fixed_warm is not None else \
-            (n_warm < max(args.warmup, 3) or time.time() - t_w < 0.7):
+    while (n_extra < 200) if world > 1 else (time.time() - t_w < 0.7):
         run_step()
-        n_warm += 1
-        if n_warm % 8 == 0:
+        n_extra += 1
+        if n_extra % 8 == 0:
             torch.cuda.synchronize()
+    for _ in range(n_warm):
+        run_step()
     torch.cuda.synchronize()
 
     # ---- timed region: CUDA events on the launching stream, barrier + synchronize on both sides
@@ -330,6 +348,7 @@ def run_ours(args):
     stages['gain_mix'], mixres = time_graph(lambda: pipe.stage_mix(buses, gains))
     stages['loudness'], lufs = time_graph(lambda: pipe.stage_loudness(mixres['mix']))
     stages['scale'], _ = time_graph(lambda: pipe.stage_normalise(mixres['mix'], lufs))
+    mono_keep = mono
     del buses, mono, mixres
     stem_s_per_step = N_SEG * N_STEMS * SECONDS
     value = world * stem_s_per_step * args.steps / (elapsed_ms * 1e-3)
@@ -339,14 +358,55 @@ def run_ours(args):
     peak, peak_src = peaks()
     k1_ms_per_launch = stages['stft_db'] / 4.0
     achieved = ab['stft_db'] / 4.0 / (k1_ms_per_launch * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'stft_db_async_kernel<false,true> (K1, mono rows from the bus-sum kernel)', 'achieved': achieved, 'peak': peak,
+    roofline = {'bound': 'hbm', 'kernel': k1_kernel + ' (K1: 4 launches per step, mono rows from the bus-sum kernel)',
+                'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': ab['stft_db'] / 4.0, 'avg_launch_ms': k1_ms_per_launch,
                 'stage_ms': stages, 'stage_algorithmic_bytes': ab}
+    # DRAM traffic needs a profiler: it is taken from the committed ncu capture of this launch, but only if that
+    # capture is of the kernel that was dispatched just now (otherwise null rather than a stale number)
     traffic_path = os.path.join(ROOT, 'profiles', 'k1_traffic.json')
     if os.path.exists(traffic_path):
         with open(traffic_path) as f:
-            roofline['traffic'] = json.load(f).get('dram_bytes_per_launch')
+            tj = json.load(f)
+        if tj.get('dispatched_kernel') == k1_kernel:
+            roofline['traffic'] = tj.get('dram_bytes_per_launch')
+            roofline['traffic_source'] = 'profiles/k1_traffic.json (ncu --set full, commit %s)' % tj.get('commit', '?')
+        else:
+            roofline['traffic_source'] = 'profiles/k1_traffic.json is of %r, not of the kernel dispatched here' % tj.get('dispatched_kernel')
+
+    # ---- the same step with K1 in float64 arithmetic (meets north_star's 1e-4 dB on EVERY bin; the reference's
+    # training-path dtype).  Same batch, same graph capture, same event timing.
+    f64_leg = None
+    parity = None
+    if rank == 0:
+        import torch as _t
+        pipe.feature_compute_dtype = _t.float64
+        g64, _ = capture(lambda: pipe.run(raw, m, feats_out=feats_buf))
+        for _ in range(3):
+            g64.replay()
+        n64 = max(3, args.steps // 4)
+        a, b = _t.cuda.Event(enable_timing=True), _t.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n64):
+            g64.replay()
+        b.record()
+        _t.cuda.synchronize()
+        ms64 = a.elapsed_time(b) / n64
+        k1_64, _ = time_graph(lambda: pipe.features(mono_keep, feats_buf))
+        k1_64_name = lib.dam_last_stft_kernel().decode()
+        pipe.feature_compute_dtype = None
+        f64_leg = {'value': stem_s_per_step / (ms64 * 1e-3), 'unit': UNIT, 'ms_per_step': ms64, 'steps': n64,
+                   'k1_ms_per_step': k1_64, 'k1_kernel': k1_64_name,
+                   'k1_roofline_frac': ab['stft_db'] / (k1_64 * 1e-3) / 1e9 / peak,
+                   'note': 'per GPU; K1 computes in float64 (<= 1e-4 dB on every bin vs the reference float64 path), '
+                           'output rounded to float32'}
+        # parity of the benchmarked arithmetic against the reference's own outputs (tests/golden, unmodified
+        # reference): measured here, asserted in tests/test_stft_gpu.py
+        sys.path.insert(0, os.path.join(ROOT, 'tools'))
+        import parity_report
+        parity = parity_report.k1_vs_reference_goldens(dev)
+    del mono_keep
 
     # ---- end to end through the public API with HOST buffers (uploads/downloads inside the timed region)
     e2e = None
@@ -429,7 +489,7 @@ def run_ours(args):
         del net
         # CPU baseline (the oracle port) on this box's host cores, bounded sample; rank 0 at N = 1 only
         if world == 1:
-            v, dt, cores, sample, extra = cpu_reference_throughput(4, 3, 1, variants=True)
+            v, dt, cores, sample, extra = cpu_reference_throughput(N_SEG, 3, 1, variants=True)
             cpu_base = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample,
                         'ms_per_step': dt * 1e3, 'other_cells_stem_s_per_s': extra}
         else:
@@ -437,16 +497,14 @@ def run_ours(args):
                         'sample': 'not timed at N > 1 (the CPU leg runs on rank 0 of the N = 1 run only)'}
 
     if rank == 0:
-        launches = sum(P.KERNEL_LAUNCHES_PER_BATCH.values()) * args.steps
+        launches = launches_per_step * args.steps
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': n_warm, 'cuda_graph': use_graph, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
+            'warmup': n_warm, 'warmup_extra_steps': n_extra, 'cuda_graph': use_graph, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'segments_per_gpu': N_SEG, 'stems': N_STEMS, 'seconds': SECONDS,
-                       'hop': HOP, 'chunk_samples': CHUNK_SAMPLES,
-                       'l2': 'inputs (1.8 GB per step) are larger than the 126 MB L2; no explicit flush',
-                       'parallelism': 'segments sharded per GPU, no data-path collective'},
+            'config': dict(CONFIG),
             'roofline': roofline, 'cpu_baseline': cpu_base, 'e2e': e2e, 'gpu_launches': launches,
+            'gpu_launches_per_step': launches_per_step, 'parity': parity, 'float64_compute': f64_leg,
             'clocks': clocks, 'cnn': cnn,
             'check': {'lufs0': float(res['lufs'][0]), 'peak0': float(res['peak'][0, 0])},
         }
@@ -461,9 +519,14 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='segments', choices=['segments', 'corpus', 'train'])
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload != 'segments':
+        sys.path.insert(0, os.path.join(ROOT, 'tools'))
+        import bench_workloads
+        (bench_workloads.run_corpus if args.workload == 'corpus' else bench_workloads.run_train)(args)
     else:
         run_ours(args)
 

@@ -50,15 +50,20 @@ __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
     atomicMax(reinterpret_cast<long long*>(addr), __double_as_longlong(v));
 }
 
-template <typename T, int V> struct Vec { T v[V]; };
+template <typename T, int V> struct alignas(V * sizeof(T) >= 16 ? 16 : V * sizeof(T)) Vec { T v[V]; };
 template <typename T, int V>
 __device__ __forceinline__ Vec<T, V> load_vec(const T* p) {
     Vec<T, V> r;
-    if (V == 1) { r.v[0] = __ldg(p); return r; }
     constexpr int kBytes = V * (int)sizeof(T);
-    if (kBytes == 16) {
+    static_assert(V == 1 || kBytes == 8 || kBytes == 16 || kBytes == 32, "load_vec: unsupported vector width");
+    if (V == 1) {
+        r.v[0] = __ldg(p);
+    } else if (kBytes == 8) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+        *reinterpret_cast<uint2*>(&r) = raw;
+    } else if (kBytes == 16) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
-        r = *reinterpret_cast<const Vec<T, V>*>(&raw);
+        *reinterpret_cast<uint4*>(&r) = raw;
     } else {      // 32 bytes
         const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
         const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
@@ -69,9 +74,13 @@ __device__ __forceinline__ Vec<T, V> load_vec(const T* p) {
 }
 template <typename T, int V>
 __device__ __forceinline__ void store_vec(T* p, const Vec<T, V>& r) {
-    if (V == 1) { *p = r.v[0]; return; }
     constexpr int kBytes = V * (int)sizeof(T);
-    if (kBytes == 16) {
+    static_assert(V == 1 || kBytes == 8 || kBytes == 16 || kBytes == 32, "store_vec: unsupported vector width");
+    if (V == 1) {
+        *p = r.v[0];
+    } else if (kBytes == 8) {
+        *reinterpret_cast<uint2*>(p) = *reinterpret_cast<const uint2*>(&r);
+    } else if (kBytes == 16) {
         *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&r);
     } else {
         reinterpret_cast<uint4*>(p)[0] = reinterpret_cast<const uint4*>(&r)[0];

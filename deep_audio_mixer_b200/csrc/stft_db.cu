@@ -134,151 +134,6 @@ stft_db_kernel(const StftParams p) {
 }
 
 // ==========================================================================================
-// Asynchronously staged variant (float32 source and arithmetic, mono or planar stereo, unit scale,
-// FT = 8, packed-complex codelets).  The phase kernel above stalls every warp of the CTA on the
-// global loads of its next tile (18 % of warp stall samples, profiles/).  Here the staging buffer does
-// NOT alias the exchange buffer: as soon as stage 1 has the samples of tile i in registers, one thread
-// hands the raw samples of tile i+1 to the TMA unit (cp.async.bulk, one contiguous run per channel,
-// completion on an mbarrier), and they land in shared memory while both transform stages of tile i
-// run.  A stereo tile is averaged in place by a short shared->shared pass ((L + R) * 0.5, numpy's
-// float32 mean over two channels); tiles that touch a row end (reflection) or are not 16-byte aligned
-// take the synchronous path of the phase kernel into the same buffer.
-// kTabSmem = false keeps the window and twiddle tables in global memory (L1-resident, 17 KB) to make
-// room for the staging buffer of stereo hop-512 / mono hop-1024 tiles with two CTAs per SM.
-
-constexpr int kAsyncFT = 8;
-
-// shared-memory bytes of the async kernel: [tables] + exchange + staging (channels x span floats) + mbarrier
-inline size_t async_smem_bytes(int hop, int channels, bool tab_smem) {
-    const size_t tables = tab_smem ? kNfft * sizeof(float) + (size_t)kKp * kRow * sizeof(float2) + kNyqTab * sizeof(float) : 0;
-    const size_t xch = (size_t)kAsyncFT * XchStride<float, 8>::v * sizeof(float2);
-    const size_t stage = (size_t)channels * ((size_t)(kAsyncFT - 1) * hop + kNfft) * sizeof(float);
-    return tables + xch + stage + 16;
-}
-
-template <bool kStats, bool kTabSmem>
-__global__ void __launch_bounds__(32 * kAsyncFT, 2)
-stft_db_async_kernel(const StftParams p) {
-    using OUT = float;
-    constexpr int kFT = kAsyncFT;
-    constexpr int kXch = XchStride<float, 8>::v;
-    constexpr int kThreads = 32 * kFT;
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* s_win = reinterpret_cast<float*>(smem_raw);                                  // [2048]   (kTabSmem)
-    float2* s_tw = reinterpret_cast<float2*>(s_win + (kTabSmem ? kNfft : 0));           // [33][34] (kTabSmem)
-    float* s_nq = reinterpret_cast<float*>(s_tw + (kTabSmem ? kKp * kRow : 0));         // [8][32]
-    float2* s_xch = reinterpret_cast<float2*>(s_nq + (kTabSmem ? kNyqTab : 0));         // [kFT][kXch]
-    float* s_stage = reinterpret_cast<float*>(s_xch + kFT * kXch);                      // [C][span_max]
-    const int hop = p.hop;
-    const int span_max = (kFT - 1) * hop + kNfft;
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(s_stage + (size_t)p.channels * span_max);
-
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-
-    if (kTabSmem) {
-        for (int i = tid; i < kNfft; i += kThreads) s_win[i] = __ldg(p.window + i);
-        const float2* tw = reinterpret_cast<const float2*>(p.twiddle);
-        for (int i = tid; i < kKp * kRow; i += kThreads) s_tw[i] = tw[i];
-    }
-    if (kTabSmem) nyq_table_init<float>(s_nq, tid);
-    const float* nq = kTabSmem ? s_nq : reinterpret_cast<const float*>(p.twiddle) + 2 * kKp * kRow;
-    if (tid == 0) mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-
-    const long long T = p.T;
-    const long long n = p.n_samples;
-    const int C = p.channels;
-    const unsigned tiles_per_row = (unsigned)p.tiles_per_row, n_tiles = (unsigned)p.n_tiles;
-    const float* win = kTabSmem ? s_win : p.window;
-    const float2* twp = kTabSmem ? s_tw : reinterpret_cast<const float2*>(p.twiddle);
-    StatAcc st;
-
-    // Hand tile `t` to the TMA unit if it is an interior, 16-byte aligned tile; uniform over the CTA.
-    auto prefetch = [&](unsigned t) -> bool {
-        if (t >= n_tiles) return false;
-        const unsigned r = t / tiles_per_row;
-        const long long f0 = (long long)(t - r * tiles_per_row) * kFT;
-        const int cnt = (int)((T - f0) < kFT ? (T - f0) : kFT);
-        const long long g0 = f0 * hop - kNfft / 2;
-        const int span = (cnt - 1) * hop + kNfft;
-        if (g0 < 0 || g0 + span > n) return false;
-        const float* src = reinterpret_cast<const float*>(p.audio) + row_offset(p, r) + g0;
-        if ((reinterpret_cast<unsigned long long>(src) & 15ull) != 0 || (span & 3) != 0) return false;
-        if (C == 2 && ((p.chan_stride * 4) & 15ll) != 0) return false;
-        if (tid == 0) {
-            const unsigned bytes = (unsigned)span * 4u;
-            mbar_expect_tx(bar, bytes * (unsigned)C);
-            bulk_g2s(s_stage, src, bytes, bar);
-            if (C == 2) bulk_g2s(s_stage + span_max, src + p.chan_stride, bytes, bar);
-        }
-        return true;
-    };
-
-    unsigned phase = 0;
-    bool in_flight = prefetch(blockIdx.x);
-    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const unsigned urow = tile / tiles_per_row;
-        const long long row = urow;
-        const long long t0 = (long long)(tile - urow * tiles_per_row) * kFT;
-        const int nf = (int)((T - t0) < kFT ? (T - t0) : kFT);
-        OUT* out_row = reinterpret_cast<OUT*>(p.out) + row * p.out_row_stride + t0;
-        const int span = (nf - 1) * hop + kNfft;
-
-        if (in_flight) {
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            if (C == 2) {
-                // in-place channel mean over the left-channel run; every 16-byte vector has one owner
-                float4* l4 = reinterpret_cast<float4*>(s_stage);
-                const float4* r4 = reinterpret_cast<const float4*>(s_stage + span_max);
-                for (int v = tid; v < span / 4; v += kThreads) {
-                    float4 a = l4[v];
-                    const float4 b = r4[v];
-                    a.x = (a.x + b.x) * 0.5f; a.y = (a.y + b.y) * 0.5f; a.z = (a.z + b.z) * 0.5f; a.w = (a.w + b.w) * 0.5f;
-                    l4[v] = a;
-                }
-                __syncthreads();
-            }
-        } else {
-            stage_tile<float, float, float, kThreads>(p, s_stage, row, t0 * hop - kNfft / 2, span, tid);
-            __syncthreads();
-        }
-
-        // ---- stage 1 loads: warp = frame, lane = b
-        pk2 xp[32];
-        {
-            const float* f = s_stage + (warp < nf ? warp : nf - 1) * hop + lane;
-            const float* w = win + lane;
-#pragma unroll
-            for (int m = 0; m < 32; ++m) {
-                const float w0 = kTabSmem ? w[64 * m] : __ldg(w + 64 * m);
-                const float w1 = kTabSmem ? w[64 * m + 32] : __ldg(w + 64 * m + 32);
-                xp[m] = pk_mul(pk_make(f[64 * m], f[64 * m + 32]), pk_make(w0, w1));
-            }
-        }
-        fence_proxy_async();     // order this thread's generic accesses to s_stage before the TMA writes
-        __syncthreads();         // every frame is in registers (and stage 2 of the previous tile is done)
-
-        in_flight = prefetch(tile + gridDim.x);
-
-        if (warp < nf)
-            stage1_frame_pc<OUT, kStats>(xp, s_xch + warp * kXch + lane, out_row + warp, p.bin_stride, nq, p, lane, st);
-        __syncthreads();
-
-        // ---- stage 2: thread = (k' = tid / FT in 0..31, frame = tid % FT)
-        {
-            const int kp = tid / kFT, t = tid % kFT;
-            if (t < nf)
-                stage2_task_pc<OUT, kStats, !kTabSmem>(s_xch + t * kXch + kp * kRow, twp + kp * kRow, out_row + t, p.bin_stride, kp, p, st);
-        }
-    }
-    if (kStats) st.flush(p.stats, lane);
-}
-
-// ==========================================================================================
 // Generic window sizes (power of two, 64..8192 except 2048): a plain shared-memory radix-2 transform,
 // one CTA per (row, tile of 8 frames).  The reference only ever uses window_size = 2048
 // (data/dataset.py:132), so this path exists for API completeness (window_size is a runtime argument
@@ -538,52 +393,6 @@ int launch(StftParams p, cudaStream_t stream) {
     return DAM_OK;
 }
 
-// Async kernel launch: returns DAM_OK after launching, or 1 when the shape does not fit two CTAs per SM
-// (the caller then uses the phase kernel).
-template <bool kStats>
-int launch_async(StftParams p, cudaStream_t stream, int force_tab) {
-    constexpr int kThreads = 32 * kAsyncFT;
-    p.tiles_per_row = (p.T + kAsyncFT - 1) / kAsyncFT;
-    p.n_tiles = p.tiles_per_row * p.n_rows;
-    DAM_CHECK_ARG(p.n_tiles < 0x7fffffffLL, "too many frame tiles for one launch (%lld); split the batch",
-                  (long long)p.n_tiles);
-    p.l2_prefetch = 0;
-    static std::mutex mu;
-    static bool configured[64] = {};
-    int dev = 0;
-    DAM_CHECK_CUDA(cudaGetDevice(&dev));
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (!configured[dev]) {
-            DAM_CHECK_CUDA(cudaFuncSetAttribute(stft_db_async_kernel<kStats, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            DAM_CHECK_CUDA(cudaFuncSetAttribute(stft_db_async_kernel<kStats, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            DAM_CHECK_CUDA(cudaFuncSetAttribute(stft_db_async_kernel<kStats, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            DAM_CHECK_CUDA(cudaFuncSetAttribute(stft_db_async_kernel<kStats, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            configured[dev] = true;
-        }
-    }
-    for (int tab = 1; tab >= 0; --tab) {
-        if (force_tab >= 0 && tab != force_tab) continue;
-        const size_t smem = async_smem_bytes(p.hop, p.channels, tab != 0);
-        if (smem > 227 * 1024) continue;
-        int occ = 0;
-        if (tab) DAM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stft_db_async_kernel<kStats, true>, kThreads, smem));
-        else     DAM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stft_db_async_kernel<kStats, false>, kThreads, smem));
-        if (occ < 2) continue;
-        long long grid = (long long)dam_sm_count() * 2;
-        if (grid > p.n_tiles) grid = p.n_tiles;
-        static const bool trace = getenv("DAM_K1_TRACE") != nullptr;
-        if (trace) fprintf(stderr, "[dam] stft_db_async_kernel tables=%s smem=%zu hop=%d C=%d T=%lld\n", tab ? "smem" : "global",
-                           smem, p.hop, p.channels, (long long)p.T);
-        if (tab) { stft_db_async_kernel<kStats, true><<<(unsigned)grid, kThreads, smem, stream>>>(p); dam_note_launch(); }
-        else     { stft_db_async_kernel<kStats, false><<<(unsigned)grid, kThreads, smem, stream>>>(p); dam_note_launch(); }
-        DAM_CHECK_CUDA(cudaGetLastError());
-        dam_k1_last_kernel_name = "stft_db_async_kernel (round-1 cp.async.bulk kernel)";
-        return DAM_OK;
-    }
-    return 1;
-}
-
 }  // namespace
 
 // Creates the per-device constant tables of K1 (the only allocation + synchronous copy the library ever does for
@@ -661,41 +470,25 @@ extern "C" int dam_stft_db(const void* audio, int audio_dtype, int channels,
     const bool st = stats != nullptr;
     if (compute_dtype == DAM_F32) {
         p.twiddle = tw->f32;
-        // Frames per tile: 8 (two 8-warp CTAs per SM) by default.  16 (one 16-warp CTA per SM) writes 64-byte
-        // row segments: measured +15 % when rows are not sector aligned (T % 8 != 0) at hop >= 1024, -17 %
-        // when they are, -4 % at hop 512; it also wastes more of a short row's last tile.  DAM_FT_F32 = 8 | 16
-        // overrides the choice, DAM_K1_PC=0 selects the scalar codelets instead of the packed-complex ones.
-        static const int ft_env = [] { const char* e = getenv("DAM_FT_F32"); return e ? atoi(e) : 0; }();
-        static const bool use_pc = [] { const char* e = getenv("DAM_K1_PC"); return !(e && atoi(e) == 0); }();
-        int ft = 8;
-        if (ft_env == 8 || ft_env == 16) ft = ft_env;
-        else if (hop >= 1024 && (p.bin_stride % 8) != 0 && p.T >= 160) ft = 16;
-        // TMA-staged kernel: measured +7..10 % on mono rows whose length is a multiple of 8 frames (sector-aligned
-        // output rows) at hop >= 512, neutral on stereo, and 4..27 % SLOWER on unaligned rows (T = 173, 87), where
-        // every 32-byte output segment straddles two sectors and the phase kernel's lock-step CTAs cope better.
-        // DAM_K1_ASYNC: 0 = never, 1 (default) = where it measured faster, 2 / 3 / 4 = wherever it applies with
-        // the tables in shared memory / in global memory / wherever they fit.
+        // TMA-staged kernel (stft_tma.cu) wherever the shape qualifies: float32 / PCM16 source, mono or two
+        // channels, hop a multiple of 8 up to 1024, no row gain.  DAM_K1_ASYNC: 0 = never (phase kernel only),
+        // 1 (default) = wherever it qualifies, 2 / 3 = with the tables forced into shared / global memory.
         static const int async_env = [] { const char* e = getenv("DAM_K1_ASYNC"); return e ? atoi(e) : 1; }();
-        if (use_pc && async_env >= 1 && async_env <= 4 && (ft_env == 0 || ft_env == 8)) {
-            // TMA-staged kernel (stft_tma.cu) wherever the shape qualifies: float32 / PCM16, mono or two channels,
-            // hop a multiple of 8 up to 1024, no row gain.  DAM_K1_ASYNC: 0 = never, 2 / 3 = force the tables into
-            // shared / global memory, 5 = the round-1 cp.async.bulk kernel (A/B only).
+        static const int ft_env = [] { const char* e = getenv("DAM_FT_F32"); return e ? atoi(e) : 0; }();
+        if (async_env >= 1 && async_env <= 4 && (ft_env == 0 || ft_env == 8)) {
             const int force = async_env == 2 ? 1 : (async_env == 3 ? 0 : -1);
             const int rc2 = dam_k1_launch_tma(p, s, force);
             if (rc2 <= 0) return rc2;
         }
-        const bool async_ok = use_pc && ft == 8 && audio_dtype == DAM_F32 && (channels == 1 || channels == 2) &&
-                              input_scale == 1.0 && row_gain == nullptr && samp_stride == 1 && (hop % 4) == 0;
-        if (async_ok && async_env == 5) {
-            const int rc2 = st ? launch_async<true>(p, s, -1) : launch_async<false>(p, s, -1);
-            if (rc2 <= 0) return rc2;
-        }
-        if (use_pc) {
-            if (ft == 16) return st ? launch<float, float, true, 16, true>(p, s) : launch<float, float, false, 16, true>(p, s);
-            return st ? launch<float, float, true, 8, true>(p, s) : launch<float, float, false, 8, true>(p, s);
-        }
-        if (ft == 16) return st ? launch<float, float, true, 16>(p, s) : launch<float, float, false, 16>(p, s);
-        return st ? launch<float, float, true, 8>(p, s) : launch<float, float, false, 8>(p, s);
+        // Phase kernel (everything else: row gains, odd hops, strided samples, more than two channels).  Frames per
+        // tile: 8 (two 8-warp CTAs per SM); 16 (one 16-warp CTA per SM) writes 64-byte row segments and measured
+        // +15 % when rows are not sector aligned (T % 8 != 0) at hop >= 1024, -17 % when they are, -4 % at hop 512.
+        // DAM_FT_F32 = 8 | 16 overrides the choice.
+        int ft = 8;
+        if (ft_env == 8 || ft_env == 16) ft = ft_env;
+        else if (hop >= 1024 && (p.bin_stride % 8) != 0 && p.T >= 160) ft = 16;
+        if (ft == 16) return st ? launch<float, float, true, 16, true>(p, s) : launch<float, float, false, 16, true>(p, s);
+        return st ? launch<float, float, true, 8, true>(p, s) : launch<float, float, false, 8, true>(p, s);
     }
     p.twiddle = tw->f64;
     if (out_dtype == DAM_F32) return st ? launch<double, float, true, 8>(p, s) : launch<double, float, false, 8>(p, s);

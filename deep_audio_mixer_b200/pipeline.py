@@ -20,9 +20,6 @@ import torch
 from . import features, mixing
 from .loudness import Meter
 
-KERNEL_LAUNCHES_PER_BATCH = {'bus_sum': 1, 'stft_db': 4, 'gain_mix': 1, 'kweight': 3, 'gating': 1, 'scale': 1}
-
-
 class SegmentBatchPipeline:
     def __init__(self, n_stems=8, group=(0, 1, 1, 2, 2, 3, 3, 3), chunk_samples=88200, hop=512, n_fft=2048,
                  sr=44100, target_lufs=-20.0, device=None):
@@ -33,6 +30,8 @@ class SegmentBatchPipeline:
         self.meter = Meter(sr)
         self.timings = None          # optional dict of CUDA event pairs per stage
         self.mono_features = True    # K1 reads the bus-sum kernel's mono down-mix instead of averaging channels
+        self.feature_compute_dtype = None     # None: follows the audio like the reference (float32); torch.float64
+                                              # meets 1e-4 dB on every bin (the reference's training-path dtype)
 
     def n_chunks(self, n_samples: int) -> int:
         return n_samples // self.chunk_samples
@@ -69,13 +68,14 @@ class SegmentBatchPipeline:
                 view = src.as_strided((B, nc, self.chunk_samples), (buses.stride(0), self.chunk_samples, 1),
                                       src.storage_offset())
                 features.stft_db(view, self.n_fft, self.hop, out=out[:, s], out_row_stride=S * F * pitch,
-                                 frame_pitch=pitch)
+                                 frame_pitch=pitch, compute_dtype=self.feature_compute_dtype, out_dtype=torch.float32)
             else:
                 C = buses.shape[2]
                 view = src.as_strided((B, nc, C, self.chunk_samples),
                                       (buses.stride(0), self.chunk_samples, buses.stride(2), 1), src.storage_offset())
                 features.stft_db(view, self.n_fft, self.hop, channel_axis=-2, out=out[:, s],
-                                 out_row_stride=S * F * pitch, frame_pitch=pitch)
+                                 out_row_stride=S * F * pitch, frame_pitch=pitch,
+                                 compute_dtype=self.feature_compute_dtype, out_dtype=torch.float32)
         return out[..., :T]
 
     def _ev(self, name):

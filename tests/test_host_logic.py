@@ -170,3 +170,121 @@ def test_dataset_indexing_without_gpu(tmp_path):
     per_song = [int(d / 2) for d in ds.get_song_durations()]
     expect = [(s, c) for s, n in enumerate(per_song) for c in range(n)]
     assert seen == expect
+
+
+def _make_tiny_model():
+    """Same forward contract as the reference models (forward(x[B,4,F,T]) -> (masked, (m1..m4))) with the tail
+    written as the reference's torch expression (model_scalar_1s.py:260-275): the product's CUDA tail cannot run
+    on the CPU, and what this test covers is the trainer / DDP harness, not the kernel."""
+    import torch
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(4, 3, 3, padding=1)
+            self.heads = torch.nn.ModuleList([torch.nn.Linear(3, 1) for _ in range(4)])
+
+        def forward(self, x):
+            h = torch.relu(self.conv(x)).mean(dim=(2, 3))
+            ms = tuple(head(h) for head in self.heads)
+            masked = sum(m.unsqueeze(2) * x[:, i] for i, m in enumerate(ms))
+            return masked, ms
+
+    return Tiny()
+
+
+def _ddp_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from deep_audio_mixer_b200 import trainer as TR, sharding
+    torch.manual_seed(0)
+    model = _make_tiny_model()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(8, 4, 9, 7, generator=g)
+    gt = torch.randn(8, 9, 7, generator=g)
+    lo, hi = sharding.shard_range(8, rank, world)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    tr = TR.ModelTrainer(model, torch.nn.MSELoss(), opt, torch.device('cpu'), ddp=True, log_every=0)
+    assert isinstance(tr.model, torch.nn.parallel.DistributedDataParallel)
+    tr.optimizer.zero_grad()
+    masked, _ = tr.model(x[lo:hi])
+    tr.criterion(masked, gt[lo:hi]).backward()
+    grads = [p.grad.clone() for p in model.parameters()]
+    loss = tr.train_step(x[lo:hi], gt[lo:hi])
+    q.put((rank, [g_.numpy() for g_ in grads], [p.detach().numpy() for p in model.parameters()], float(loss)))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_ddp_gradients_equal_single_rank():
+    """Config 4 (row e2): two ranks on half batches, gradients averaged by the DDP all-reduce, equal the
+    single-process gradients on the concatenated batch; after one Adam(weight_decay=1e-5) step both ranks hold
+    the same parameters as the single-process run (model_trainer.py:25-44, training_ignite.ipynb:286-300)."""
+    import torch
+    import torch.multiprocessing as mp
+    from deep_audio_mixer_b200 import trainer as TR
+    torch.manual_seed(0)
+    model = _make_tiny_model()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(8, 4, 9, 7, generator=g)
+    gt = torch.randn(8, 9, 7, generator=g)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    tr = TR.ModelTrainer(model, torch.nn.MSELoss(), opt, torch.device('cpu'), log_every=0)
+    masked, _ = model(x)
+    torch.nn.MSELoss()(masked, gt).backward()
+    ref_grads = [p.grad.clone().numpy() for p in model.parameters()]
+    tr.train_step(x, gt)
+    ref_params = [p.detach().numpy() for p in model.parameters()]
+
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, grads, params, loss in res:
+        for a, b in zip(grads, ref_grads):
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-7), rank
+        for a, b in zip(params, ref_params):
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-7), rank
+
+
+def test_trainer_epoch_matches_reference_loop():
+    """ModelTrainer._train_epoch / _validate_epoch return what the reference's loops return (mean of the
+    per-batch losses) and step the optimiser once per batch."""
+    import torch
+    from deep_audio_mixer_b200 import trainer as TR
+    torch.manual_seed(3)
+    data = [(torch.randn(2, 4, 5, 6), torch.randn(2, 5, 6)) for _ in range(3)]
+
+    def run(use_trainer):
+        torch.manual_seed(0)
+        model = _make_tiny_model()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-2, weight_decay=1e-5)
+        crit = torch.nn.MSELoss()
+        if use_trainer:
+            tr = TR.ModelTrainer(model, crit, opt, torch.device('cpu'), log_every=0)
+            return tr._train_epoch(data), tr._validate_epoch(data)
+        running = 0.0
+        for xb, yb in data:                    # model_trainer.py:25-44
+            opt.zero_grad()
+            masked, _ = model(xb)
+            loss = crit(masked, yb)
+            loss.backward()
+            opt.step()
+            running += loss.item()
+        val = 0.0
+        with torch.no_grad():
+            for xb, yb in data:
+                val += crit(model(xb)[0], yb).item()
+        return running / len(data), val / len(data)
+
+    a, b = run(True), run(False)
+    assert abs(a[0] - b[0]) < 1e-6 and abs(a[1] - b[1]) < 1e-6

@@ -1,5 +1,5 @@
 """A/B of K1's kernels (DAM_K1_ASYNC = 0 phase kernel, 1 = default: the TMA-staged kernel of stft_tma.cu wherever
-the shape qualifies, 3 = the same with the tables in global memory, 5 = the round-1 cp.async.bulk kernel) on the
+the shape qualifies, 3 = the same with the tables in global memory) on the
 shapes that matter; every mode must give bit-identical output.  Each mode runs in its own process because the
 knob is read once.
 
@@ -77,7 +77,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == 'child':
         return child()
     table = {}
-    modes = [('phase', {'DAM_K1_ASYNC': '0'}), ('r1 async', {'DAM_K1_ASYNC': '5'}), ('tma (default)', {}),
+    modes = [('phase', {'DAM_K1_ASYNC': '0'}), ('tma (default)', {}),
              ('tma tab-global', {'DAM_K1_ASYNC': '3'})]
     # library variants (build.py --variant NAME ...): the default dispatch on each
     for v in [v for v in os.environ.get('AB_VARIANTS', '').split(',') if v]:
