@@ -187,19 +187,39 @@ def run_reference(args):
 
 
 def bind_to_gpu_numa_node(local):
-    """Pin this rank (and so the pages of its pinned host buffers, by first touch) to the CPUs NVML reports as
-    local to its GPU: with several ranks the end-to-end leg is bound by host memory / PCIe root placement."""
+    """Pin this rank (and so the pages of its pinned host buffers, by first touch) to the CPUs of the NUMA node its
+    GPU hangs off -- sysfs numa_node of the PCI device, NVML's CPU affinity as a fall-back: with several ranks the
+    end-to-end leg is bound by host memory / PCIe root placement."""
+    allowed = os.sched_getaffinity(0)
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        addr = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open('/sys/bus/pci/devices/%s/numa_node' % addr) as f:
+            node = int(f.read().strip())
+        if node >= 0:
+            cpus = set()
+            with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+                for part in f.read().strip().split(','):
+                    lo, _, hi = part.partition('-')
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+            use = cpus & allowed
+            if use and use != allowed:
+                os.sched_setaffinity(0, use)
+                return {'source': 'sysfs', 'numa_node': node, 'cpus': len(use)}
+            return {'source': 'sysfs', 'numa_node': node, 'cpus': len(use), 'bound': False}
+    except Exception:            # noqa: BLE001 -- best effort
+        pass
     try:
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(local)
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
         cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
-        allowed = os.sched_getaffinity(0)
         use = cpus & allowed
         if use and use != allowed:
             os.sched_setaffinity(0, use)
-            return sorted(use)[:1] + [len(use)]
+            return {'source': 'nvml', 'cpus': len(use)}
     except Exception:            # noqa: BLE001 -- best effort; the bench runs unpinned otherwise
         pass
     return None
@@ -420,14 +440,15 @@ def run_ours(args):
         streams = [torch.cuda.Stream(dev) for _ in range(3)]
         e2e_steps = max(3, min(args.steps, 7))
 
-        def time_host_steps(src_host):
+        def time_host_steps(src_host, dst_host=None, copy_mode='overlap'):
             """Per-step CUDA-event times of run_host (upload + kernels + download each step); the rate is
             quoted on the MEDIAN step (one host-side hiccup -- page migration, another process on the PCIe
             root -- otherwise triples a 5-step sum) and every step time is listed beside it."""
+            dst_host = out_host if dst_host is None else dst_host
             # warm-up: the caching allocator needs a few steps to grow the pools the three streams recycle
             # (every cudaMalloc on the way synchronises); fixed count so that all ranks stay in step
-            for _ in range(10):
-                pipe.run_host(src_host, m_host, out_host, lufs_host, streams=streams)
+            for _ in range(6):
+                pipe.run_host(src_host, m_host, dst_host, lufs_host, streams=streams, copy_mode=copy_mode)
                 torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
@@ -435,7 +456,7 @@ def run_ours(args):
             for _ in range(e2e_steps):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
-                pipe.run_host(src_host, m_host, out_host, lufs_host, streams=streams)
+                pipe.run_host(src_host, m_host, dst_host, lufs_host, streams=streams, copy_mode=copy_mode)
                 b.record()
                 torch.cuda.synchronize()
                 times.append(a.elapsed_time(b))
@@ -445,24 +466,49 @@ def run_ours(args):
             times = [float(v) for v in t.cpu()]
             return float(np.median(times)), times
 
+        up_bytes = int(raw_host.numel() * 4 + m_host.numel() * 4)
+        down_bytes = int(out_host.numel() * 8 + lufs_host.numel() * 8)
         med, step_ms = time_host_steps(raw_host)
         e2e = {'value': world * stem_s_per_step / (med * 1e-3), 'unit': UNIT,
-               'h2d_bytes_per_step': int(raw_host.numel() * 4 + m_host.numel() * 4),
-               'd2h_bytes_per_step': int(out_host.numel() * 8 + lufs_host.numel() * 8),
+               'h2d_bytes_per_step': up_bytes, 'd2h_bytes_per_step': down_bytes,
                'ms_per_step': med, 'step_ms': [round(v, 3) for v in step_ms], 'statistic': 'median step, max over ranks',
-               'cpu_binding': numa,
-               'pcie_ceiling': 'measured on this pool (profiles/r01_pcie_probe.json): 55.6 GB/s H2D alone, 52.5 GB/s with a '
-                               'concurrent D2H; this step moves %.2f GB up' % (raw_host.numel() * 4 / 1e9),
+               'cpu_binding': numa, 'achieved_GBps_all_ranks': world * (up_bytes + down_bytes) / med / 1e6,
                'check': float(lufs_host[0])}
-        # the same call fed with PCM16 host buffers (the format the reference's WAV files are in):
-        # int16 -> x/32768 float32 happens inside the bus-sum kernel, halving the upload
+        # the measured ceiling of this box with all ranks copying at once (tools/pcie_probe_multi.py, committed)
+        probe_path = os.path.join(ROOT, 'profiles', 'r02_pcie_probe_%d.json' % world)
+        if os.path.exists(probe_path):
+            with open(probe_path) as f:
+                pj = json.load(f)
+            best = None
+            for placement in ('default_placement', 'numa_bound'):
+                if isinstance(pj.get(placement), dict):
+                    for mode in ('bidir', 'serial'):
+                        g = pj[placement][mode]['aggregate_GBps']
+                        if best is None or g > best[0]:
+                            best = (g, placement + '/' + mode)
+            if best is not None:
+                e2e['pcie_ceiling'] = {'aggregate_GBps': best[0], 'mode': best[1], 'source': 'profiles/r02_pcie_probe_%d.json' % world,
+                                       'e2e_over_ceiling': e2e['achieved_GBps_all_ranks'] / best[0]}
+        # variants of the same call (not the headline): one copy direction at a time per GPU; PCM16 host buffers
+        # (the format the reference's WAV files are in -- int16 -> x/32768 float32 happens inside the bus-sum
+        # kernel, halving the upload); float32 mix out (halves the download; the reference's mix is float64)
+        med_s, step_s = time_host_steps(raw_host, copy_mode='serial')
+        e2e['serial_copies'] = {'value': world * stem_s_per_step / (med_s * 1e-3), 'unit': UNIT, 'ms_per_step': med_s,
+                                'step_ms': [round(v, 3) for v in step_s]}
         raw16_host = torch.empty((N_SEG, N_STEMS, N_CH, n), dtype=torch.int16).pin_memory()
         raw16_host.copy_((raw * 32768.0).round().clamp(-32768, 32767).to(torch.int16))
         med16, step16 = time_host_steps(raw16_host)
         e2e['pcm16_input'] = {'value': world * stem_s_per_step / (med16 * 1e-3), 'unit': UNIT,
                               'h2d_bytes_per_step': int(raw16_host.numel() * 2 + m_host.numel() * 4),
-                              'd2h_bytes_per_step': int(out_host.numel() * 8 + lufs_host.numel() * 8),
+                              'd2h_bytes_per_step': down_bytes,
                               'ms_per_step': med16, 'step_ms': [round(v, 3) for v in step16], 'check': float(lufs_host[0])}
+        out32_host = torch.empty((N_SEG, N_CH, n), dtype=torch.float32).pin_memory()
+        med32, step32 = time_host_steps(raw16_host, dst_host=out32_host)
+        e2e['pcm16_input_float32_mix_out'] = {'value': world * stem_s_per_step / (med32 * 1e-3), 'unit': UNIT,
+                                              'h2d_bytes_per_step': int(raw16_host.numel() * 2 + m_host.numel() * 4),
+                                              'd2h_bytes_per_step': int(out32_host.numel() * 4 + lufs_host.numel() * 8),
+                                              'ms_per_step': med32, 'step_ms': [round(v, 3) for v in step32]}
+        del out32_host
         del raw_host, out_host, raw16_host
 
     if rank == 0:

@@ -38,6 +38,7 @@ SIGNATURES = {
     'dam_kweight_segments': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _c.POINTER(_d), _vp, _i64, _vp, _vp,
                                   _c.c_size_t, _vp]),
     'dam_scale': (_i, [_vp, _i, _i64, _d, _vp, _i, _vp]),
+    'dam_pcm_unpack': (_i, [_vp, _i, _i64, _d, _vp, _i, _vp]),
     'dam_kweight_num_blocks': (_i64, [_i64, _d, _d, _d]),
     'dam_kweight_blocks_workspace_bytes': (_c.c_size_t, [_i64, _i64, _d, _d, _d]),
     'dam_kweight_blocks': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _d, _c.POINTER(_d), _d, _d, _vp, _vp, _c.c_size_t, _vp]),
@@ -85,3 +86,39 @@ def stream_ptr(stream=None):
 
 def ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+# ---- small host -> device uploads (gain tables, factors): a ring of pinned staging buffers, asynchronous copies.
+# A pageable source would make every cudaMemcpyAsync synchronous (and each call would stall the stream it is on).
+_RING = {}
+_RING_SLOTS, _RING_BYTES = 8, 1 << 16
+
+
+def upload_small(arr, device):
+    """numpy array -> device tensor of the same dtype / shape, on torch's current stream, without a pageable copy.
+    Arrays above 64 KB fall back to a one-off pinned buffer."""
+    import numpy as np
+    import torch
+    arr = np.ascontiguousarray(arr)
+    nbytes = arr.nbytes
+    dev = torch.device(device)
+    if nbytes == 0:
+        return torch.empty(arr.shape, dtype=torch.from_numpy(arr).dtype, device=dev)
+    if nbytes > _RING_BYTES:
+        return torch.from_numpy(arr).pin_memory().to(dev, non_blocking=True)
+    ring = _RING.get(dev)
+    if ring is None:
+        ring = {'bufs': [torch.empty(_RING_BYTES, dtype=torch.uint8).pin_memory() for _ in range(_RING_SLOTS)],
+                'events': [None] * _RING_SLOTS, 'next': 0}
+        _RING[dev] = ring
+    i = ring['next']
+    ring['next'] = (i + 1) % _RING_SLOTS
+    if ring['events'][i] is not None:
+        ring['events'][i].synchronize()          # the copy that last used this slot has finished (8 uploads ago)
+    stage = ring['bufs'][i][:nbytes]
+    stage.numpy()[:] = arr.reshape(-1).view(np.uint8)
+    out = stage.to(dev, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    ring['events'][i] = ev
+    return out.view(torch.from_numpy(arr).dtype).reshape(arr.shape)

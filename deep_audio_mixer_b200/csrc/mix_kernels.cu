@@ -802,7 +802,48 @@ __global__ void __launch_bounds__(kBlock) scale_scalar_kernel(const TI* __restri
         store_vec<TO, V>(out + v * V, y);
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// N1: packed little-endian PCM bytes -> float samples (x * scale), element for element (the channel
+// interleave is kept; K1 / the bus sum take interleaved rows).  24-bit is the case no tensor dtype covers.
+template <int kBytes, typename TO>
+__global__ void __launch_bounds__(kBlock) pcm_unpack_kernel(const unsigned char* __restrict__ src, long long n, double scale,
+                                                            TO* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n; i += (long long)gridDim.x * kBlock) {
+        const unsigned char* b = src + i * kBytes;
+        int v;
+        if (kBytes == 2) v = (int)(short)(b[0] | (b[1] << 8));
+        else if (kBytes == 3) v = ((int)(b[0] | (b[1] << 8) | (b[2] << 16)) << 8) >> 8;      // sign-extend 24 bits
+        else v = (int)(b[0] | (b[1] << 8) | (b[2] << 16) | ((unsigned)b[3] << 24));
+        out[i] = (TO)((double)v * scale);
+    }
+}
+
 }  // namespace
+
+extern "C" int dam_pcm_unpack(const void* src, int bits, int64_t n, double scale, void* out, int out_dtype, void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(src && out, "null pointer argument");
+    DAM_CHECK_ARG(bits == 16 || bits == 24 || bits == 32, "bits must be 16, 24 or 32");
+    DAM_CHECK_ARG(out_dtype == DAM_F32 || out_dtype == DAM_F64, "out_dtype must be F32 or F64");
+    DAM_CHECK_ARG(n >= 0, "negative size");
+    if (n == 0) return DAM_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = grid_for(n, 8);
+    const unsigned char* s = reinterpret_cast<const unsigned char*>(src);
+#define DAM_UNPACK(B)                                                                                        \
+    do {                                                                                                     \
+        if (out_dtype == DAM_F32) pcm_unpack_kernel<B, float><<<grid, kBlock, 0, st>>>(s, n, scale, (float*)out);   \
+        else pcm_unpack_kernel<B, double><<<grid, kBlock, 0, st>>>(s, n, scale, (double*)out);                      \
+        dam_note_launch();                                                                                   \
+    } while (0)
+    if (bits == 16) DAM_UNPACK(2);
+    else if (bits == 24) DAM_UNPACK(3);
+    else DAM_UNPACK(4);
+#undef DAM_UNPACK
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
 
 extern "C" int dam_scale(const void* x, int dtype, int64_t n, double gain, void* out, int out_dtype, void* stream) {
     dam_clear_error();

@@ -72,7 +72,13 @@ stft_db_kernel(const StftParams p) {
             const long long g0 = t0 * hop - kNfft / 2;
             const int span = (nf - 1) * hop + kNfft;
             if (p.audio_dtype == DAM_F32)      stage_tile<R, float, float, kThreads>(p, s_stage, row, g0, span, tid);
-            else if (p.audio_dtype == DAM_I16) stage_tile<R, float, short, kThreads>(p, s_stage, row, g0, span, tid);
+            else if (p.audio_dtype == DAM_I16) {
+                // PCM16 prologue in the COMPUTE precision: x / 32768 and the mean of two channels are exact in
+                // float32, so float32 compute keeps the float32 prologue (librosa.load semantics); float64 compute
+                // is the soundfile path (sf.read yields float64), where the augmentation gain multiplies a double
+                if (sizeof(R) == 8) stage_tile<R, double, short, kThreads>(p, s_stage, row, g0, span, tid);
+                else stage_tile<R, float, short, kThreads>(p, s_stage, row, g0, span, tid);
+            }
             else                               stage_tile<R, double, double, kThreads>(p, s_stage, row, g0, span, tid);
         }
         __syncthreads();

@@ -114,14 +114,38 @@ class MultitrackAudioDataset(data.Dataset):
             chunks.append(audio)
         return np.stack(chunks)
 
+    def _read_chunk_device(self, song_i: int, chunk_i: int) -> torch.Tensor:
+        """The chunk of every track on the device, [5, n, C], in the narrowest form that still yields the bits of
+        soundfile's float64 samples (N1): PCM16 files are uploaded as int16 (2 bytes per sample instead of 8; K1
+        scales by 1/32768 and averages the channels exactly), PCM24 files as their 3-byte samples and decoded by
+        dam_pcm_unpack; anything else goes up as the float64 array ``_read_chunk`` returns."""
+        song_name = self.songlist[song_i]
+        a = chunk_i * self._chunk_length * self._sr
+        b = (chunk_i + 1) * self._chunk_length * self._sr
+        paths = [self._get_track_path(song_name, t) for t in self._tracklist]
+        infos = [wavio.info(p) for p in paths]
+        widths = {(wi.sampwidth, wi.is_float, wi.channels) for wi in infos}
+        if len(widths) == 1 and not infos[0].is_float and infos[0].sampwidth in (2, 3):
+            sw, _, ch = next(iter(widths))
+            if ch == 1:
+                raise IndexError('tracks are expected to be stereo (data/dataset.py:195)')
+            raw = np.stack([wavio.read_bytes(p, a, b)[0] for p in paths])          # [5, n * C * sw] uint8
+            dev_raw = torch.from_numpy(raw).to(self._dev(), non_blocking=True)
+            n = raw.shape[1] // (sw * ch)
+            if sw == 2:
+                return dev_raw.view(torch.int16).reshape(5, n, ch)
+            from . import mixing
+            return mixing.pcm_unpack(dev_raw.reshape(-1), 24, torch.float64, shape=(5, n, ch))
+        return torch.from_numpy(self._read_chunk(song_i, chunk_i)).to(self._dev(), non_blocking=True)
+
     def _featurise(self, audio: torch.Tensor, gains=None) -> torch.Tensor:
-        """audio [R, n, C] float64 interleaved on the device -> [R, 1025, T] float64."""
+        """audio [R, n, C] interleaved on the device (float64, or int16 PCM) -> [R, 1025, T] float64."""
         g = None if gains is None else torch.as_tensor(gains, dtype=torch.float64)
-        return features.stft_db(audio, channel_axis=-1, row_gain=g)
+        return features.stft_db(audio, channel_axis=-1, row_gain=g, compute_dtype=torch.float64, out_dtype=torch.float64)
 
     def _process_on_the_fly(self, song_i: int, chunk_i: int) -> tuple:
         """data/dataset.py:185-210: five tracks, mono down-mix, optional gain, features; one launch."""
-        audio = torch.from_numpy(self._read_chunk(song_i, chunk_i)).to(self._dev(), non_blocking=True)
+        audio = self._read_chunk_device(song_i, chunk_i)
         gains = [np.random.uniform(0.6, 1.4) for _ in self._tracklist] if self._augment else None
         feats = self._featurise(audio, gains)
         train, gt = feats[:4], feats[4]
@@ -132,9 +156,11 @@ class MultitrackAudioDataset(data.Dataset):
     def get_batch(self, indices) -> tuple:
         """Featurise many chunks in one launch: returns (train [B, 4, 1025, T], gt [B, 1025, T]) on
         the device.  This is the path a training loop should use instead of forked workers."""
-        audio = np.stack([self._read_chunk(*self._calculate_song_index(i)) for i in indices])   # [B,5,n,C]
-        B = audio.shape[0]
-        dev_audio = torch.from_numpy(audio).to(self._dev(), non_blocking=True).reshape(B * 5, *audio.shape[2:])
+        chunks = [self._read_chunk_device(*self._calculate_song_index(i)) for i in indices]    # B x [5,n,C]
+        B = len(chunks)
+        if len({c.dtype for c in chunks}) > 1:
+            chunks = [c.double() / 32768.0 if c.dtype == torch.int16 else c for c in chunks]
+        dev_audio = torch.stack(chunks).reshape(B * 5, *chunks[0].shape[1:])
         gains = np.random.uniform(0.6, 1.4, size=B * 5) if self._augment else None
         feats = self._featurise(dev_audio, gains)                                             # [B*5, F, T]
         feats = feats.reshape(B, 5, feats.shape[-2], feats.shape[-1])
@@ -168,8 +194,7 @@ class MultitrackAudioDataset(data.Dataset):
             suffix = '_norm' if self._normalize else ''
             tag = '' if names == 'read' else '_{}s'.format(self._chunk_length)
             for chunk_i in range(int(self.song_durations[song_i] / self._chunk_length)):
-                audio = torch.from_numpy(self._read_chunk(song_i, chunk_i)).to(self._dev())
-                feats = self._featurise(audio).cpu().numpy()
+                feats = self._featurise(self._read_chunk_device(song_i, chunk_i)).cpu().numpy()
                 np.save(os.path.join(features_dir, '{}_gt{}{}.npy'.format(chunk_i, tag, suffix)), feats[4])
                 np.save(os.path.join(features_dir, '{}_train{}{}.npy'.format(chunk_i, tag, suffix)), feats[:4])
 

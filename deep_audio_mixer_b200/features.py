@@ -31,7 +31,7 @@ def stft_db(audio: torch.Tensor, n_fft: int = 2048, hop: int = 1024, window: tor
             compute_dtype: torch.dtype = None, out_dtype: torch.dtype = None,
             input_scale: float = None, row_gain: torch.Tensor = None,
             out: torch.Tensor = None, out_row_stride: int = 0, stats: torch.Tensor = None,
-            stream=None, frame_pitch: int = 0) -> torch.Tensor:
+            frame_pitch: int = 0) -> torch.Tensor:
     """20*log10(max(|STFT(audio)|, amin)) for every row of a CUDA tensor.
 
     audio        [..., n] (mono rows), or with ``channel_axis`` = -2 ([..., C, n], planar) or -1
@@ -47,6 +47,8 @@ def stft_db(audio: torch.Tensor, n_fft: int = 2048, hop: int = 1024, window: tor
                  multiple of 8 (T = 173, 87); the result is then the [..., :T] view of a [..., F, pitch]
                  buffer (non-contiguous, like the reference's own compute_features output).
     Returns      [..., n_fft/2+1, T] contiguous (T innermost), T = 1 + n // hop.
+    The kernel runs on torch's CURRENT stream (the stream the caching allocator hands the temporaries and the
+    output out on); use ``with torch.cuda.stream(s):`` to run it elsewhere.
     """
     if not audio.is_cuda:
         raise ValueError('stft_db needs a CUDA tensor (host arrays go through compute_features)')
@@ -132,7 +134,7 @@ def stft_db(audio: torch.Tensor, n_fft: int = 2048, hop: int = 1024, window: tor
             row_stride, chan_stride, samp_stride, n_inner, outer_stride, float(input_scale), _lib.ptr(row_gain),
             _lib.ptr(window), n_fft, hop, float(amin), float(multiplier),
             _lib.dtype_code(compute_dtype), _lib.ptr(out), _lib.dtype_code(out_dtype), int(out_row_stride),
-            0 if pitch == T else pitch, _lib.ptr(stats), _lib.stream_ptr(stream))
+            0 if pitch == T else pitch, _lib.ptr(stats), _lib.stream_ptr())
     _lib.check(rc, 'dam_stft_db')
     if out_row_stride:
         return out

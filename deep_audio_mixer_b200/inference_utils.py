@@ -3,9 +3,12 @@
 What changes under the hood (same results): all chunks of a song are featurised by ONE K1 launch per
 stem straight into the [chunks, 4, 1025, T] model input (stereo -> mono fused into the staging), the
 CNN runs once on that batch instead of once per chunk with a device->host sync each time, and the
-zero-order-hold mask, the per-stem multiply and (optionally) the stem sum are one K2 pass.  The tiny
-gain post-processing (10**(0.5 m) and the Savitzky-Golay filter over <= a few hundred values) stays
-on the host with numpy/scipy, exactly as the reference computes it.
+zero-order-hold mask, the per-stem multiply and (optionally) the stem sum are one K2 pass.  The gain post-processing between the two halves stays on the DEVICE as well
+(N3 of SURVEY 8(f)): 10**(0.5 m) is evaluated in float64 and rounded to float32 (the correctly rounded value of
+the reference's float32 np.power), and scipy's savgol_filter(raw, win, 2) -- a LINEAR map of the K raw gains,
+edge polynomials of mode='interp' included -- is applied as a precomputed K x K float64 operator, so nothing
+synchronises with the host between the CNN and the mix; the gains are copied back once, at the end, only
+because the reference returns them as Python lists.
 """
 import numpy as np
 import torch
@@ -84,21 +87,76 @@ def song_features(stems: torch.Tensor, chunk_samples: int, n_chunks: int, window
     return out
 
 
-def predict_gains(model, feats: torch.Tensor, batch: int = 64) -> np.ndarray:
-    """Run the CNN on [K, 4, F, T] features; returns raw head outputs m [K, 4] (float32, host)."""
+def predict_gains_device(model, feats: torch.Tensor, batch: int = 64) -> torch.Tensor:
+    """Run the CNN on [K, 4, F, T] features; returns the raw head outputs m [K, 4] float32 ON THE DEVICE.
+    The reference calls the model once per chunk with batch 1 (inference_utils.py:111-124); batching K chunks
+    gives the same gains only in eval mode (BatchNorm running statistics, no dropout), so the model is switched
+    to eval() for the call and its previous mode restored afterwards."""
+    was_training = bool(getattr(model, 'training', False))
+    if was_training:
+        model.eval()
     outs = []
-    with torch.no_grad():
-        for i in range(0, feats.shape[0], batch):
-            _, ms = model(feats[i:i + batch].float())
-            outs.append(torch.cat([m.reshape(-1, 1) for m in ms], dim=1))
-    return torch.cat(outs).float().cpu().numpy()
+    try:
+        with torch.no_grad():
+            for i in range(0, feats.shape[0], batch):
+                _, ms = model(feats[i:i + batch].float())
+                outs.append(torch.cat([m.reshape(-1, 1) for m in ms], dim=1))
+    finally:
+        if was_training:
+            model.train()
+    if not outs:
+        return torch.empty((0, 4), dtype=torch.float32, device=feats.device)
+    return torch.cat(outs).float()
+
+
+def predict_gains(model, feats: torch.Tensor, batch: int = 64) -> np.ndarray:
+    """Host copy of ``predict_gains_device`` (one synchronisation)."""
+    return predict_gains_device(model, feats, batch).cpu().numpy()
+
+
+def gains_from_heads(m: torch.Tensor) -> torch.Tensor:
+    """scalar_dB_to_amplitude on the device: float32(10**(0.5 m)) evaluated in float64, i.e. the correctly
+    rounded float32 value of the reference's np.power(10.0, 0.5 * float32) (data/dataset_utils.py:46-50; numpy >= 2
+    keeps that expression in float32, and its float32 power is faithful, not correctly rounded: the two agree to
+    one float32 ulp, 6e-8 relative, tested)."""
+    return torch.pow(10.0, 0.5 * m.double()).float()
+
+
+def _savgol_window(num_chunks: int) -> int:
+    cand = int(num_chunks / 4)
+    return cand if cand % 2 else cand + 1
 
 
 def smooth_gains(raw, num_chunks: int) -> np.ndarray:
-    """inference_utils.py:137-140: Savitzky-Golay, window odd(int(num_chunks/4)), order 2."""
-    cand = int(num_chunks / 4)
-    win = cand if cand % 2 else cand + 1
-    return savgol_filter(raw, win, 2)
+    """inference_utils.py:137-140: Savitzky-Golay, window odd(int(num_chunks/4)), order 2 (host, scipy)."""
+    return savgol_filter(raw, _savgol_window(num_chunks), 2)
+
+
+_SAVGOL_OPS = {}
+
+
+def savgol_operator(n_gains: int, num_chunks: int, device=None) -> torch.Tensor:
+    """[K, K] float64 matrix A with savgol_filter(x, win, 2) == A @ x for every x of length K = n_gains: scipy's
+    filter (interior convolution AND the polynomial fits of mode='interp' at both ends) is linear in x, so A is
+    obtained by filtering the K unit vectors with scipy itself.  Banded in the interior, dense in the first and
+    last win // 2 rows.  Cached per (K, win, device); scipy raises for win <= 2 exactly as in the reference."""
+    win = _savgol_window(num_chunks)
+    dev = _device(device)
+    key = (n_gains, win, str(dev))
+    op = _SAVGOL_OPS.get(key)
+    if op is None:
+        A = savgol_filter(np.eye(n_gains), win, 2, axis=0)          # column j = filter response to e_j
+        op = torch.from_numpy(np.ascontiguousarray(A)).to(dev)
+        if len(_SAVGOL_OPS) > 256:
+            _SAVGOL_OPS.clear()
+        _SAVGOL_OPS[key] = op
+    return op
+
+
+def smooth_gains_device(raw: torch.Tensor, num_chunks: int) -> torch.Tensor:
+    """raw [K, S] (float32 / float64, device) -> Savitzky-Golay smoothed gains [K, S] float64, on the device.
+    Equal to scipy's result to rounding (different summation order: <= 1e-15 relative)."""
+    return savgol_operator(raw.shape[0], num_chunks, raw.device) @ raw.double()
 
 
 def mix_song_smooth(dataset, model, loaded_tracks: dict, chunk_length=1, sr=44100,
@@ -114,16 +172,19 @@ def mix_song_smooth(dataset, model, loaded_tracks: dict, chunk_length=1, sr=4410
     num_chunks = int(N / chunk_samples)
     n_an = num_chunks - 1                      # the last chunk is never analysed (range(1, num_chunks))
     feats = song_features(stems, chunk_samples, n_an)
-    m = predict_gains(model, feats)            # [n_an, 4] float32
-    raw_gains, smooth = {}, {}
-    g = np.empty((S, n_an), dtype=np.float64)
-    for i, t in enumerate(keys):
-        raw = [float(scalar_dB_to_amplitude(np.squeeze(m[k, i]))) for k in range(n_an)]
-        raw_gains[t] = raw
-        sm = smooth_gains(raw, num_chunks)
-        smooth[t] = list(sm)
-        g[i] = sm
+    m = predict_gains_device(model, feats)     # [n_an, 4] float32, device
+    raw_dev = gains_from_heads(m)              # float32, like float(np.power(10.0, 0.5 * float32))
+    smooth_dev = smooth_gains_device(raw_dev, num_chunks)                     # [n_an, S] float64
+    g = smooth_dev.t().contiguous()                                            # [S, n_an]
     res = mixing.gain_mix(stems, g, compute_dtype=torch.float64, want_mix=want_mix, want_stems=True)
+    # everything above is asynchronous; the gains come back once because the reference returns Python lists
+    if return_device:
+        raw_gains = {t: raw_dev[:, i].double() for i, t in enumerate(keys)}
+        smooth = {t: g[i] for i, t in enumerate(keys)}
+    else:
+        raw_h, smooth_h = raw_dev.double().cpu().numpy(), g.cpu().numpy()
+        raw_gains = {t: [float(v) for v in raw_h[:, i]] for i, t in enumerate(keys)}
+        smooth = {t: list(smooth_h[i]) for i, t in enumerate(keys)}
     mixed = unstack_tracks(res['stems'], keys, to_host=host and not return_device)
     if want_mix:
         mix = res['mix'] if (return_device or not host) else res['mix'].cpu().numpy()

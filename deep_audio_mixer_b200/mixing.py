@@ -14,14 +14,16 @@ def _check_cuda(t, name):
 
 def gain_mix(stems: torch.Tensor, gains, interp_coef: int = None, hold_single: bool = False,
              compute_dtype: torch.dtype = torch.float64, out_dtype: torch.dtype = None,
-             want_mix: bool = True, want_stems: bool = False, want_stats: bool = False, stream=None):
+             want_mix: bool = True, want_stems: bool = False, want_stats: bool = False):
     """Zero-order-hold gain masks x stems, summed over stems (kernel K2).
 
     stems [S, C, N] (or a batch [B, S, C, N]) CUDA float32/float64 planar audio; gains [S, K]
     ([B, S, K]) array-like or tensor, amplitude
     gains.  mask_s[i] = gains[s][min(i // interp_coef, K-1)], interp_coef = int(N / K) by default
     (inference_utils.py:26); K == 1 gives an all-zero mask unless hold_single (the reference quirk).
-    Returns dict(mix=[C, N], stems=[S, C, N], peak=[C], sumsq=[C]) for the requested outputs.
+    Returns dict(mix=[C, N], stems=[S, C, N], peak=[C], sumsq=[C]) for the requested outputs.  Runs on torch's
+    current stream.  Device gains are used in place (no copy, no synchronisation); host gains go through a small
+    ring of pinned staging buffers and an asynchronous copy.
     """
     _check_cuda(stems, 'stems')
     batched = stems.dim() == 4
@@ -33,8 +35,11 @@ def gain_mix(stems: torch.Tensor, gains, interp_coef: int = None, hold_single: b
         stems = stems.unsqueeze(0)
     B, S, C, N = stems.shape
     dev = stems.device
-    g = torch.as_tensor(np.asarray(gains, dtype=np.float64) if not isinstance(gains, torch.Tensor) else gains)
-    g = g.to(device=dev, dtype=torch.float64).reshape(B, S, -1).contiguous()
+    if isinstance(gains, torch.Tensor) and gains.is_cuda:
+        g = gains.to(dtype=torch.float64).reshape(B, S, -1).contiguous()         # no-ops when already in that form
+    else:
+        g = _lib.upload_small(np.asarray(gains.cpu() if isinstance(gains, torch.Tensor) else gains, dtype=np.float64), dev)
+        g = g.reshape(B, S, -1)
     K = g.shape[2]
     assert K <= N or N == 0, "Target mask should be longer than the initial one"
     if interp_coef is None:
@@ -51,7 +56,7 @@ def gain_mix(stems: torch.Tensor, gains, interp_coef: int = None, hold_single: b
             S, C, N, stems.stride(1), stems.stride(2),
             _lib.ptr(g), K, int(interp_coef), int(bool(hold_single)), _lib.dtype_code(compute_dtype),
             _lib.ptr(mix), _lib.ptr(st_out), _lib.dtype_code(out_dtype),
-            _lib.ptr(peak), _lib.ptr(sumsq), _lib.stream_ptr(stream))
+            _lib.ptr(peak), _lib.ptr(sumsq), _lib.stream_ptr())
     _lib.check(rc, 'dam_gain_mix')
     if not batched:
         mix, st_out, peak, sumsq = [None if t is None else t[0] for t in (mix, st_out, peak, sumsq)]
@@ -98,6 +103,21 @@ def bus_sum(stems: torch.Tensor, group, n_bus: int = 4, batch_dims: int = 0,
                                     _lib.ptr(out), _lib.ptr(mono), C, _lib.stream_ptr())
     _lib.check(rc, 'dam_bus_sum')
     return (out, mono) if want_mono else out
+
+
+def pcm_unpack(raw: torch.Tensor, bits: int, out_dtype=torch.float64, shape=None) -> torch.Tensor:
+    """Packed little-endian PCM bytes (uint8 CUDA tensor) -> float samples scaled by 2**-(bits-1), the values
+    soundfile.read returns (N1: 24-bit WAV data decoded on the device, 3 bytes per sample over PCIe)."""
+    _check_cuda(raw, 'raw')
+    if raw.dtype != torch.uint8 or not raw.is_contiguous():
+        raise ValueError('raw must be a contiguous uint8 tensor')
+    n = raw.numel() // (bits // 8)
+    out = torch.empty(n, dtype=out_dtype, device=raw.device)
+    with torch.cuda.device(raw.device):
+        rc = _lib.lib().dam_pcm_unpack(_lib.ptr(raw), int(bits), n, 1.0 / float(1 << (bits - 1)), _lib.ptr(out),
+                                       _lib.dtype_code(out_dtype), _lib.stream_ptr())
+    _lib.check(rc, 'dam_pcm_unpack')
+    return out.reshape(shape) if shape is not None else out
 
 
 def row_reduce(x: torch.Tensor, want_absmax=True, want_sumsq=True):
@@ -152,10 +172,14 @@ def scale(x: torch.Tensor, gain: float, out_dtype=None) -> torch.Tensor:
 
 
 def normalize_loudness(data: torch.Tensor, input_loudness: float, target_loudness: float,
-                       out_dtype=None) -> torch.Tensor:
-    """pyloudnorm.normalize.loudness: data * 10**((target - input)/20) (evaluation.py:64)."""
+                       out_dtype=torch.float64) -> torch.Tensor:
+    """pyloudnorm.normalize.loudness: ``np.power(10.0, (target - input) / 20.0) * data`` (evaluation.py:64,
+    mean_loudness_model.py:15-17, listening_test_data_preparation.py:23).  The gain is a numpy float64 scalar, so
+    under numpy >= 2 (the version the goldens were generated with) the product -- and the result -- is float64
+    whatever the dtype of ``data``; every drop-in of that expression here (sum_and_normalize, produce_mixture,
+    MeanLoudnessModel) follows this one rule."""
     gain = float(np.power(10.0, (target_loudness - input_loudness) / 20.0))
-    return scale(data, gain, out_dtype=out_dtype or data.dtype)
+    return scale(data, gain, out_dtype=out_dtype)
 
 
 def peak_normalize(x: torch.Tensor) -> torch.Tensor:

@@ -138,16 +138,20 @@ class SegmentBatchPipeline:
         return dict(mix=norm, lufs=lufs, peak=res['peak'], sumsq=res['sumsq'], features=feats, m=m)
 
     def run_host(self, raw_host: torch.Tensor, m_host: torch.Tensor, out_host: torch.Tensor,
-                 lufs_host: torch.Tensor, sub_batch: int = 4, streams=None):
-        """End-to-end form with HOST (pinned) buffers: raw_host [B, S, C, N] float32 -> out_host
-        [B, C, N] float64 and lufs_host [B].  The batch is cut into sub-batches; uploads, kernels and
-        downloads of consecutive sub-batches overlap on three streams."""
+                 lufs_host: torch.Tensor, sub_batch: int = 4, streams=None, copy_mode: str = 'overlap'):
+        """End-to-end form with HOST (pinned) buffers: raw_host [B, S, C, N] float32 or int16 (PCM16) -> out_host
+        [B, C, N] (float64 like the reference's mix, or float32: the dtype of ``out_host`` decides) and lufs_host
+        [B].  The batch is cut into sub-batches; uploads, kernels and downloads of consecutive sub-batches overlap
+        on three streams.  copy_mode='serial' queues the downloads on the upload stream, one direction at a time
+        per GPU (with many GPUs behind one host, concurrent up- and downloads interfere: see DESIGN.md section 6)."""
         B = raw_host.shape[0]
         nc = self.n_chunks(raw_host.shape[-1])
         dev = self.device
         if streams is None:
             streams = [torch.cuda.Stream(dev) for _ in range(3)]
         s_in, s_cmp, s_out = streams
+        if copy_mode == 'serial':
+            s_out = s_in
         cur = torch.cuda.current_stream(dev)
         for st in streams:
             st.wait_stream(cur)
@@ -168,7 +172,7 @@ class SegmentBatchPipeline:
                 ev_cmp.record(s_cmp)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_cmp)
-                out_host[b0:b1].copy_(res['mix'], non_blocking=True)
+                out_host[b0:b1].copy_(res['mix'], non_blocking=True)      # converts on the device if out_host is float32
                 lufs_host[b0:b1].copy_(res['lufs'], non_blocking=True)
                 res['mix'].record_stream(s_out)
                 res['lufs'].record_stream(s_out)

@@ -70,6 +70,19 @@ def read_raw(path, start=0, stop=None):
     return data.reshape(n, wi.channels), wi.samplerate
 
 
+def read_bytes(path, start=0, stop=None):
+    """The stored bytes of frames [start, stop) untouched (uint8 array) plus the file's WavInfo: what the device
+    ingest uploads -- 2 or 3 bytes per sample instead of the 8 of a float64 array."""
+    wi = info(path)
+    stop = wi.frames if stop is None else min(stop, wi.frames)
+    start = max(0, min(start, stop))
+    n = stop - start
+    with open(path, 'rb') as f:
+        f.seek(wi.data_offset + start * wi.sampwidth * wi.channels)
+        buf = f.read(n * wi.sampwidth * wi.channels)
+    return np.frombuffer(buf, dtype=np.uint8), wi
+
+
 def read(path, start=0, stop=None, dtype='float64'):
     """soundfile.read(path, start=, stop=): float [n, C] (or [n] for mono), PCM scaled by
     2**-(bits-1)."""
@@ -85,7 +98,7 @@ def read(path, start=0, stop=None, dtype='float64'):
 
 
 def write(path, data, samplerate, subtype='PCM_16'):
-    """soundfile.write for [n, C] / [n] arrays: PCM_16 (default, clipped) or FLOAT."""
+    """soundfile.write for [n, C] / [n] arrays: PCM_16 (default, clipped), PCM_24 or FLOAT."""
     data = np.asarray(data)
     if data.ndim == 1:
         data = data[:, None]
@@ -93,10 +106,13 @@ def write(path, data, samplerate, subtype='PCM_16'):
     if subtype == 'PCM_16':
         pcm = np.clip(np.round(data.astype(np.float64) * 32768.0), -32768, 32767).astype('<i2')
         tag, bits, payload = 1, 16, pcm.tobytes()
+    elif subtype == 'PCM_24':
+        v = np.clip(np.round(data.astype(np.float64) * 8388608.0), -8388608, 8388607).astype('<i4')
+        tag, bits, payload = 1, 24, np.ascontiguousarray(v).view(np.uint8).reshape(-1, 4)[:, :3].tobytes()
     elif subtype == 'FLOAT':
         tag, bits, payload = 3, 32, data.astype('<f4').tobytes()
     else:
-        raise ValueError('subtype must be PCM_16 or FLOAT')
+        raise ValueError('subtype must be PCM_16, PCM_24 or FLOAT')
     sw = bits // 8
     with open(path, 'wb') as f:
         f.write(struct.pack('<4sI4s', b'RIFF', 36 + len(payload), b'WAVE'))

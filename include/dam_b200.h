@@ -257,6 +257,14 @@ int dam_gated_loudness(const double* seg_sumsq, int64_t n_signals, int n_channel
 /* Number of frames dam_stft_db produces for n_samples (1 + n_samples / hop). */
 int64_t dam_stft_num_frames(int64_t n_samples, int hop);
 
+/*
+ * N1: packed little-endian PCM samples -> float samples, element for element (interleaving kept):
+ * out[i] = (sample i as a signed `bits`-bit integer) * scale.  Replaces the decode half of
+ * soundfile.read / librosa.load (data/dataset.py:194, data/dataset_utils.py:53-83) for the sample widths no
+ * tensor dtype covers (24-bit); scale = 2^-(bits-1) reproduces soundfile.  src: n * bits/8 bytes on the device.
+ */
+int dam_pcm_unpack(const void* src, int bits, int64_t n, double scale, void* out, int out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

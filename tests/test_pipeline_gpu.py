@@ -14,6 +14,7 @@ from deep_audio_mixer_b200 import dataset as D
 from deep_audio_mixer_b200 import evaluation as E
 from deep_audio_mixer_b200 import inference_utils as IU
 from deep_audio_mixer_b200 import models as M
+from deep_audio_mixer_b200 import mixing as mixing_mod
 from deep_audio_mixer_b200 import synthetic, wavio
 
 pytestmark = pytest.mark.gpu
@@ -236,3 +237,154 @@ def test_bus_sum_mono_output_feeds_k1_with_the_same_bits(cuda_device):
     b3, m3 = mixing.bus_sum(raw3, [0, 0, 1, 1], 2, batch_dims=1, want_mono=True)
     b3h = b3.cpu().numpy()                                       # numpy divides; torch multiplies by 1/3
     assert np.array_equal(m3.cpu().numpy(), ((b3h[:, :, 0] + b3h[:, :, 1]) + b3h[:, :, 2]) / np.float32(3.0))
+
+
+# ---- N3: gain post-processing on the device ------------------------------------------------------------------
+@pytest.mark.parametrize('K', [14, 29, 149, 299])
+def test_savgol_operator_matches_scipy(cuda_device, K):
+    """inference_utils.py:136-141: savgol_filter(raw, odd(int(num_chunks/4)), 2) as a precomputed K x K operator
+    applied on the device.  scipy's own result (interior convolution and the mode='interp' edge polynomials) is
+    reproduced to rounding; bit equality is not attainable with a different summation order."""
+    from scipy.signal import savgol_filter
+    num_chunks = K + 1
+    rng = np.random.default_rng(K)
+    raw = rng.uniform(0.3, 2.0, size=(K, 4))
+    win = int(num_chunks / 4)
+    win = win if win % 2 else win + 1
+    ref = savgol_filter(raw, win, 2, axis=0)
+    got = IU.smooth_gains_device(torch.from_numpy(raw).cuda(), num_chunks).cpu().numpy()
+    assert got.dtype == np.float64 and got.shape == ref.shape
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-13
+    assert np.array_equal(IU.smooth_gains(raw[:, 0], num_chunks), savgol_filter(raw[:, 0], win, 2))
+    with pytest.raises(ValueError):                      # num_chunks <= 7: scipy refuses win <= polyorder, like the reference
+        IU.smooth_gains_device(torch.ones(6, 4, device='cuda'), 7)
+
+
+def test_gains_from_heads_equals_numpy_float32_power(cuda_device):
+    """scalar_dB_to_amplitude (data/dataset_utils.py:46-50) on float32 head outputs, device vs numpy."""
+    rng = np.random.default_rng(5)
+    m = rng.uniform(-3.0, 1.5, size=(4096, 4)).astype(np.float32)
+    ref = np.power(10.0, 0.5 * m)                        # numpy >= 2: float32 in, float32 out
+    assert ref.dtype == np.float32
+    got = IU.gains_from_heads(torch.from_numpy(m).cuda()).cpu().numpy()
+    assert got.dtype == np.float32
+    ulp = np.abs(got.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64))
+    # numpy's float32 power is itself only faithful (<= 1 ulp): the device value, the correctly rounded one, is
+    # within one float32 ulp (6e-8 relative) of it on every element
+    assert ulp.max() <= 1
+    exact = np.power(10.0, 0.5 * m.astype(np.float64)).astype(np.float32)
+    assert (got == exact).mean() > 0.999
+
+
+def test_mix_song_smooth_device_resident_has_no_host_round_trip(cuda_device):
+    """return_device=True: tracks in, tracks / gains out, all on the device; equal to the host-facing call."""
+    sr, N = 44100, 44100 * 12
+    song = synthetic.make_song(41, 4, N, kind='music', dtype=np.float32)
+    host_tracks = {k: song[i] for i, k in enumerate(OM.STEMS)}
+    dev_tracks = {k: torch.from_numpy(v).cuda() for k, v in host_tracks.items()}
+    a = IU.mix_song_smooth(D.Featuriser(), FakeGainModel(), host_tracks, chunk_length=1, sr=sr)
+    b = IU.mix_song_smooth(D.Featuriser(), FakeGainModel(), dev_tracks, chunk_length=1, sr=sr, return_device=True)
+    for k in OM.STEMS:
+        assert b[0][k].is_cuda and b[1][k].is_cuda and b[2][k].is_cuda
+        assert np.array_equal(a[0][k], b[0][k].cpu().numpy())
+        assert np.array_equal(np.array(a[1][k]), b[1][k].cpu().numpy())
+        assert np.array_equal(np.array(a[2][k]), b[2][k].cpu().numpy())
+
+
+def test_mix_song_legacy(cuda_device):
+    """inference_utils.py:44-102 (legacy mix_song): mono tracks, chunk k of every stem multiplied by the RAW head
+    output m_k, stems summed, samples past the analysed chunks left at zero; mask_history holds the raw outputs."""
+    sr, N = 8000, 8000 * 7 + 123
+    song = synthetic.make_song(42, 4, N, sr=sr, kind='music', dtype=np.float32)[:, 0]          # [4, N] mono
+    tracks = {k: song[i] for i, k in enumerate(OM.STEMS)}
+    model = FakeGainModel()
+    mixed, hist = IU.mix_song(D.Featuriser(), model, tracks, chunk_length=1, sr=sr)
+    assert mixed.dtype == np.float64 and mixed.shape == (N,)
+    n_an = N // sr - 1
+    assert all(len(hist[k]) == n_an for k in OM.STEMS)
+    # oracle: the reference's loop with the model called per chunk on the oracle's features
+    expect = np.zeros(N)
+    for k in range(n_an):
+        seg = slice(k * sr, (k + 1) * sr)
+        feats = np.stack([OF.compute_features(tracks[t][seg].astype(np.float32), window=W) for t in OM.STEMS])
+        with torch.no_grad():
+            _, ms = model(torch.from_numpy(feats)[None].float())
+        for i, t in enumerate(OM.STEMS):
+            assert abs(hist[t][k] - float(ms[i])) <= 5e-5 * max(1.0, abs(float(ms[i])))
+            expect[seg] += tracks[t][seg].astype(np.float64) * hist[t][k]
+    assert np.all(mixed[n_an * sr:] == 0.0)
+    assert np.allclose(mixed, expect, rtol=1e-12, atol=1e-15)
+
+
+# ---- N4: feature cache round trip ------------------------------------------------------------------------------
+def test_feature_cache_round_trip(cuda_device, tmp_path):
+    """data/dataset.py:213-268: precompute_features writes {chunk}_train.npy / {chunk}_gt.npy straight from K1
+    output; a dataset opened with compute_features=False reads back exactly what __getitem__ computes on the fly,
+    under the names the reference's reader uses (its own writer uses other names: names='write' produces those)."""
+    root = str(tmp_path)
+    names = _write_dataset(root)
+    ds = D.MultitrackAudioDataset(root, songlist=list(names), chunk_length=2, seed=3)
+    ds.precompute_features()
+    cached = D.MultitrackAudioDataset(root, songlist=list(ds.songlist), chunk_length=2, compute_features=False)
+    cached.songlist, cached.song_durations = list(ds.songlist), list(ds.song_durations)
+    assert len(cached) == len(ds)
+    for i in range(len(ds)):
+        train, gt = ds[i]
+        ctrain, cgt = cached[i]
+        assert ctrain.shape == (4, 1025, 87) and cgt.shape == (1025, 87) and ctrain.dtype == np.float64
+        assert np.array_equal(train.numpy(), ctrain) and np.array_equal(gt.numpy(), cgt)
+    song0 = ds.songlist[0]
+    fdir = os.path.join(root, song0, song0 + '_FEATURES')
+    assert sorted(os.listdir(fdir))[:2] == ['0_gt.npy', '0_train.npy']
+    ds.precompute_features(names='write')
+    assert os.path.exists(os.path.join(fdir, '0_train_2s.npy')) and os.path.exists(os.path.join(fdir, '0_gt_2s.npy'))
+    assert np.array_equal(np.load(os.path.join(fdir, '0_train_2s.npy')), np.load(os.path.join(fdir, '0_train.npy')))
+    # augmentation on cached features adds 20 log10(g_s) per stem (data/dataset.py:170-179)
+    aug = D.MultitrackAudioDataset(root, songlist=list(ds.songlist), chunk_length=2, compute_features=False, augment_data=True)
+    aug.songlist, aug.song_durations = list(ds.songlist), list(ds.song_durations)
+    np.random.seed(11)
+    atrain, _ = aug[0]
+    np.random.seed(11)
+    g = np.random.uniform(0.6, 1.4, size=4)
+    assert np.allclose(atrain, cached[0][0] + 20 * np.log10(g)[:, None, None])
+
+
+# ---- N1: the dataset uploads the stored samples, not float64 --------------------------------------------------
+def test_dataset_pcm_ingest_is_bit_identical_to_float64_upload(cuda_device, tmp_path):
+    """PCM16 files go up as int16 and PCM24 files as their 3-byte samples (decoded by dam_pcm_unpack); the features
+    are the bits the float64 upload of soundfile-style samples gives, with and without the augmentation gain."""
+    sr = 44100
+    for subtype, dtype in (('PCM_16', torch.int16), ('PCM_24', torch.float64)):
+        root = str(tmp_path / subtype)
+        os.makedirs(root)
+        name = 'S'
+        song = synthetic.make_song(91, 5, sr * 5 + 777, kind='music', dtype=np.float32) * 0.5
+        os.makedirs(os.path.join(root, name, name + '_STEMS_JOINED'))
+        for j, t in enumerate(['bass', 'drums', 'vocals', 'other']):
+            wavio.write(os.path.join(root, name, name + '_STEMS_JOINED', '%s_STEM_%s.wav' % (name, t.upper())), song[j].T, sr, subtype)
+        wavio.write(os.path.join(root, name, name + '_MIX.wav'), song[4].T, sr, subtype)
+        ds = D.MultitrackAudioDataset(root, songlist=[name], chunk_length=2)
+        dev_audio = ds._read_chunk_device(0, 1)
+        assert dev_audio.dtype == dtype and dev_audio.shape == (5, 2 * sr, 2)
+        host64 = ds._read_chunk(0, 1)                                        # float64 [5, n, 2], as soundfile returns it
+        if subtype == 'PCM_24':
+            assert np.array_equal(dev_audio.cpu().numpy(), host64)
+        gains = [0.61, 0.97, 1.0, 1.23, 1.39]
+        for g in (None, gains):
+            a = ds._featurise(dev_audio, g)
+            b = ds._featurise(torch.from_numpy(host64).cuda(), g)
+            assert a.dtype == torch.float64 and torch.equal(a, b)
+        train, gt = ds[1]
+        ref = np.stack([OF.compute_features(np.mean(x, axis=1), window=W) for x in host64])
+        assert np.max(np.abs(train.numpy() - ref[:4])) <= 1e-4 and np.max(np.abs(gt.numpy() - ref[4])) <= 1e-4
+
+
+def test_host_gains_upload_ring(cuda_device):
+    """gain_mix with host gains: many calls through the 8-slot pinned ring give the same result as device gains."""
+    stems = torch.randn(3, 2, 5000, device='cuda')
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        g = rng.uniform(0.5, 1.5, size=(3, 7))
+        a = mixing_mod.gain_mix(stems, g)['mix']
+        b = mixing_mod.gain_mix(stems, torch.from_numpy(g).cuda())['mix']
+        assert torch.equal(a, b)
