@@ -46,6 +46,7 @@ class Meter:
         self._coeffs = (_biquad(4.0, 1 / np.sqrt(2), 1500.0, rate, 'high_shelf') +
                         _biquad(0.0, 0.5, 38.0, rate, 'high_pass'))
         self._bounds_cache = {}
+        self._ws_cache = {}          # (R, n, device, stream) -> (segment sums, filter-state workspace), reused per shape
 
     # -- gating-block geometry, evaluated in floating point exactly like pyloudnorm does
     def _geometry(self, n, dev):
@@ -104,14 +105,34 @@ class Meter:
         _lib.check(rc, 'dam_kweight_blocks')
         return z
 
+    def _workspace(self, R, n, n_seg, dev):
+        """Scratch of one call, kept per (shape, device, stream): small songs otherwise spend more time in two
+        allocator calls and a memset launch than in the kernels.  Calls are ordered on the stream, and every caller
+        consumes the segment sums before the next call of the same shape is enqueued."""
+        key = (R, n, n_seg, str(dev), torch.cuda.current_stream(dev).cuda_stream)
+        hit = self._ws_cache.get(key)
+        if hit is None:
+            ws_bytes = _lib.lib().dam_kweight_workspace_bytes(R, n)
+            hit = (torch.empty((R, n_seg), dtype=torch.float64, device=dev),
+                   torch.empty(ws_bytes // 8 + 2, dtype=torch.float64, device=dev), ws_bytes)
+            if len(self._ws_cache) > 32:
+                self._ws_cache.clear()
+            self._ws_cache[key] = hit
+        return hit
+
     def _segment_sums(self, rows: torch.Tensor):
         R, n = rows.shape
         dev = rows.device
         bounds, n_seg, first, last, num_blocks = self._geometry(n, dev)[:5]
-        seg = torch.zeros((R, n_seg), dtype=torch.float64, device=dev)
         lib = _lib.lib()
-        ws_bytes = lib.dam_kweight_workspace_bytes(R, n)
-        ws = torch.empty(ws_bytes // 8 + 2, dtype=torch.float64, device=dev)
+        if torch.cuda.is_current_stream_capturing():
+            # inside a CUDA-graph capture the scratch must belong to the graph's private pool
+            ws_bytes = lib.dam_kweight_workspace_bytes(R, n)
+            seg = torch.empty((R, n_seg), dtype=torch.float64, device=dev)
+            ws = torch.empty(ws_bytes // 8 + 2, dtype=torch.float64, device=dev)
+        else:
+            seg, ws, ws_bytes = self._workspace(R, n, n_seg, dev)
+        seg.zero_()
         coeffs = (ctypes.c_double * 10)(*self._coeffs)
         with torch.cuda.device(dev):
             rc = lib.dam_kweight_segments(_lib.ptr(rows), _lib.dtype_code(rows.dtype), R, n,

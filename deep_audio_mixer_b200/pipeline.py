@@ -182,6 +182,66 @@ class SegmentBatchPipeline:
         return keep
 
 
+class SongBatchMixdown:
+    """Known-gain single-pass mixdown of a BATCH of songs of one shape (BASELINE.json config 5, the listening-test
+    flow of data/listening_test_data_preparation.py:19-53 with per-chunk gains already known): dB-STFT features of
+    every stem chunk, zero-order-hold gain masks + stem sum, BS.1770 loudness of every mix, -20 LUFS normalisation.
+    One launch per stage for the whole batch (K1 x 1, K2 x 1, K4 x 3 + gating, K5 x 1), nothing synchronises with
+    the host and all shapes are static, so a batch is CUDA-graph capturable -- a 30 s song alone sits on the launch
+    floor (a few hundred microseconds of launches for ~50 us of memory traffic), sixteen of them do not."""
+
+    def __init__(self, chunk_samples=88200, hop=1024, n_fft=2048, sr=44100, target_lufs=-20.0):
+        self.chunk_samples, self.hop, self.n_fft, self.sr, self.target = chunk_samples, hop, n_fft, sr, target_lufs
+        self.meter = Meter(sr)
+
+    def feature_buffer(self, n_rows: int, device=None) -> torch.Tensor:
+        """[n_rows, F, pitch] float32 with the frame axis padded to a multiple of 8 (sector-aligned rows, see
+        SegmentBatchPipeline.feature_buffer); ``features`` returns its [..., :T] view."""
+        T = features.num_frames(self.chunk_samples, self.hop)
+        return torch.empty((n_rows, self.n_fft // 2 + 1, features.aligned_pitch(T)), dtype=torch.float32, device=device)
+
+    def features(self, stems: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """stems [B, S, C, N] float32 / int16 -> [B * S * n_chunks, F, T] float32 (rows ordered song, stem, chunk),
+        channels averaged inside K1, ONE launch: rows are addressed on two levels (stem plane, chunk)."""
+        B, S, C, N = stems.shape
+        nc = N // self.chunk_samples
+        if not stems.is_contiguous():
+            raise ValueError('stems must be contiguous [B, S, C, N]')
+        view = stems.as_strided((B * S, nc, C, self.chunk_samples), (stems.stride(1), self.chunk_samples, stems.stride(2), 1),
+                                stems.storage_offset())
+        if out is None:
+            out = self.feature_buffer(B * S * nc, stems.device)
+        T = features.num_frames(self.chunk_samples, self.hop)
+        F = self.n_fft // 2 + 1
+        pitch = out.shape[-1]
+        if tuple(out.shape[:2]) != (B * S * nc, F) or pitch < T or not out.is_contiguous():
+            raise ValueError('features: out must be a contiguous [%d, %d, >=%d] buffer' % (B * S * nc, F, T))
+        if C == 1:
+            features.stft_db(view[:, :, 0], self.n_fft, self.hop, out=out, out_row_stride=F * pitch, frame_pitch=pitch)
+        else:
+            features.stft_db(view, self.n_fft, self.hop, channel_axis=-2, out=out, out_row_stride=F * pitch, frame_pitch=pitch)
+        return out[..., :T]
+
+    def run(self, stems: torch.Tensor, gains: torch.Tensor, want_features: bool = True, feats_out: torch.Tensor = None):
+        """stems [B, S, C, N], gains [B, S, K] (device).  Returns dict(features, mix [B, C, N] float64 normalised to
+        the target, lufs [B] before normalisation, peak, sumsq)."""
+        B, S, C, N = stems.shape
+        feats = self.features(stems, feats_out) if want_features else None
+        res = mixing.gain_mix(stems, gains, compute_dtype=torch.float64, want_mix=True, want_stats=True)
+        lufs = self.meter.integrated_loudness_device(res['mix'])
+        factor = torch.pow(10.0, (self.target - lufs) / 20.0)
+        norm = mixing.scale_rows(res['mix'].reshape(B, C * N), factor).reshape(B, C, N)
+        return dict(features=feats, mix=norm, lufs=lufs, peak=res['peak'], sumsq=res['sumsq'])
+
+    @staticmethod
+    def algorithmic_bytes(B, S, C, N, chunk_samples, hop, n_fft=2048, want_features=True):
+        """Single-pass minimum: every stem sample read once, features and the normalised mix written
+        once (the loudness reduction rides on the mix pass)."""
+        nc = N // chunk_samples
+        feats = B * S * nc * (n_fft // 2 + 1) * (1 + chunk_samples // hop) * 4 if want_features else 0
+        return B * S * C * N * 4 + feats + B * C * N * 8
+
+
 def algorithmic_bytes(B, S, C, N, n_chunks, chunk_samples, hop, n_fft=2048, n_bus=4):
     """Minimum HBM bytes per stage for one batch (each operand read/written once)."""
     F = n_fft // 2 + 1

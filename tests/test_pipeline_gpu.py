@@ -388,3 +388,29 @@ def test_host_gains_upload_ring(cuda_device):
         a = mixing_mod.gain_mix(stems, g)['mix']
         b = mixing_mod.gain_mix(stems, torch.from_numpy(g).cuda())['mix']
         assert torch.equal(a, b)
+
+
+def test_song_batch_mixdown_matches_oracle(cuda_device):
+    """Config 5 (data/listening_test_data_preparation.py:19-53 with known per-chunk gains): a batch of songs through
+    one launch per stage equals the oracle song by song -- features, float64 mix (bit exact before normalisation),
+    loudness, -20 LUFS normalisation."""
+    from deep_audio_mixer_b200.pipeline import SongBatchMixdown
+    sr, N, S, B = 44100, 44100 * 5 + 100, 3, 2
+    songs = np.stack([synthetic.make_song(300 + b, S, N, kind='music', dtype=np.float32) for b in range(B)])   # [B,S,2,N]
+    gains = np.random.default_rng(3).uniform(0.5, 1.5, size=(B, S, 4))
+    mixer = SongBatchMixdown(chunk_samples=sr, hop=1024, sr=sr)
+    res = mixer.run(torch.from_numpy(songs).cuda(), torch.from_numpy(gains).cuda())
+    nc = N // sr
+    feats = res['features'].cpu().numpy().reshape(B, S, nc, 1025, -1)
+    for b in range(B):
+        st = OM.apply_gains(songs[b], gains[b])
+        mix = OM.stem_sum(st)
+        L = OL.integrated_loudness(mix.T, sr)
+        assert abs(float(res['lufs'][b]) - L) < 1e-8
+        assert np.allclose(res['mix'][b].cpu().numpy(), OM.normalize_loudness(mix, L, -20.0), rtol=1e-12, atol=0)
+        for s in range(S):
+            for k in range(nc):
+                mono = np.mean(songs[b, s][:, k * sr:(k + 1) * sr], axis=0)
+                truth = OF.compute_features(mono.astype(np.float64), window=W)
+                amp_t, amp_g = 10.0 ** (truth / 20), 10.0 ** (feats[b, s, k].astype(np.float64) / 20)
+                assert np.max(np.abs(amp_g - amp_t) / amp_t.max(axis=0, keepdims=True)) <= 1e-6
