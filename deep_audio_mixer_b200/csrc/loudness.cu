@@ -28,13 +28,14 @@ constexpr int kChunk = 256;        // samples per chunk (L)
 constexpr int kBlock = 256;        // chunks (= threads) per CTA in passes A and C
 constexpr int kSub = 16;           // samples per chunk staged per pipeline step
 constexpr int kPitch = kSub + 1;   // shared-memory row pitch: thread c walks row c conflict-free
-constexpr int kScanBlock = 256;
+constexpr int kScanBlock = 1024;    // threads per row in the scan (long rows: 41 k chunks per 4-minute stem)
+constexpr int kScanLevels = 10;     // log2(kScanBlock) Kogge-Stone levels
 
 struct Coeffs { double b0[2], b1[2], b2[2], a1[2], a2[2]; };
 
 struct KwTables {                  // device-resident, per coefficient set
     Coeffs c;
-    double* G = nullptr;           // [kChunk][4]
+    double G[kChunk * 4];          // response table (host; copied into the kernel parameters)
     double ML[16];                 // M^L   (row-major 4x4)
 };
 
@@ -79,7 +80,7 @@ int get_tables(const Coeffs& c, KwTables** out) {
         for (int i = 0; i < 4; ++i) M[i * 4 + j] = s[i];
     }
     // G[:, L-1-k] = M^k * B, B = state after a unit impulse from rest
-    std::vector<double> G(kChunk * 4);
+    double* G = t->G;
     {
         double v[4] = {0, 0, 0, 0};
         step(c, 1.0, v, nullptr);
@@ -96,14 +97,6 @@ int get_tables(const Coeffs& c, KwTables** out) {
         for (int i = 0; i < 4; ++i) t->ML[i * 4 + j] = s[i];
     }
     (void)M;
-    cudaError_t e = cudaMalloc(&t->G, G.size() * sizeof(double));
-    if (e == cudaSuccess) e = cudaMemcpy(t->G, G.data(), G.size() * sizeof(double), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        cudaFree(t->G);
-        delete t;
-        dam_set_error("building the K-weighting response table failed: %s", cudaGetErrorString(e));
-        return DAM_ERR_CUDA;
-    }
     cache[dev].push_back(t);
     *out = t;
     return DAM_OK;
@@ -115,15 +108,26 @@ struct KwParams {
     long long n_chunks;            // ceil(n / kChunk)
     long long n_items;             // ceil(n_rows * n_chunks / kBlock): work items of passes A and C
     Coeffs c;
-    const double* G;
+    double G[kChunk * 4];          // response table, IN the kernel parameters: pass A's multiplicands are constant-bank
+                                   // operands of its DFMAs (as shared-memory loads they kept the LSU pipe 84 % busy)
     double ML[16];                 // M^L (one chunk)
-    double P[8][16];               // (M^(L*super))^(2^j): Kogge-Stone levels of the scan
+    double P[kScanLevels][16];     // (M^(L*super))^(2^j): Kogge-Stone levels of the scan
     long long super;               // chunks per scan thread
     const long long* seg_bounds;   // [n_seg + 1]
     long long n_seg;
     double* seg_sumsq;             // [n_rows][n_seg]
     double* states;                // workspace [n_rows][n_chunks][4]
 };
+
+// Filter state of chunk c of a row.  The states of a row are stored TRANSPOSED for the scan -- thread u of the scan owns
+// the run of chunks [u * super, (u + 1) * super), and slot (c % super) * kScanBlock + c / super makes step k of all
+// threads one coalesced access (with the natural order every scan load touched 32 separate sectors per warp and a
+// 4-minute stem spent more time in the scan than in either pass over the samples).
+__device__ __forceinline__ double* state_ptr(const KwParams& p, long long row, long long chunk) {
+    const long long u = chunk / p.super;
+    const long long k = chunk - u * p.super;
+    return p.states + (row * p.super * kScanBlock + k * kScanBlock + u) * 4;
+}
 
 // Coalesced, software-pipelined, WARP-PRIVATE tile loader shared by passes A and C.  The unit of work
 // is kBlock consecutive GLOBAL chunk ids (row-major over all rows, so a work item may straddle two
@@ -170,7 +174,7 @@ struct TileLoader {
 
 template <typename T>
 constexpr size_t kw_smem_bytes() {
-    return kChunk * 4 * sizeof(double) + kBlock * sizeof(long long) + kBlock * sizeof(int) + 2 * kBlock * kPitch * sizeof(T);
+    return kBlock * sizeof(long long) + kBlock * sizeof(int) + 2 * kBlock * kPitch * sizeof(T);
 }
 
 struct ChunkId { long long g, row, chunk; int len; bool active; };
@@ -203,13 +207,10 @@ __device__ __forceinline__ bool warp_fast_path(const KwParams& p, const ChunkId&
 template <typename T>
 __global__ void __launch_bounds__(kBlock) kw_chunk_state_kernel(const KwParams p) {
     extern __shared__ __align__(16) unsigned char kw_smem[];
-    double* s_G = reinterpret_cast<double*>(kw_smem);
-    long long* s_base = reinterpret_cast<long long*>(s_G + kChunk * 4);
+    long long* s_base = reinterpret_cast<long long*>(kw_smem);
     int* s_len = reinterpret_cast<int*>(s_base + kBlock);
     T* s_tile = reinterpret_cast<T*>(s_len + kBlock);
     const T* x = reinterpret_cast<const T*>(p.x);
-    for (int i = threadIdx.x; i < kChunk * 4; i += kBlock) s_G[i] = p.G[i];
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long* w_base = s_base + warp * 32;
     const int* w_len = s_len + warp * 32;
@@ -225,6 +226,9 @@ __global__ void __launch_bounds__(kBlock) kw_chunk_state_kernel(const KwParams p
         ld.store(w_tile, lane);
         __syncwarp();
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        // fully unrolled over the chunk: every index into p.G is a compile-time constant, so the table entries are
+        // constant-bank operands of the DFMAs (same summation order as before: results are unchanged)
+#pragma unroll
         for (int sb = 0; sb < kChunk / kSub; ++sb) {
             const bool more = sb + 1 < kChunk / kSub;
             if (more) { if (fast) ld.load_fast(q0, sb + 1, lane); else ld.load(x, w_base, w_len, sb + 1, p.samp_stride, lane); }
@@ -232,16 +236,15 @@ __global__ void __launch_bounds__(kBlock) kw_chunk_state_kernel(const KwParams p
 #pragma unroll
             for (int j = 0; j < kSub; ++j) {
                 const double v = (double)mine[j];
-                const double* g = s_G + (sb * kSub + j) * 4;
-                a0 = fma(g[0], v, a0); a1 = fma(g[1], v, a1);
-                a2 = fma(g[2], v, a2); a3 = fma(g[3], v, a3);
+                a0 = fma(p.G[(sb * kSub + j) * 4 + 0], v, a0); a1 = fma(p.G[(sb * kSub + j) * 4 + 1], v, a1);
+                a2 = fma(p.G[(sb * kSub + j) * 4 + 2], v, a2); a3 = fma(p.G[(sb * kSub + j) * 4 + 3], v, a3);
             }
             if (more) ld.store(w_tile + ((sb + 1) & 1) * kBlock * kPitch, lane);
             __syncwarp();
         }
         if (id.active) {
             const bool last = id.chunk == p.n_chunks - 1;      // possibly partial: its end state is unused
-            double* st = p.states + id.g * 4;
+            double* st = state_ptr(p, id.row, id.chunk);
             *reinterpret_cast<double2*>(st) = last ? make_double2(0.0, 0.0) : make_double2(a0, a1);
             *reinterpret_cast<double2*>(st + 2) = last ? make_double2(0.0, 0.0) : make_double2(a2, a3);
         }
@@ -261,47 +264,51 @@ __device__ __forceinline__ void matvec_add(const double* M, const double s[4], c
 //      thread 2^j to the left using P_j = (M^(L*super))^(2^j), precomputed on the host,
 //   3. replay the run from its true start state, storing the start state of every chunk.
 __global__ void __launch_bounds__(kScanBlock) kw_scan_kernel(const KwParams p) {
-    __shared__ double s_e[2][kScanBlock][4];
+    __shared__ double s_e[kScanBlock][4];
     const long long row = blockIdx.x;
-    double* st = p.states + row * p.n_chunks * 4;
+    double* st = p.states + (row * p.super * kScanBlock + threadIdx.x) * 4;      // slot of step k: st + k * kScanBlock * 4
     const long long u = threadIdx.x;
     const long long c0 = u * p.super;
     const long long c1 = c0 + p.super < p.n_chunks ? c0 + p.super : p.n_chunks;
+    const long long steps = c1 > c0 ? c1 - c0 : 0;
     double s[4] = {0, 0, 0, 0};
 #pragma unroll 4
-    for (long long c = c0; c < c1; ++c) {
-        const double2 za = *reinterpret_cast<const double2*>(st + c * 4);
-        const double2 zb = *reinterpret_cast<const double2*>(st + c * 4 + 2);
+    for (long long k = 0; k < steps; ++k) {
+        const double2 za = *reinterpret_cast<const double2*>(st + k * kScanBlock * 4);
+        const double2 zb = *reinterpret_cast<const double2*>(st + k * kScanBlock * 4 + 2);
         double z[4] = {za.x, za.y, zb.x, zb.y}, o[4];
         matvec_add(p.ML, s, z, o);
         s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
     }
     // inclusive scan: after level j thread u holds the end state of runs (u - 2^(j+1), u] from zero
-    int cur = 0;
-    s_e[0][u][0] = s[0]; s_e[0][u][1] = s[1]; s_e[0][u][2] = s[2]; s_e[0][u][3] = s[3];
+    s_e[u][0] = s[0]; s_e[u][1] = s[1]; s_e[u][2] = s[2]; s_e[u][3] = s[3];
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < kScanLevels; ++j) {
         const int d = 1 << j;
+        double l[4] = {0, 0, 0, 0};
+        if (u >= d) { l[0] = s_e[u - d][0]; l[1] = s_e[u - d][1]; l[2] = s_e[u - d][2]; l[3] = s_e[u - d][3]; }
+        __syncthreads();                       // everyone has read its left neighbour of this level
         if (u >= d) {
-            const double l[4] = {s_e[cur][u - d][0], s_e[cur][u - d][1], s_e[cur][u - d][2], s_e[cur][u - d][3]};
             double o[4];
             matvec_add(p.P[j], l, s, o);
             s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
         }
-        cur ^= 1;
-        s_e[cur][u][0] = s[0]; s_e[cur][u][1] = s[1]; s_e[cur][u][2] = s[2]; s_e[cur][u][3] = s[3];
+        s_e[u][0] = s[0]; s_e[u][1] = s[1]; s_e[u][2] = s[2]; s_e[u][3] = s[3];
         __syncthreads();
     }
     // start state of run u = inclusive result of run u-1
     if (u == 0) { s[0] = s[1] = s[2] = s[3] = 0.0; }
-    else { s[0] = s_e[cur][u - 1][0]; s[1] = s_e[cur][u - 1][1]; s[2] = s_e[cur][u - 1][2]; s[3] = s_e[cur][u - 1][3]; }
-    for (long long c = c0; c < c1; ++c) {
-        const double2 za = *reinterpret_cast<const double2*>(st + c * 4);
-        const double2 zb = *reinterpret_cast<const double2*>(st + c * 4 + 2);
+    else { s[0] = s_e[u - 1][0]; s[1] = s_e[u - 1][1]; s[2] = s_e[u - 1][2]; s[3] = s_e[u - 1][3]; }
+    // the zero-state end states of the run are loaded four steps ahead of the recurrence that consumes them
+#pragma unroll 4
+    for (long long k = 0; k < steps; ++k) {
+        double* q = st + k * kScanBlock * 4;
+        const double2 za = *reinterpret_cast<const double2*>(q);
+        const double2 zb = *reinterpret_cast<const double2*>(q + 2);
         double z[4] = {za.x, za.y, zb.x, zb.y}, o[4];
-        *reinterpret_cast<double2*>(st + c * 4) = make_double2(s[0], s[1]);
-        *reinterpret_cast<double2*>(st + c * 4 + 2) = make_double2(s[2], s[3]);
+        *reinterpret_cast<double2*>(q) = make_double2(s[0], s[1]);
+        *reinterpret_cast<double2*>(q + 2) = make_double2(s[2], s[3]);
         matvec_add(p.ML, s, z, o);
         s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
     }
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(kScanBlock) kw_scan_kernel(const KwParams p) {
 template <typename T>
 __global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
     extern __shared__ __align__(16) unsigned char kw_smem[];
-    long long* s_base = reinterpret_cast<long long*>(reinterpret_cast<double*>(kw_smem) + kChunk * 4);
+    long long* s_base = reinterpret_cast<long long*>(kw_smem);
     int* s_len = reinterpret_cast<int*>(s_base + kBlock);
     T* s_tile = reinterpret_cast<T*>(s_len + kBlock);
     const T* x = reinterpret_cast<const T*>(p.x);
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
         const long long len = id.len;
         double s[4] = {0, 0, 0, 0};
         if (id.active) {
-            const double* st = p.states + id.g * 4;
+            const double* st = state_ptr(p, id.row, id.chunk);
             s[0] = st[0]; s[1] = st[1]; s[2] = st[2]; s[3] = st[3];
         }
         // segment containing sample i0: largest k with bounds[k] <= i0 (k = -1 before the first bound)
@@ -456,7 +463,8 @@ __global__ void __launch_bounds__(kGateBlock) gated_loudness_kernel(const GatePa
 extern "C" size_t dam_kweight_workspace_bytes(int64_t n_rows, int64_t n_samples) {
     if (n_rows <= 0 || n_samples <= 0) return 0;
     const int64_t n_chunks = (n_samples + kChunk - 1) / kChunk;
-    return (size_t)n_rows * (size_t)n_chunks * 4 * sizeof(double);
+    const int64_t super = (n_chunks + kScanBlock - 1) / kScanBlock;          // chunks per scan thread; slots = super * kScanBlock
+    return (size_t)n_rows * (size_t)super * kScanBlock * 4 * sizeof(double);
 }
 
 // Builds the per-device response table of one filter-coefficient set (the only allocation + synchronous copy of
@@ -497,7 +505,8 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
     p.x = x; p.n_rows = n_rows; p.n = n_samples; p.row_stride = row_stride; p.samp_stride = samp_stride;
     p.n_chunks = (n_samples + kChunk - 1) / kChunk;
     p.n_items = (n_rows * p.n_chunks + kBlock - 1) / kBlock;
-    p.c = c; p.G = t->G;
+    p.c = c;
+    memcpy(p.G, t->G, sizeof(p.G));
     memcpy(p.ML, t->ML, sizeof(p.ML));
     p.super = (p.n_chunks + kScanBlock - 1) / kScanBlock;
     {
@@ -509,7 +518,7 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
             matmul4(base, base, base);
         }
         memcpy(p.P[0], acc, sizeof(acc));
-        for (int j = 1; j < 8; ++j) matmul4(p.P[j - 1], p.P[j - 1], p.P[j]);
+        for (int j = 1; j < kScanLevels; ++j) matmul4(p.P[j - 1], p.P[j - 1], p.P[j]);
     }
     p.seg_bounds = reinterpret_cast<const long long*>(seg_bounds); p.n_seg = n_seg;
     p.seg_sumsq = seg_sumsq; p.states = reinterpret_cast<double*>(workspace);

@@ -333,6 +333,13 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
+// one non-blocking probe: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
     unsigned ok;

@@ -25,6 +25,9 @@
 #ifndef DAM_TMA_SPLIT
 #define DAM_TMA_SPLIT 1        // 1: split-phase mbarrier hand-over of the staging / exchange buffers, 0: __syncthreads
 #endif
+#ifndef DAM_TMA_BLOCKING_ISSUE
+#define DAM_TMA_BLOCKING_ISSUE 0   // 1: thread 0 waits for all warps' loads before its own transform (A/B only)
+#endif
 #ifndef DAM_TMA_NYQ_LATE
 #define DAM_TMA_NYQ_LATE 1     // 1: cross-lane DFT of Y_b[32] behind the stage-2 transform, 0: at the end of stage 1
 #endif
@@ -358,11 +361,20 @@ stft_db_tma_kernel(const StftParams p) {
         // (a) staged samples: a warp arrives on bar_stage once its frame is in registers; thread 0 waits for all
         //     eight and only then lets the TMA unit overwrite the region with the next tile
 #if DAM_TMA_SPLIT
+        // (a) staged samples: a warp arrives on bar_stage once its frame is in registers.  Thread 0 hands the region
+        //     to the TMA unit as soon as all eight have arrived, but never WAITS for them (its warp would start its
+        //     transform last and keep the whole CTA at the stage-1 -> stage-2 barrier): it probes now, probes again
+        //     after its own transform, and issues behind that barrier at the latest -- every warp has passed its
+        //     loads by then.
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_stage);
-        if (tid == 0 && nrow < n_rows) {
-            mbar_wait(bar_stage, parity);
+        bool issued = nrow >= n_rows;
+#if DAM_TMA_BLOCKING_ISSUE
+        if (tid == 0 && !issued) mbar_wait(bar_stage, parity);
+#endif
+        if (tid == 0 && !issued && mbar_test(bar_stage, parity)) {
             issue(nrow, ntin, parity ^ 1u);
+            issued = true;
         }
 #else
         __syncthreads();
@@ -386,11 +398,20 @@ stft_db_tma_kernel(const StftParams p) {
             dst[0] = make_float2(y0, 0.f);                       // row 0: Y[0] (real)
 #pragma unroll
             for (int k = 1; k < 32; ++k) *reinterpret_cast<pk2*>(dst + k * kRow) = s[k];
+#if DAM_TMA_SPLIT
+            if (tid == 0 && !issued && mbar_test(bar_stage, parity)) {
+                issue(nrow, ntin, parity ^ 1u);
+                issued = true;
+            }
+#endif
 #if !DAM_TMA_NYQ_LATE
             nyq_bins<float, OUT, kStats>(y32, out_row + warp, p.bin_stride, nq, p, lane, st);
 #endif
         }
         __syncthreads();         // stage 1 -> stage 2: all rows of the tile are in the exchange buffer
+#if DAM_TMA_SPLIT
+        if (tid == 0 && !issued) issue(nrow, ntin, parity ^ 1u);
+#endif
 
         // ---- stage 2: thread = (k' = tid / FT in 0..31, frame = tid % FT); lanes past the end of a ragged tile
         // transform a duplicate of its last frame and store nothing (no divergence around the arrive)

@@ -407,7 +407,7 @@ def test_song_batch_mixdown_matches_oracle(cuda_device):
         mix = OM.stem_sum(st)
         L = OL.integrated_loudness(mix.T, sr)
         assert abs(float(res['lufs'][b]) - L) < 1e-8
-        assert np.allclose(res['mix'][b].cpu().numpy(), OM.normalize_loudness(mix, L, -20.0), rtol=1e-12, atol=0)
+        assert np.allclose(res['mix'][b].cpu().numpy(), OM.normalize_loudness(mix, L, -20.0), rtol=1e-9, atol=0)     # the gain follows the device loudness (1e-9 LU apart)
         for s in range(S):
             for k in range(nc):
                 mono = np.mean(songs[b, s][:, k * sr:(k + 1) * sr], axis=0)
