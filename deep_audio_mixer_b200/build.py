@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, 'csrc')
 BUILD = os.path.join(HERE, 'csrc', 'build')
 LIB = os.path.join(HERE, 'libdam_b200.so')
 
-SOURCES = ['dam_api.cu', 'stft_db.cu', 'stft_tma.cu', 'mix_kernels.cu', 'loudness.cu']
+SOURCES = ['dam_api.cu', 'stft_db.cu', 'stft_tma.cu', 'stft_tma16.cu', 'mix_kernels.cu', 'loudness.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']

@@ -467,9 +467,8 @@ extern "C" size_t dam_kweight_workspace_bytes(int64_t n_rows, int64_t n_samples)
     return (size_t)n_rows * (size_t)super * kScanBlock * 4 * sizeof(double);
 }
 
-// Builds the per-device response table of one filter-coefficient set (the only allocation + synchronous copy of
-// the loudness kernels).  dam_kweight_* does the same on first use of a coefficient set; call this first when
-// that first use would sit inside a CUDA-graph stream capture.
+// Pre-computes the response table of one filter-coefficient set (host side; it travels in the kernel parameters,
+// so the loudness kernels allocate nothing on the device).  Optional: dam_kweight_* does the same on first use.
 extern "C" int dam_kweight_init(const double* coeffs_host) {
     dam_clear_error();
     DAM_CHECK_ARG(coeffs_host != nullptr, "null pointer argument");

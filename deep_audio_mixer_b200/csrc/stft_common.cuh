@@ -42,6 +42,7 @@ enum TmaMode { TMA_F32_MONO = 0, TMA_F32_PLANAR2 = 1, TMA_F32_INTER2 = 2, TMA_I1
 // stft_tma.cu: launches the TMA-staged kernel if the shape qualifies.  Returns DAM_OK (launched), 1 (shape does
 // not qualify: the caller uses the phase kernel) or a negative error code.  p.twiddle must be the float table.
 int dam_k1_launch_tma(StftParams p, cudaStream_t stream, int force_tab);
+int dam_k1_launch_tma16(StftParams p, cudaStream_t stream, int force_tab);     // 16 frames per tile (stft_tma16.cu)
 // name of the K1 kernel the last dam_stft_db call of this process dispatched (dam_last_stft_kernel())
 extern const char* dam_k1_last_kernel_name;
 

@@ -34,9 +34,13 @@
 
 namespace {
 
-constexpr int kFT = 8;                      // frames per tile = warps per CTA
+#ifndef DAM_TMA_FT
+#define DAM_TMA_FT 8           // frames per tile = warps per CTA: 8 (two CTAs per SM); stft_tma16.cu compiles this file
+#endif                         // again with 16 (one 16-warp CTA per SM, 64-byte store segments) as dam_k1_launch_tma16
+constexpr int kFT = DAM_TMA_FT;             // frames per tile = warps per CTA
+constexpr int kCtasPerSm = 16 / kFT;
 constexpr int kThreads = 32 * kFT;
-constexpr int kXch = XchStride<float, 8>::v;
+constexpr int kXch = XchStride<float, kFT>::v;
 constexpr int kWtStride = 68;               // floats per lane of the transposed window table
 constexpr int kRawSlack = 64;               // bytes behind a raw run for the 16-byte rounding of a skewed copy
 // Samples staged in front of a tile's first frame.  When n_samples is a multiple of hop the last frame of a row is
@@ -243,7 +247,7 @@ __device__ __forceinline__ Tile tile_of(unsigned tin, int hop, int T, long long 
 }
 
 template <bool kStats, bool kTabSmem, int kPitch, int kMaxIt>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 stft_db_tma_kernel(const StftParams p) {
     using OUT = float;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -469,9 +473,14 @@ int launch_pitch(const StftParams& p, size_t smem, unsigned grid, cudaStream_t s
 
 }  // namespace
 
+#if DAM_TMA_FT == 8
 const char* dam_k1_last_kernel_name = "";
+#define DAM_TMA_ENTRY dam_k1_launch_tma
+#else
+#define DAM_TMA_ENTRY dam_k1_launch_tma16
+#endif
 
-int dam_k1_launch_tma(StftParams p, cudaStream_t stream, int force_tab) {
+int DAM_TMA_ENTRY(StftParams p, cudaStream_t stream, int force_tab) {
     // ---- does the shape qualify?  (anything else runs the phase kernel, same results)
     const int hop = p.hop;
     if (hop % 8 != 0 || hop < 64 || hop > 1024) return 1;
@@ -509,15 +518,17 @@ int dam_k1_launch_tma(StftParams p, cudaStream_t stream, int force_tab) {
     for (int tab = 1; tab >= 0; --tab) {
         if (force_tab >= 0 && tab != force_tab) continue;
         const size_t smem = tma_smem_bytes(hop, mode, tab != 0);
-        if (2 * (smem + 1024) > 228 * 1024) continue;                // two CTAs per SM or not at all
-        long long grid = (long long)dam_sm_count() * 2;
+        if (kCtasPerSm * (smem + 1024) > 228 * 1024) continue;       // two CTAs per SM (one of 16 warps) or not at all
+        long long grid = (long long)dam_sm_count() * kCtasPerSm;
         if (grid > p.n_tiles) grid = p.n_tiles;
         p.step_rows = (unsigned)(grid / p.tiles_per_row);
         p.step_tiles = (unsigned)(grid % p.tiles_per_row);
         static const bool trace = getenv("DAM_K1_TRACE") != nullptr;
         if (trace) fprintf(stderr, "[dam] stft_db_tma_kernel mode=%d tables=%s smem=%zu hop=%d pitch=%lld T=%lld\n", mode,
                            tab ? "smem" : "global", smem, hop, (long long)p.bin_stride, (long long)p.T);
-        dam_k1_last_kernel_name = tab ? "stft_db_tma_kernel<tables in shared memory>" : "stft_db_tma_kernel<tables in global memory>";
+        dam_k1_last_kernel_name = kFT == 8 ? (tab ? "stft_db_tma_kernel<tables in shared memory>" : "stft_db_tma_kernel<tables in global memory>")
+                                           : (tab ? "stft_db_tma_kernel<16 frames per tile, tables in shared memory>"
+                                                  : "stft_db_tma_kernel<16 frames per tile, tables in global memory>");
         // conversion items per thread: span_max / 4 / 256 rounded up = 10 at hop 1024, the largest hop accepted
         static_assert(((kFT - 1) * 1024 + kNfft + kPre + 3) / 4 <= 10 * kThreads, "kMaxIt");
         return tab ? launch_pitch<true, 10>(p, smem, (unsigned)grid, stream) : launch_pitch<false, 10>(p, smem, (unsigned)grid, stream);

@@ -11,11 +11,12 @@
  *   - Unless a name ends in _host, every data pointer is a DEVICE pointer owned by the caller
  *     (e.g. torch.Tensor.data_ptr()); the call is asynchronous and ordered on `stream`
  *     (a cudaStream_t passed as void*; NULL = the legacy default stream).
- *   - No ownership transfer, no exceptions across the boundary.  The only global state are per-device
- *     constant tables (FFT twiddles; the K-weighting response table of each filter-coefficient set),
- *     created under a mutex with one cudaMalloc + synchronous cudaMemcpy on FIRST USE.  Nothing else
- *     allocates.  Call dam_init() / dam_kweight_init() beforehand if the first use would otherwise sit
- *     inside a CUDA-graph stream capture (an allocation there invalidates the capture).
+ *   - No ownership transfer, no exceptions across the boundary.  The only device-side global state is
+ *     one constant table per device (FFT twiddles), created under a mutex with one cudaMalloc +
+ *     synchronous cudaMemcpy on FIRST USE of dam_stft_db.  Nothing else allocates (the K-weighting
+ *     response table of a filter-coefficient set is host-side and travels in the kernel parameters).
+ *     Call dam_init() beforehand if that first use would otherwise sit inside a CUDA-graph stream
+ *     capture (an allocation there invalidates the capture).
  *   - Return value: DAM_OK (0) or a negative dam_status; dam_last_error() returns a
  *     thread-local human-readable message for the last failing call on this thread.
  *   - Strides are in ELEMENTS of the tensor's dtype, sizes in elements, never bytes.
@@ -216,7 +217,7 @@ int dam_row_reduce(const void* x, int dtype, int64_t n_rows, int64_t n, int64_t 
  *                16-byte aligned.
  */
 size_t dam_kweight_workspace_bytes(int64_t n_rows, int64_t n_samples);
-/* Build the response table of one coefficient set (HOST double[10], as below) on the current device now. */
+/* Pre-compute the (host-side) response table of one coefficient set (HOST double[10], as below); optional. */
 int dam_kweight_init(const double* coeffs_host);
 int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, int64_t n_samples,
                          int64_t row_stride, int64_t samp_stride,
