@@ -491,16 +491,16 @@ def run_ours(args):
         if os.path.exists(probe_path):
             with open(probe_path) as f:
                 pj = json.load(f)
-            best = None
-            for placement in ('default_placement', 'numa_bound'):
-                if isinstance(pj.get(placement), dict):
-                    for mode in ('bidir', 'serial'):
-                        g = pj[placement][mode]['aggregate_GBps']
-                        if best is None or g > best[0]:
-                            best = (g, placement + '/' + mode)
-            if best is not None:
-                e2e['pcie_ceiling'] = {'aggregate_GBps': best[0], 'mode': best[1], 'source': 'profiles/r02_pcie_probe_%d.json' % world,
-                                       'e2e_over_ceiling': e2e['achieved_GBps_all_ranks'] / best[0]}
+            pl = pj.get('numa_bound') if isinstance(pj.get('numa_bound'), dict) else pj['default_placement']
+            h2d, bidir = pl['h2d']['aggregate_GBps'], pl['bidir']['aggregate_GBps']
+            # lower bound of a step on this host: the uploads alone at the rate all ranks get together when nothing
+            # else is on the links (the downloads can hide behind them at best); `bidir` is the rate of the same
+            # traffic mix with both directions started together
+            floor_ms = world * up_bytes / h2d / 1e6
+            e2e['pcie_ceiling'] = {'h2d_only_aggregate_GBps': h2d, 'bidir_aggregate_GBps': bidir,
+                                   'source': 'profiles/r02_pcie_probe_%d.json (tools/pcie_probe_multi.py, all ranks at once)' % world,
+                                   'step_floor_ms': floor_ms, 'e2e_ms_over_floor': med / floor_ms,
+                                   'e2e_GBps_over_bidir': e2e['achieved_GBps_all_ranks'] / bidir}
         # variants of the same call (not the headline): one copy direction at a time per GPU; PCM16 host buffers
         # (the format the reference's WAV files are in -- int16 -> x/32768 float32 happens inside the bus-sum
         # kernel, halving the upload); float32 mix out (halves the download; the reference's mix is float64)
