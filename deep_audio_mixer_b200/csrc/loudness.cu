@@ -17,6 +17,8 @@
 #include "dam_common.cuh"
 
 #include <math.h>
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <mutex>
 #include <string.h>
@@ -113,6 +115,9 @@ struct KwParams {
     double ML[16];                 // M^L (one chunk)
     double P[kScanLevels][16];     // (M^(L*super))^(2^j): Kogge-Stone levels of the scan
     long long super;               // chunks per scan thread
+    long long cpp;                 // chunks per part = super * kScanBlock; a row is scanned by `parts` CTAs of one cluster
+    int parts;
+    double Q[16];                  // (M^L)^cpp: carries a start state across one whole part
     const long long* seg_bounds;   // [n_seg + 1]
     long long n_seg;
     double* seg_sumsq;             // [n_rows][n_seg]
@@ -124,9 +129,11 @@ struct KwParams {
 // threads one coalesced access (with the natural order every scan load touched 32 separate sectors per warp and a
 // 4-minute stem spent more time in the scan than in either pass over the samples).
 __device__ __forceinline__ double* state_ptr(const KwParams& p, long long row, long long chunk) {
-    const long long u = chunk / p.super;
-    const long long k = chunk - u * p.super;
-    return p.states + (row * p.super * kScanBlock + k * kScanBlock + u) * 4;
+    const long long part = chunk / p.cpp;
+    const long long cl = chunk - part * p.cpp;
+    const long long u = cl / p.super;
+    const long long k = cl - u * p.super;
+    return p.states + ((row * p.parts + part) * p.cpp + k * kScanBlock + u) * 4;
 }
 
 // Coalesced, software-pipelined, WARP-PRIVATE tile loader shared by passes A and C.  The unit of work
@@ -263,24 +270,8 @@ __device__ __forceinline__ void matvec_add(const double* M, const double s[4], c
 //   2. Kogge-Stone scan of the affine maps s -> P s + e across the CTA: level j combines with the
 //      thread 2^j to the left using P_j = (M^(L*super))^(2^j), precomputed on the host,
 //   3. replay the run from its true start state, storing the start state of every chunk.
-__global__ void __launch_bounds__(kScanBlock) kw_scan_kernel(const KwParams p) {
-    __shared__ double s_e[kScanBlock][4];
-    const long long row = blockIdx.x;
-    double* st = p.states + (row * p.super * kScanBlock + threadIdx.x) * 4;      // slot of step k: st + k * kScanBlock * 4
-    const long long u = threadIdx.x;
-    const long long c0 = u * p.super;
-    const long long c1 = c0 + p.super < p.n_chunks ? c0 + p.super : p.n_chunks;
-    const long long steps = c1 > c0 ? c1 - c0 : 0;
-    double s[4] = {0, 0, 0, 0};
-#pragma unroll 4
-    for (long long k = 0; k < steps; ++k) {
-        const double2 za = *reinterpret_cast<const double2*>(st + k * kScanBlock * 4);
-        const double2 zb = *reinterpret_cast<const double2*>(st + k * kScanBlock * 4 + 2);
-        double z[4] = {za.x, za.y, zb.x, zb.y}, o[4];
-        matvec_add(p.ML, s, z, o);
-        s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
-    }
-    // inclusive scan: after level j thread u holds the end state of runs (u - 2^(j+1), u] from zero
+__device__ __forceinline__ void scan_levels(const KwParams& p, double (&s)[4], double (*s_e)[4], long long u) {
+    // inclusive Kogge-Stone scan: after level j thread u holds the end state of runs (u - 2^(j+1), u]
     s_e[u][0] = s[0]; s_e[u][1] = s[1]; s_e[u][2] = s[2]; s_e[u][3] = s[3];
     __syncthreads();
 #pragma unroll
@@ -297,20 +288,88 @@ __global__ void __launch_bounds__(kScanBlock) kw_scan_kernel(const KwParams p) {
         s_e[u][0] = s[0]; s_e[u][1] = s[1]; s_e[u][2] = s[2]; s_e[u][3] = s[3];
         __syncthreads();
     }
-    // start state of run u = inclusive result of run u-1
-    if (u == 0) { s[0] = s[1] = s[2] = s[3] = 0.0; }
-    else { s[0] = s_e[u - 1][0]; s[1] = s_e[u - 1][1]; s[2] = s_e[u - 1][2]; s[3] = s_e[u - 1][3]; }
-    // the zero-state end states of the run are loaded four steps ahead of the recurrence that consumes them
+}
+
+// One CLUSTER of p.parts CTAs per row (one CTA for short rows): a single CTA scanning a 4-minute stem was bound by the
+// memory bandwidth of its one SM (47 % long-scoreboard + 34 % LG-throttle stalls, 8 SMs busy for 8 rows).  Every CTA
+// scans its part from a zero start state, the parts' end states are exchanged through distributed shared memory,
+// every CTA folds the ones in front of it into its true start state and scans again with that seed.
+__global__ void __launch_bounds__(kScanBlock) kw_scan_kernel(const KwParams p) {
+    namespace cg = cooperative_groups;
+    __shared__ double s_e[kScanBlock][4];
+    __shared__ double s_E[4];                  // end state of this CTA's part from a zero start (read by the cluster)
+    __shared__ double s_S[4];                  // true start state of this CTA's part
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned part = p.parts > 1 ? cluster.block_rank() : 0;
+    const long long row = blockIdx.x / p.parts;
+    double* st = p.states + ((row * p.parts + part) * p.cpp + threadIdx.x) * 4;   // slot of step k: st + k * kScanBlock * 4
+    const long long u = threadIdx.x;
+    const long long c0 = (long long)part * p.cpp + u * p.super;
+    long long c1 = c0 + p.super;
+    if (c1 > p.n_chunks) c1 = p.n_chunks;
+    const long long steps = c1 > c0 ? c1 - c0 : 0;
+    double e[4] = {0, 0, 0, 0};                // end state of this thread's run from a zero start
 #pragma unroll 4
     for (long long k = 0; k < steps; ++k) {
-        double* q = st + k * kScanBlock * 4;
-        const double2 za = *reinterpret_cast<const double2*>(q);
-        const double2 zb = *reinterpret_cast<const double2*>(q + 2);
+        const double2 za = *reinterpret_cast<const double2*>(st + k * kScanBlock * 4);
+        const double2 zb = *reinterpret_cast<const double2*>(st + k * kScanBlock * 4 + 2);
         double z[4] = {za.x, za.y, zb.x, zb.y}, o[4];
-        *reinterpret_cast<double2*>(q) = make_double2(s[0], s[1]);
-        *reinterpret_cast<double2*>(q + 2) = make_double2(s[2], s[3]);
-        matvec_add(p.ML, s, z, o);
-        s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+        matvec_add(p.ML, e, z, o);
+        e[0] = o[0]; e[1] = o[1]; e[2] = o[2]; e[3] = o[3];
+    }
+    double s[4] = {e[0], e[1], e[2], e[3]};
+    if (p.parts > 1) {
+        scan_levels(p, s, s_e, u);
+        if (u == kScanBlock - 1) { s_E[0] = s[0]; s_E[1] = s[1]; s_E[2] = s[2]; s_E[3] = s[3]; }
+        cluster.sync();                        // every part's end state is published
+        if (u == 0) {
+            double S[4] = {0, 0, 0, 0};
+            for (unsigned i = 0; i < part; ++i) {          // parts in front of this one are full: Q carries S across each
+                const double* r = cluster.map_shared_rank(s_E, i);
+                const double z[4] = {r[0], r[1], r[2], r[3]};
+                double o[4];
+                matvec_add(p.Q, S, z, o);
+                S[0] = o[0]; S[1] = o[1]; S[2] = o[2]; S[3] = o[3];
+            }
+            s_S[0] = S[0]; s_S[1] = S[1]; s_S[2] = S[2]; s_S[3] = S[3];
+        }
+        cluster.sync();                        // remote reads done before any CTA may exit; s_S visible to the CTA
+        // second scan, seeded: thread 0's run now starts from S
+        s[0] = e[0]; s[1] = e[1]; s[2] = e[2]; s[3] = e[3];
+        if (u == 0) {
+            const double S[4] = {s_S[0], s_S[1], s_S[2], s_S[3]};
+            double o[4];
+            matvec_add(p.P[0], S, e, o);
+            s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+        }
+    } else if (u == 0) {
+        s_S[0] = s_S[1] = s_S[2] = s_S[3] = 0.0;
+    }
+    scan_levels(p, s, s_e, u);
+    // start state of run u = inclusive result of run u-1 (the part's start state for run 0)
+    if (u == 0) { s[0] = s_S[0]; s[1] = s_S[1]; s[2] = s_S[2]; s[3] = s_S[3]; }
+    else { s[0] = s_e[u - 1][0]; s[1] = s_e[u - 1][1]; s[2] = s_e[u - 1][2]; s[3] = s_e[u - 1][3]; }
+    // The zero-state end states of four steps are loaded BEFORE the first of their slots is overwritten with a start
+    // state: written as load / store pairs per step the compiler must assume the store aliases the next load.
+    for (long long k0 = 0; k0 < steps; k0 += 4) {
+        double2 za[4], zb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long k = k0 + j < steps ? k0 + j : steps - 1;
+            za[j] = *reinterpret_cast<const double2*>(st + k * kScanBlock * 4);
+            zb[j] = *reinterpret_cast<const double2*>(st + k * kScanBlock * 4 + 2);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (k0 + j < steps) {
+                double* q = st + (k0 + j) * kScanBlock * 4;
+                double z[4] = {za[j].x, za[j].y, zb[j].x, zb[j].y}, o[4];
+                *reinterpret_cast<double2*>(q) = make_double2(s[0], s[1]);
+                *reinterpret_cast<double2*>(q + 2) = make_double2(s[2], s[3]);
+                matvec_add(p.ML, s, z, o);
+                s[0] = o[0]; s[1] = o[1]; s[2] = o[2]; s[3] = o[3];
+            }
+        }
     }
 }
 
@@ -460,11 +519,25 @@ __global__ void __launch_bounds__(kGateBlock) gated_loudness_kernel(const GatePa
 
 }  // namespace
 
+// Scan partition of a row of n_chunks chunks: `parts` CTAs of one thread-block cluster (1 for rows up to 8192 chunks,
+// up to 8 for the 41 k chunks of a 4-minute stem), every CTA 1024 threads x `super` consecutive chunks.
+static void scan_partition(int64_t n_chunks, int* parts, int64_t* super) {
+    int p = (int)((n_chunks + 8191) / 8192);
+    p = p < 1 ? 1 : (p > 8 ? 8 : p);
+    if (p == 3) p = 4;                       // cluster sizes 1, 2, 4, 8
+    else if (p > 4 && p < 8) p = 8;
+    const int64_t per_part = (n_chunks + p - 1) / p;
+    *parts = p;
+    *super = (per_part + kScanBlock - 1) / kScanBlock;
+}
+
 extern "C" size_t dam_kweight_workspace_bytes(int64_t n_rows, int64_t n_samples) {
     if (n_rows <= 0 || n_samples <= 0) return 0;
     const int64_t n_chunks = (n_samples + kChunk - 1) / kChunk;
-    const int64_t super = (n_chunks + kScanBlock - 1) / kScanBlock;          // chunks per scan thread; slots = super * kScanBlock
-    return (size_t)n_rows * (size_t)super * kScanBlock * 4 * sizeof(double);
+    int parts;
+    int64_t super;
+    scan_partition(n_chunks, &parts, &super);                                // slots per row = parts * super * kScanBlock
+    return (size_t)n_rows * (size_t)parts * (size_t)super * kScanBlock * 4 * sizeof(double);
 }
 
 // Pre-computes the response table of one filter-coefficient set (host side; it travels in the kernel parameters,
@@ -507,7 +580,12 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
     p.c = c;
     memcpy(p.G, t->G, sizeof(p.G));
     memcpy(p.ML, t->ML, sizeof(p.ML));
-    p.super = (p.n_chunks + kScanBlock - 1) / kScanBlock;
+    {
+        int parts;
+        int64_t super;
+        scan_partition(p.n_chunks, &parts, &super);
+        p.parts = parts; p.super = super; p.cpp = super * kScanBlock;
+    }
     {
         // P_0 = (M^L)^super by binary exponentiation, P_{j+1} = P_j^2
         double base[16], acc[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
@@ -518,6 +596,7 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
         }
         memcpy(p.P[0], acc, sizeof(acc));
         for (int j = 1; j < kScanLevels; ++j) matmul4(p.P[j - 1], p.P[j - 1], p.P[j]);
+        matmul4(p.P[kScanLevels - 1], p.P[kScanLevels - 1], p.Q);          // P_0^1024 = (M^L)^cpp
     }
     p.seg_bounds = reinterpret_cast<const long long*>(seg_bounds); p.n_seg = n_seg;
     p.seg_sumsq = seg_sumsq; p.states = reinterpret_cast<double*>(workspace);
@@ -548,7 +627,22 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
     if (dtype == DAM_F32) { kw_chunk_state_kernel<float><<<grid, kBlock, kw_smem_bytes<float>(), st>>>(p); dam_note_launch(); }
     else { kw_chunk_state_kernel<double><<<grid, kBlock, kw_smem_bytes<double>(), st>>>(p); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
-    { kw_scan_kernel<<<(unsigned)n_rows, kScanBlock, 0, st>>>(p); dam_note_launch(); }
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_rows * p.parts));
+        cfg.blockDim = dim3(kScanBlock);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.parts;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DAM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kw_scan_kernel, p));
+        dam_note_launch();
+    }
     DAM_CHECK_CUDA(cudaGetLastError());
     if (dtype == DAM_F32) { kw_apply_kernel<float><<<grid, kBlock, kw_smem_bytes<float>(), st>>>(p); dam_note_launch(); }
     else { kw_apply_kernel<double><<<grid, kBlock, kw_smem_bytes<double>(), st>>>(p); dam_note_launch(); }

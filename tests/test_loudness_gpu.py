@@ -75,3 +75,17 @@ def test_kweight_blocks_one_call_entry_point(cuda_device, n, rate):
     assert np.allclose(z, z2, rtol=1e-12, atol=0)
     with pytest.raises(Exception):
         Meter(rate).block_energies_device(torch.zeros(1, int(0.3 * rate), device='cuda', dtype=torch.float64))
+
+
+@pytest.mark.parametrize('n', [256 * 8192 + 300, 256 * 8193 * 2 + 5, 256 * 41344 - 77])
+def test_long_rows_scan_over_a_cluster_of_ctas(cuda_device, n):
+    """Rows of more than 8 192 chunks (47 s) are scanned by a thread-block cluster of 2 / 4 / 8 CTAs that hand the
+    parts' end states over through distributed shared memory: a 4-minute stem (41 344 chunks, 8 parts, the last two
+    partial / empty) must give the oracle's loudness like a short one."""
+    rng = np.random.default_rng(n % 1000)
+    x = (rng.normal(size=(n, 1)) * 0.1 * (1.0 + 0.5 * np.sin(np.arange(n) / 3.0e5))[:, None])
+    meter = Meter(44100)
+    assert abs(meter.integrated_loudness(x) - OL.integrated_loudness(x, 44100)) < 1e-8
+    z = meter.block_energies(torch.from_numpy(np.ascontiguousarray(x.T)).cuda())
+    z_ref = OL.block_energies(x, 44100)
+    assert np.max(np.abs(z - z_ref) / (np.abs(z_ref) + 1e-300)) < 1e-9
