@@ -121,7 +121,8 @@ struct KwParams {
     const long long* seg_bounds;   // [n_seg + 1]
     long long n_seg;
     double* seg_sumsq;             // [n_rows][n_seg]
-    double* states;                // workspace [n_rows][n_chunks][4]
+    double* states;                // workspace [n_rows][parts * cpp][4] (transposed per part, see state_ptr)
+    double* partials;              // workspace [n_rows * n_chunks][2]: pass C's per-chunk sums for the (at most two) segments it touches
 };
 
 // Filter state of chunk c of a row.  The states of a row are stored TRANSPOSED for the scan -- thread u of the scan owns
@@ -414,6 +415,12 @@ __global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
         }
         double* out = p.seg_sumsq + id.row * p.n_seg;
         double acc = 0.0;
+        // A chunk touches at most two segments unless segments are shorter than a chunk: the sums of the segment the
+        // chunk starts in and of the next one go to a per-chunk slot and are added up in chunk order by
+        // kw_segment_reduce_kernel (atomics would make the last bit of the loudness depend on the scheduling);
+        // only a third and later segment inside one chunk falls back to atomicAdd.
+        int flushes = 0;
+        double part0 = 0.0, part1 = 0.0;
         ld.store(w_tile, lane);
         __syncwarp();
 
@@ -436,7 +443,10 @@ __global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
                     for (int j = 0; j < kSub && base + j < len; ++j) {
                         const long long gi = i0 + base + j;
                         while (gi >= next) {          // crossed a segment boundary: flush
-                            if (seg >= 0 && seg < p.n_seg && acc != 0.0) atomicAdd(out + seg, acc);
+                            if (flushes == 0) part0 = acc;
+                            else if (flushes == 1) part1 = acc;
+                            else if (seg >= 0 && seg < p.n_seg && acc != 0.0) atomicAdd(out + seg, acc);
+                            ++flushes;
                             acc = 0.0;
                             ++seg;
                             next = seg + 1 <= p.n_seg ? p.seg_bounds[seg + 1] : (long long)0x7fffffffffffffffLL;
@@ -450,8 +460,32 @@ __global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
             if (more) ld.store(w_tile + ((sb + 1) & 1) * kBlock * kPitch, lane);
             __syncwarp();
         }
-        if (seg >= 0 && seg < p.n_seg && acc != 0.0) atomicAdd(out + seg, acc);
+        if (flushes == 0) part0 = acc;
+        else if (flushes == 1) part1 = acc;
+        else if (seg >= 0 && seg < p.n_seg && acc != 0.0) atomicAdd(out + seg, acc);
+        if (id.active) *reinterpret_cast<double2*>(p.partials + id.g * 2) = make_double2(part0, part1);
     }
+}
+
+// seg_sumsq[row][k] += the per-chunk partial sums of segment k, in chunk order (one thread per segment).
+__global__ void __launch_bounds__(256) kw_segment_reduce_kernel(const KwParams p) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= p.n_rows * p.n_seg) return;
+    const long long row = idx / p.n_seg, k = idx - row * p.n_seg;
+    const long long b0 = p.seg_bounds[k], b1 = p.seg_bounds[k + 1];
+    if (b0 >= p.n || b1 <= b0) return;
+    const long long c_lo = b0 / kChunk;
+    long long c_hi = (b1 - 1) / kChunk;
+    if (c_hi > p.n_chunks - 1) c_hi = p.n_chunks - 1;
+    const double* part = p.partials + row * p.n_chunks * 2;
+    double total = 0.0;
+    for (long long c = c_lo; c <= c_hi; ++c) {
+        const long long i0 = c * kChunk;
+        if (i0 >= b0) total += part[c * 2];                                   // the chunk starts inside segment k
+        else if (k == 0 || p.seg_bounds[k - 1] <= i0) total += part[c * 2 + 1];   // segment k starts at the chunk's first boundary
+        // else: a third or later segment of that chunk, added atomically by pass C
+    }
+    p.seg_sumsq[row * p.n_seg + k] += total;
 }
 
 // Gating + LUFS on the device (one CTA per signal), so batch pipelines never synchronise with the host.
@@ -537,7 +571,8 @@ extern "C" size_t dam_kweight_workspace_bytes(int64_t n_rows, int64_t n_samples)
     int parts;
     int64_t super;
     scan_partition(n_chunks, &parts, &super);                                // slots per row = parts * super * kScanBlock
-    return (size_t)n_rows * (size_t)parts * (size_t)super * kScanBlock * 4 * sizeof(double);
+    return (size_t)n_rows * (size_t)parts * (size_t)super * kScanBlock * 4 * sizeof(double) +
+           (size_t)n_rows * (size_t)n_chunks * 2 * sizeof(double);                // + per-chunk partial segment sums
 }
 
 // Pre-computes the response table of one filter-coefficient set (host side; it travels in the kernel parameters,
@@ -600,6 +635,7 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
     }
     p.seg_bounds = reinterpret_cast<const long long*>(seg_bounds); p.n_seg = n_seg;
     p.seg_sumsq = seg_sumsq; p.states = reinterpret_cast<double*>(workspace);
+    p.partials = p.states + (size_t)n_rows * (size_t)p.parts * (size_t)p.cpp * 4;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     static std::mutex mu;
     static bool configured[64] = {};
@@ -646,6 +682,8 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
     DAM_CHECK_CUDA(cudaGetLastError());
     if (dtype == DAM_F32) { kw_apply_kernel<float><<<grid, kBlock, kw_smem_bytes<float>(), st>>>(p); dam_note_launch(); }
     else { kw_apply_kernel<double><<<grid, kBlock, kw_smem_bytes<double>(), st>>>(p); dam_note_launch(); }
+    DAM_CHECK_CUDA(cudaGetLastError());
+    { kw_segment_reduce_kernel<<<(unsigned)((n_rows * n_seg + 255) / 256), 256, 0, st>>>(p); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }

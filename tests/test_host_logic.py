@@ -27,7 +27,8 @@ def test_library_exports_every_declared_symbol():
     assert lib.dam_version().decode().count('.') == 2
     assert lib.dam_stft_num_frames(88200, 1024) == 87
     # 4 chunks of 256 samples per row -> one slot per scan thread (1024), 4 doubles each, transposed for the scan
-    assert lib.dam_kweight_workspace_bytes(2, 1000) == 2 * 1024 * 4 * 8
+    # plus two partial segment sums per chunk
+    assert lib.dam_kweight_workspace_bytes(2, 1000) == 2 * 1024 * 4 * 8 + 2 * 4 * 2 * 8
 
 
 def test_ctypes_signatures_match_the_header_prototypes():
