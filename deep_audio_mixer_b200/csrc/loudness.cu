@@ -467,10 +467,13 @@ __global__ void __launch_bounds__(kBlock) kw_apply_kernel(const KwParams p) {
     }
 }
 
-// seg_sumsq[row][k] += the per-chunk partial sums of segment k, in chunk order (one thread per segment).
+// seg_sumsq[row][k] += the per-chunk partial sums of segment k: one WARP per segment, lane l takes chunks c_lo + l,
+// c_lo + l + 32, ... in order and the 32 lane sums are combined by a fixed shuffle tree -- the same order in every
+// run, whatever the scheduling.
 __global__ void __launch_bounds__(256) kw_segment_reduce_kernel(const KwParams p) {
-    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= p.n_rows * p.n_seg) return;
+    const long long idx = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (idx >= p.n_rows * p.n_seg) return;                                        // warp-uniform
     const long long row = idx / p.n_seg, k = idx - row * p.n_seg;
     const long long b0 = p.seg_bounds[k], b1 = p.seg_bounds[k + 1];
     if (b0 >= p.n || b1 <= b0) return;
@@ -478,14 +481,16 @@ __global__ void __launch_bounds__(256) kw_segment_reduce_kernel(const KwParams p
     long long c_hi = (b1 - 1) / kChunk;
     if (c_hi > p.n_chunks - 1) c_hi = p.n_chunks - 1;
     const double* part = p.partials + row * p.n_chunks * 2;
+    const bool second_ok = k == 0 || p.seg_bounds[k - 1] <= c_lo * kChunk;       // segment k starts at chunk c_lo's FIRST boundary
     double total = 0.0;
-    for (long long c = c_lo; c <= c_hi; ++c) {
-        const long long i0 = c * kChunk;
-        if (i0 >= b0) total += part[c * 2];                                   // the chunk starts inside segment k
-        else if (k == 0 || p.seg_bounds[k - 1] <= i0) total += part[c * 2 + 1];   // segment k starts at the chunk's first boundary
+    for (long long c = c_lo + lane; c <= c_hi; c += 32) {
+        const double2 v = *reinterpret_cast<const double2*>(part + c * 2);
+        if (c * kChunk >= b0) total += v.x;                                       // the chunk starts inside segment k
+        else if (second_ok) total += v.y;
         // else: a third or later segment of that chunk, added atomically by pass C
     }
-    p.seg_sumsq[row * p.n_seg + k] += total;
+    total = dam_warp_sum(total);
+    if (lane == 0) p.seg_sumsq[row * p.n_seg + k] += total;
 }
 
 // Gating + LUFS on the device (one CTA per signal), so batch pipelines never synchronise with the host.
@@ -683,7 +688,7 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
     if (dtype == DAM_F32) { kw_apply_kernel<float><<<grid, kBlock, kw_smem_bytes<float>(), st>>>(p); dam_note_launch(); }
     else { kw_apply_kernel<double><<<grid, kBlock, kw_smem_bytes<double>(), st>>>(p); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
-    { kw_segment_reduce_kernel<<<(unsigned)((n_rows * n_seg + 255) / 256), 256, 0, st>>>(p); dam_note_launch(); }
+    { kw_segment_reduce_kernel<<<(unsigned)((n_rows * n_seg * 32 + 255) / 256), 256, 0, st>>>(p); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }
