@@ -61,10 +61,12 @@ inline size_t tma_smem_bytes(int hop, int mode, bool tab_smem) {
 
 // offset-binary trick: int16 v -> float32 v exactly, two samples per 32-bit word
 //   bits(0x4B000000 | u16) = 2^23 + u16;  with u16 = v ^ 0x8000 (offset binary) the value is 2^23 + 32768 + v
-__device__ __forceinline__ void cvt2_i16(unsigned word, float& lo, float& hi) {
+//   With the exponent lowered by s the same two instructions yield v * 2^-s (the x / 32768 of PCM16, s = 15: the
+//   float 256 + u16 / 32768 minus 257), so a power-of-two input scale costs nothing.
+__device__ __forceinline__ void cvt2_i16(unsigned word, unsigned magic_bits, float magic_off, float& lo, float& hi) {
     const unsigned w = word ^ 0x80008000u;
-    lo = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)) - 8421376.0f;
-    hi = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)) - 8421376.0f;
+    lo = __uint_as_float(__byte_perm(w, magic_bits, 0x7610)) - magic_off;
+    hi = __uint_as_float(__byte_perm(w, magic_bits, 0x7632)) - magic_off;
 }
 
 // threadIdx.x through a volatile asm: values derived from it cannot be hoisted out of the tile loop (ptxas otherwise
@@ -79,6 +81,20 @@ __device__ __forceinline__ int tid_now() {
 struct ConvArgs {
     float scale;
     bool unit;
+    unsigned magic_bits;         // int16 -> float: exponent field of 2^(23 - s), s = 0 or the folded power-of-two scale
+    float magic_off;             // 2^-s * (2^23 + 2^15)
+    // PCM16 source: fold an input scale that is an exact power of two into the conversion itself
+    __device__ __forceinline__ void init(double input_scale, bool is_i16) {
+        scale = (float)input_scale;
+        unit = input_scale == 1.0;
+        int s = 0;
+        if (is_i16 && input_scale > 0.0) {
+            int e;
+            if (frexp(input_scale, &e) == 0.5 && 1 - e >= 0 && 1 - e <= 100) { s = 1 - e; unit = true; }
+        }
+        magic_bits = (unsigned)(150 - s) << 23;
+        magic_off = (float)ldexp(8421376.0, -s);
+    }
     __device__ __forceinline__ float in(float v) const { return unit ? v : __fmul_rn(v, scale); }
     __device__ __forceinline__ float mean2(float l, float r) const { return (in(l) + in(r)) * 0.5f; }
 };
@@ -123,15 +139,17 @@ __device__ __forceinline__ void convert_tile_mode(const unsigned char* raw, cons
             float4 o;
             if (kMode == TMA_I16_MONO) {
                 float v0, v1, v2, v3;
-                cvt2_i16(a[k].x, v0, v1); cvt2_i16(a[k].y, v2, v3);
+                cvt2_i16(a[k].x, cv.magic_bits, cv.magic_off, v0, v1); cvt2_i16(a[k].y, cv.magic_bits, cv.magic_off, v2, v3);
                 o = make_float4(cv.in(v0), cv.in(v1), cv.in(v2), cv.in(v3));
             } else if (kMode == TMA_I16_PLANAR2) {
                 float l0, l1, l2, l3, r0, r1, r2, r3;
-                cvt2_i16(a[k].x, l0, l1); cvt2_i16(a[k].y, l2, l3); cvt2_i16(a[k].z, r0, r1); cvt2_i16(a[k].w, r2, r3);
+                cvt2_i16(a[k].x, cv.magic_bits, cv.magic_off, l0, l1); cvt2_i16(a[k].y, cv.magic_bits, cv.magic_off, l2, l3);
+                cvt2_i16(a[k].z, cv.magic_bits, cv.magic_off, r0, r1); cvt2_i16(a[k].w, cv.magic_bits, cv.magic_off, r2, r3);
                 o = make_float4(cv.mean2(l0, r0), cv.mean2(l1, r1), cv.mean2(l2, r2), cv.mean2(l3, r3));
             } else if (kMode == TMA_I16_INTER2) {
                 float l0, r0, l1, r1, l2, r2, l3, r3;
-                cvt2_i16(a[k].x, l0, r0); cvt2_i16(a[k].y, l1, r1); cvt2_i16(a[k].z, l2, r2); cvt2_i16(a[k].w, l3, r3);
+                cvt2_i16(a[k].x, cv.magic_bits, cv.magic_off, l0, r0); cvt2_i16(a[k].y, cv.magic_bits, cv.magic_off, l1, r1);
+                cvt2_i16(a[k].z, cv.magic_bits, cv.magic_off, l2, r2); cvt2_i16(a[k].w, cv.magic_bits, cv.magic_off, l3, r3);
                 o = make_float4(cv.mean2(l0, r0), cv.mean2(l1, r1), cv.mean2(l2, r2), cv.mean2(l3, r3));
             } else if (kMode == TMA_F32_PLANAR2) {
                 const uint4 c = b[kTwo ? k : 0];
@@ -292,8 +310,7 @@ stft_db_tma_kernel(const StftParams p) {
     // second plane of a planar stereo tile: behind the first int16 plane inside the region, or the second region
     const int plane2_off = mode == TMA_I16_PLANAR2 ? span_max_of(hop) * 2 + kRawSlack : region_bytes;
     ConvArgs cv;
-    cv.scale = (float)p.input_scale;
-    cv.unit = p.input_scale == 1.0;
+    cv.init(p.input_scale, mode >= TMA_I16_MONO);
     StatAcc st;
 
     // Thread 0 hands the in-range bytes of tile (r, tin) to the TMA unit.  A source run that is not 16-byte
@@ -320,7 +337,9 @@ stft_db_tma_kernel(const StftParams p) {
         if (mode == TMA_F32_MONO) {
             s_x = reinterpret_cast<float*>(s_region + skew);
         } else {
-            convert_tile<kMaxIt>(mode, s_region + skew, s_region + skew + plane2_off, s_x, t.span, cv, tid_now());
+            // six items per thread cover a tile up to hop 512 (the unrolled, guarded iterations beyond cost issue slots)
+            if (t.span <= 6 * 4 * kThreads) convert_tile<6>(mode, s_region + skew, s_region + skew + plane2_off, s_x, t.span, cv, tid_now());
+            else convert_tile<kMaxIt>(mode, s_region + skew, s_region + skew + plane2_off, s_x, t.span, cv, tid_now());
             fence_proxy_async();                                  // generic writes before the next TMA write to the region
             __syncthreads();
         }
