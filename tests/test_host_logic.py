@@ -290,3 +290,22 @@ def test_trainer_epoch_matches_reference_loop():
 
     a, b = run(True), run(False)
     assert abs(a[0] - b[0]) < 1e-6 and abs(a[1] - b[1]) < 1e-6
+
+
+def test_corpus_spec_and_lpt_balance():
+    """bench.py --workload corpus (config 3): the synthetic MedleyDB-shaped corpus is deterministic, sized like
+    BASELINE.json says (122 songs x ~8 stems x ~4 min) and LPT keeps eight ranks within 2 % of each other."""
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import bench_workloads as BW
+    from deep_audio_mixer_b200 import sharding
+    spec = BW.corpus_spec()
+    assert spec == BW.corpus_spec() and len(spec) == 122
+    stems = np.array([s for s, _ in spec])
+    secs = np.array([t for _, t in spec])
+    assert 7.0 <= stems.mean() <= 9.0 and 220 <= secs.mean() <= 260 and np.all(secs % 5 == 0)
+    costs = [s * t for s, t in spec]
+    assert abs(sum(costs) - 122 * 8 * 240) / (122 * 8 * 240) < 0.1
+    for world in (2, 4, 8):
+        parts = sharding.assign_lpt(costs, world)
+        loads = [sum(costs[i] for i in p) for p in parts]
+        assert max(loads) / (sum(loads) / world) < 1.02
