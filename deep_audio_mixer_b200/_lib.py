@@ -27,6 +27,8 @@ SIGNATURES = {
                          _vp, _i, _i64, _i64, _vp, _vp]),
     'dam_gain_mix': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _i,
                           _vp, _vp, _vp]),
+    'dam_gain_mix_kweight': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _i, _i, _vp, _vp, _i,
+                                  _vp, _vp, _c.POINTER(_d), _vp, _c.c_size_t, _vp]),
     'dam_bus_sum': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _i64, _c.POINTER(_c.c_int32), _i, _d, _vp, _vp, _i, _vp]),
     'dam_feature_mix_fwd': (_i, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     'dam_feature_mix_bwd': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
@@ -37,6 +39,8 @@ SIGNATURES = {
     'dam_gated_loudness': (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i64, _d, _vp, _vp]),
     'dam_kweight_segments': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _c.POINTER(_d), _vp, _i64, _vp, _vp,
                                   _c.c_size_t, _vp]),
+    'dam_kweight_segments_resume': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _c.POINTER(_d), _vp, _i64, _vp, _vp,
+                                         _c.c_size_t, _vp]),
     'dam_scale': (_i, [_vp, _i, _i64, _d, _vp, _i, _vp]),
     'dam_pcm_unpack': (_i, [_vp, _i, _i64, _d, _vp, _i, _vp]),
     'dam_kweight_num_blocks': (_i64, [_i64, _d, _d, _d]),

@@ -108,7 +108,13 @@ def build_variant(name: str, defines, source: str = 'stft_tma.cu') -> str:
 if __name__ == '__main__':
     if '--variant' in sys.argv:
         i = sys.argv.index('--variant')
-        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        rest = sys.argv[i + 2:]
+        src = 'stft_tma.cu'
+        if '--source' in rest:                      # e.g. --source mix_kernels.cu
+            j = rest.index('--source')
+            src = rest[j + 1]
+            rest = rest[:j] + rest[j + 2:]
+        print(build_variant(sys.argv[i + 1], [d[2:] if d.startswith('-D') else d for d in rest], src))
     else:
         path = build_library(force='--force' in sys.argv, verbose='--verbose' in sys.argv)
         print(path)

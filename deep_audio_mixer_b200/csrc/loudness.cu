@@ -15,6 +15,7 @@
 //                       squares the output and adds it to the segment sums
 // This is the exact state hand-off (no warm-up approximation); all filter arithmetic is float64.
 #include "dam_common.cuh"
+#include "kweight_common.cuh"
 
 #include <math.h>
 #include <cooperative_groups.h>
@@ -26,11 +27,11 @@
 
 namespace {
 
-constexpr int kChunk = 256;        // samples per chunk (L)
+constexpr int kChunk = kKwChunk;    // samples per chunk (L)
 constexpr int kBlock = 256;        // chunks (= threads) per CTA in passes A and C
 constexpr int kSub = 16;           // samples per chunk staged per pipeline step
 constexpr int kPitch = kSub + 1;   // shared-memory row pitch: thread c walks row c conflict-free
-constexpr int kScanBlock = 1024;    // threads per row in the scan (long rows: 41 k chunks per 4-minute stem)
+constexpr int kScanBlock = kKwScanBlock;   // threads per row in the scan (long rows: 41 k chunks per 4-minute stem)
 constexpr int kScanLevels = 10;     // log2(kScanBlock) Kogge-Stone levels
 
 struct Coeffs { double b0[2], b1[2], b2[2], a1[2], a2[2]; };
@@ -125,16 +126,10 @@ struct KwParams {
     double* partials;              // workspace [n_rows * n_chunks][2]: pass C's per-chunk sums for the (at most two) segments it touches
 };
 
-// Filter state of chunk c of a row.  The states of a row are stored TRANSPOSED for the scan -- thread u of the scan owns
-// the run of chunks [u * super, (u + 1) * super), and slot (c % super) * kScanBlock + c / super makes step k of all
-// threads one coalesced access (with the natural order every scan load touched 32 separate sectors per warp and a
-// 4-minute stem spent more time in the scan than in either pass over the samples).
+// Filter state of chunk c of a row (layout: kweight_common.cuh).
 __device__ __forceinline__ double* state_ptr(const KwParams& p, long long row, long long chunk) {
-    const long long part = chunk / p.cpp;
-    const long long cl = chunk - part * p.cpp;
-    const long long u = cl / p.super;
-    const long long k = cl - u * p.super;
-    return p.states + ((row * p.parts + part) * p.cpp + k * kScanBlock + u) * 4;
+    const KwStateLayout lay = {p.states, p.super, p.cpp, p.parts};
+    return kw_state_ptr(lay, row, chunk);
 }
 
 // Coalesced, software-pipelined, WARP-PRIVATE tile loader shared by passes A and C.  The unit of work
@@ -233,20 +228,36 @@ __global__ void __launch_bounds__(kBlock) kw_chunk_state_kernel(const KwParams p
         if (fast) ld.load_fast(q0, 0, lane); else ld.load(x, w_base, w_len, 0, p.samp_stride, lane);
         ld.store(w_tile, lane);
         __syncwarp();
+        // Fully unrolled over the chunk: every index into p.G is a compile-time constant, so the table entries are
+        // constant-bank operands of the DFMAs.  Summation order of kweight_common.cuh (groups of 4 samples, pairwise
+        // over the groups): lvl[b] holds the finished subtree of 16 << b groups waiting for its right-hand sibling.
+        double lvl[4][4];
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        // fully unrolled over the chunk: every index into p.G is a compile-time constant, so the table entries are
-        // constant-bank operands of the DFMAs (same summation order as before: results are unchanged)
 #pragma unroll
         for (int sb = 0; sb < kChunk / kSub; ++sb) {
             const bool more = sb + 1 < kChunk / kSub;
             if (more) { if (fast) ld.load_fast(q0, sb + 1, lane); else ld.load(x, w_base, w_len, sb + 1, p.samp_stride, lane); }
             const T* mine = w_tile + (sb & 1) * kBlock * kPitch + lane * kPitch;
+            double S[4][4];
 #pragma unroll
-            for (int j = 0; j < kSub; ++j) {
-                const double v = (double)mine[j];
-                a0 = fma(p.G[(sb * kSub + j) * 4 + 0], v, a0); a1 = fma(p.G[(sb * kSub + j) * 4 + 1], v, a1);
-                a2 = fma(p.G[(sb * kSub + j) * 4 + 2], v, a2); a3 = fma(p.G[(sb * kSub + j) * 4 + 3], v, a3);
+            for (int q = 0; q < 4; ++q)
+                kw_group_sum(p.G + (sb * kSub + q * 4) * 4, (double)mine[q * 4], (double)mine[q * 4 + 1],
+                             (double)mine[q * 4 + 2], (double)mine[q * 4 + 3], S[q]);
+            double carry[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) carry[c] = __dadd_rn(__dadd_rn(S[0][c], S[1][c]), __dadd_rn(S[2][c], S[3][c]));
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if ((sb >> b) & 1) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) carry[c] = __dadd_rn(lvl[b][c], carry[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) lvl[b][c] = carry[c];
+                    break;
+                }
             }
+            if (!more) { a0 = carry[0]; a1 = carry[1]; a2 = carry[2]; a3 = carry[3]; }
             if (more) ld.store(w_tile + ((sb + 1) & 1) * kBlock * kPitch, lane);
             __syncwarp();
         }
@@ -560,7 +571,7 @@ __global__ void __launch_bounds__(kGateBlock) gated_loudness_kernel(const GatePa
 
 // Scan partition of a row of n_chunks chunks: `parts` CTAs of one thread-block cluster (1 for rows up to 8192 chunks,
 // up to 8 for the 41 k chunks of a 4-minute stem), every CTA 1024 threads x `super` consecutive chunks.
-static void scan_partition(int64_t n_chunks, int* parts, int64_t* super) {
+void dam_kw_scan_partition(int64_t n_chunks, int* parts, int64_t* super) {
     int p = (int)((n_chunks + 8191) / 8192);
     p = p < 1 ? 1 : (p > 8 ? 8 : p);
     if (p == 3) p = 4;                       // cluster sizes 1, 2, 4, 8
@@ -575,41 +586,54 @@ extern "C" size_t dam_kweight_workspace_bytes(int64_t n_rows, int64_t n_samples)
     const int64_t n_chunks = (n_samples + kChunk - 1) / kChunk;
     int parts;
     int64_t super;
-    scan_partition(n_chunks, &parts, &super);                                // slots per row = parts * super * kScanBlock
+    dam_kw_scan_partition(n_chunks, &parts, &super);                         // slots per row = parts * super * kScanBlock
     return (size_t)n_rows * (size_t)parts * (size_t)super * kScanBlock * 4 * sizeof(double) +
            (size_t)n_rows * (size_t)n_chunks * 2 * sizeof(double);                // + per-chunk partial segment sums
 }
 
 // Pre-computes the response table of one filter-coefficient set (host side; it travels in the kernel parameters,
 // so the loudness kernels allocate nothing on the device).  Optional: dam_kweight_* does the same on first use.
+static Coeffs parse_coeffs(const double* coeffs_host) {
+    Coeffs c;
+    for (int s = 0; s < 2; ++s) {
+        c.b0[s] = coeffs_host[s * 5 + 0]; c.b1[s] = coeffs_host[s * 5 + 1]; c.b2[s] = coeffs_host[s * 5 + 2];
+        c.a1[s] = coeffs_host[s * 5 + 3]; c.a2[s] = coeffs_host[s * 5 + 4];
+    }
+    return c;
+}
+
+int dam_kw_response_table(const double* coeffs_host, const double** G_host) {
+    KwTables* t = nullptr;
+    const int rc = get_tables(parse_coeffs(coeffs_host), &t);
+    if (rc == DAM_OK) *G_host = t->G;
+    return rc;
+}
+
 extern "C" int dam_kweight_init(const double* coeffs_host) {
     dam_clear_error();
     DAM_CHECK_ARG(coeffs_host != nullptr, "null pointer argument");
-    Coeffs c;
-    for (int s = 0; s < 2; ++s) {
-        c.b0[s] = coeffs_host[s * 5 + 0]; c.b1[s] = coeffs_host[s * 5 + 1]; c.b2[s] = coeffs_host[s * 5 + 2];
-        c.a1[s] = coeffs_host[s * 5 + 3]; c.a2[s] = coeffs_host[s * 5 + 4];
-    }
     KwTables* t = nullptr;
-    return get_tables(c, &t);
+    return get_tables(parse_coeffs(coeffs_host), &t);
 }
 
-extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, int64_t n_samples,
-                                    int64_t row_stride, int64_t samp_stride,
-                                    const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,
-                                    double* seg_sumsq, void* workspace, size_t workspace_bytes, void* stream) {
+// KW_RESUME: the workspace already holds every chunk's zero-state end state (dam_gain_mix_kweight left them there
+// while it wrote x), so pass A -- one of the two reads of x -- is skipped.  KW_STATES_ONLY: pass A alone (what
+// dam_gain_mix_kweight runs after a mixdown whose layout its fused kernel does not take).
+enum KwMode { KW_FULL = 0, KW_RESUME = 1, KW_STATES_ONLY = 2 };
+
+static int kweight_segments(const void* x, int dtype, int64_t n_rows, int64_t n_samples,
+                            int64_t row_stride, int64_t samp_stride,
+                            const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,
+                            double* seg_sumsq, void* workspace, size_t workspace_bytes, void* stream, KwMode mode) {
     dam_clear_error();
-    DAM_CHECK_ARG(x && coeffs_host && seg_bounds && seg_sumsq && workspace, "null pointer argument");
+    DAM_CHECK_ARG(x && coeffs_host && workspace, "null pointer argument");
+    DAM_CHECK_ARG(mode == KW_STATES_ONLY || (seg_bounds && seg_sumsq), "null pointer argument");
     DAM_CHECK_ARG(dtype == DAM_F32 || dtype == DAM_F64, "dtype must be F32 or F64");
-    DAM_CHECK_ARG(n_rows >= 1 && n_rows <= 65535 && n_samples >= 1 && n_seg >= 1, "bad sizes");
+    DAM_CHECK_ARG(n_rows >= 1 && n_rows <= 65535 && n_samples >= 1 && (n_seg >= 1 || mode == KW_STATES_ONLY), "bad sizes");
     DAM_CHECK_ARG(workspace_bytes >= dam_kweight_workspace_bytes(n_rows, n_samples),
                   "workspace too small: need %zu bytes", dam_kweight_workspace_bytes(n_rows, n_samples));
     DAM_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
-    Coeffs c;
-    for (int s = 0; s < 2; ++s) {
-        c.b0[s] = coeffs_host[s * 5 + 0]; c.b1[s] = coeffs_host[s * 5 + 1]; c.b2[s] = coeffs_host[s * 5 + 2];
-        c.a1[s] = coeffs_host[s * 5 + 3]; c.a2[s] = coeffs_host[s * 5 + 4];
-    }
+    const Coeffs c = parse_coeffs(coeffs_host);
     KwTables* t = nullptr;
     int rc = get_tables(c, &t);
     if (rc != DAM_OK) return rc;
@@ -623,7 +647,7 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
     {
         int parts;
         int64_t super;
-        scan_partition(p.n_chunks, &parts, &super);
+        dam_kw_scan_partition(p.n_chunks, &parts, &super);
         p.parts = parts; p.super = super; p.cpp = super * kScanBlock;
     }
     {
@@ -665,9 +689,12 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
     long long grid_ll = (long long)dam_sm_count() * (occ > 0 ? occ : 1);
     if (grid_ll > n_items) grid_ll = n_items;
     const unsigned grid = (unsigned)grid_ll;
-    if (dtype == DAM_F32) { kw_chunk_state_kernel<float><<<grid, kBlock, kw_smem_bytes<float>(), st>>>(p); dam_note_launch(); }
-    else { kw_chunk_state_kernel<double><<<grid, kBlock, kw_smem_bytes<double>(), st>>>(p); dam_note_launch(); }
-    DAM_CHECK_CUDA(cudaGetLastError());
+    if (mode != KW_RESUME) {
+        if (dtype == DAM_F32) { kw_chunk_state_kernel<float><<<grid, kBlock, kw_smem_bytes<float>(), st>>>(p); dam_note_launch(); }
+        else { kw_chunk_state_kernel<double><<<grid, kBlock, kw_smem_bytes<double>(), st>>>(p); dam_note_launch(); }
+        DAM_CHECK_CUDA(cudaGetLastError());
+    }
+    if (mode == KW_STATES_ONLY) return DAM_OK;
     {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(n_rows * p.parts));
@@ -691,6 +718,28 @@ extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, in
     { kw_segment_reduce_kernel<<<(unsigned)((n_rows * n_seg * 32 + 255) / 256), 256, 0, st>>>(p); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
+}
+
+extern "C" int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, int64_t n_samples,
+                                    int64_t row_stride, int64_t samp_stride,
+                                    const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,
+                                    double* seg_sumsq, void* workspace, size_t workspace_bytes, void* stream) {
+    return kweight_segments(x, dtype, n_rows, n_samples, row_stride, samp_stride, coeffs_host, seg_bounds, n_seg, seg_sumsq,
+                            workspace, workspace_bytes, stream, KW_FULL);
+}
+
+extern "C" int dam_kweight_segments_resume(const void* x, int dtype, int64_t n_rows, int64_t n_samples,
+                                           int64_t row_stride, int64_t samp_stride,
+                                           const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,
+                                           double* seg_sumsq, void* workspace, size_t workspace_bytes, void* stream) {
+    return kweight_segments(x, dtype, n_rows, n_samples, row_stride, samp_stride, coeffs_host, seg_bounds, n_seg, seg_sumsq,
+                            workspace, workspace_bytes, stream, KW_RESUME);
+}
+
+int dam_kw_chunk_states(const void* x, int dtype, int64_t n_rows, int64_t n_samples, int64_t row_stride,
+                        const double* coeffs_host, void* workspace, size_t workspace_bytes, void* stream) {
+    return kweight_segments(x, dtype, n_rows, n_samples, row_stride, 1, coeffs_host, nullptr, 0, nullptr, workspace,
+                            workspace_bytes, stream, KW_STATES_ONLY);
 }
 
 extern "C" int dam_gated_loudness(const double* seg_sumsq, int64_t n_signals, int n_channels, int64_t n_seg,

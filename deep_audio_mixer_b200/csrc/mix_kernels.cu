@@ -2,9 +2,11 @@
 // All of them stream their operands once with 128-bit accesses; grids are sized in multiples of
 // the SM count and grid-stride over the data.
 #include "dam_common.cuh"
+#include "kweight_common.cuh"
 #include <type_traits>
 
 #include <math.h>
+#include <string.h>
 
 namespace {
 
@@ -110,105 +112,304 @@ struct GainMixParams {
     double* sumsq;
 };
 
+// Per-plane constants of one (song, channel) of the mixdown.
+template <typename TS, typename TO>
+struct GainMixPlane {
+    const TS* base;
+    TO* mix;
+    TO* stems_out;                 // plane of stem 0 (stems n_channels * n apart), or null
+    const double* gains;
+    long long n, K, coef;
+    double inv_coef;
+    int n_stems;
+    bool zero_mask;
+};
+
+template <typename TS, typename TO>
+__device__ __forceinline__ GainMixPlane<TS, TO> gain_mix_plane(const GainMixParams& p, long long c, long long bt) {
+    GainMixPlane<TS, TO> q;
+    q.n = p.n_samples;
+    q.base = reinterpret_cast<const TS*>(p.stems) + bt * p.batch_stride + c * p.chan_stride;
+    q.mix = p.mix_out ? reinterpret_cast<TO*>(p.mix_out) + (bt * p.n_channels + c) * q.n : nullptr;
+    q.K = p.n_gains;
+    q.coef = p.interp_coef;
+    q.inv_coef = q.coef > 0 ? 1.0 / (double)q.coef : 0.0;
+    q.gains = p.gains + bt * p.n_stems * q.K;
+    q.stems_out = p.stems_out ? reinterpret_cast<TO*>(p.stems_out) + bt * p.n_stems * p.n_channels * q.n + c * q.n : nullptr;
+    q.n_stems = (int)p.n_stems;
+    q.zero_mask = p.zero_mask != 0;
+    return q;
+}
+
+// Samples [v * V, (v + 1) * V) of one plane: masked stems (optionally stored), their sum in stem order `o` (stored to
+// the mix), running peak and sum of squares.
+template <typename TS, typename TC, typename TO, int V>
+__device__ __forceinline__ void gain_mix_vector(const GainMixParams& p, const GainMixPlane<TS, TO>& q, long long v,
+                                                Vec<TO, V>& o, double& loc_peak, double& loc_sq) {
+    const long long K = q.K, coef = q.coef, n = q.n;
+    const int n_stems = q.n_stems;
+    const bool zero_mask = q.zero_mask;
+    const long long i0 = v * V;
+    // gain index of sample i0: k0 = min(i0 / coef, K-1), without a 64-bit integer division (double
+    // reciprocal estimate, exact to within one for i0 < 2^52, then an exact correction).  `cross` is
+    // how many of this thread's V samples still belong to gain k0 (V when no boundary is crossed).
+    int k0 = (int)K - 1;
+    int cross = V;
+    if (coef > 0) {
+        long long kk = (long long)((double)i0 * q.inv_coef);
+        if (kk * coef > i0) --kk;
+        else if ((kk + 1) * coef <= i0) ++kk;
+        if (kk < K - 1) {
+            k0 = (int)kk;
+            const long long left = (kk + 1) * coef - i0;      // samples until gain k0+1 starts
+            cross = left < V ? (int)left : V;
+        }
+    }
+    TC acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = TC(0);
+    constexpr int SU = sizeof(TS) == 4 ? 4 : 2;    // stems whose loads are in flight together
+    const TS* src = q.base + i0;
+    const double* grow = q.gains + k0;
+    TO* sout = q.stems_out ? q.stems_out + i0 : nullptr;
+    if (cross == V) {
+        // common case, no gain boundary inside the vector: one gain per stem, no per-sample index work
+        // (this loop was 535 instructions per vector with the per-sample boundary checks inlined)
+        for (int s0 = 0; s0 < n_stems; s0 += SU) {
+            Vec<TS, V> x[SU];
+            TC g[SU];
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                if (s0 + u < n_stems) {
+                    x[u] = load_vec<TS, V>(src + (long long)(s0 + u) * p.stem_stride);
+                    g[u] = zero_mask ? TC(0) : (TC)__ldg(grow + (long long)(s0 + u) * K);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                if (s0 + u < n_stems) {
+                    Vec<TO, V> y;
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        const TC prod = mul_rn((TC)x[u].v[j], g[u]);
+                        acc[j] = (s0 + u) == 0 ? prod : add_rn(acc[j], prod);
+                        y.v[j] = (TO)prod;
+                    }
+                    if (sout) store_vec<TO, V>(sout + (long long)(s0 + u) * p.n_channels * n, y);
+                }
+            }
+        }
+    } else {
+        // a gain boundary falls inside this vector (once per interp_coef samples)
+        for (int s = 0; s < n_stems; ++s) {
+            const Vec<TS, V> x = load_vec<TS, V>(src + (long long)s * p.stem_stride);
+            const double g0 = __ldg(grow + (long long)s * K);
+            Vec<TO, V> y;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                double gd = g0;
+                if (j >= cross) {
+                    long long k = (i0 + j) / coef;
+                    if (k > K - 1) k = K - 1;
+                    gd = __ldg(q.gains + (long long)s * K + k);
+                }
+                const TC g = zero_mask ? TC(0) : (TC)gd;
+                const TC prod = mul_rn((TC)x.v[j], g);
+                acc[j] = s == 0 ? prod : add_rn(acc[j], prod);
+                y.v[j] = (TO)prod;
+            }
+            if (sout) store_vec<TO, V>(sout + (long long)s * p.n_channels * n, y);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        o.v[j] = (TO)acc[j];
+        const double a = fabs((double)acc[j]);
+        loc_peak = fmax(loc_peak, a);
+        loc_sq += a * a;
+    }
+    if (q.mix) store_vec<TO, V>(q.mix + i0, o);
+}
+
 template <typename TS, typename TC, typename TO, int V>
 __global__ void __launch_bounds__(kBlock, 4) gain_mix_kernel(const GainMixParams p) {
     __shared__ double s_red[kBlock / 32];
     const long long c = blockIdx.y;
     const long long bt = blockIdx.z;
-    const long long n = p.n_samples;
-    const long long nvec = (n + V - 1) / V;
-    const TS* base = reinterpret_cast<const TS*>(p.stems) + bt * p.batch_stride + c * p.chan_stride;
-    TO* mix = p.mix_out ? reinterpret_cast<TO*>(p.mix_out) + (bt * p.n_channels + c) * n : nullptr;
+    const GainMixPlane<TS, TO> q = gain_mix_plane<TS, TO>(p, c, bt);
+    const long long nvec = (q.n + V - 1) / V;
     double loc_peak = 0.0, loc_sq = 0.0;
-    const long long K = p.n_gains, coef = p.interp_coef;
-    const double inv_coef = coef > 0 ? 1.0 / (double)coef : 0.0;
-    const double* gains = p.gains + bt * p.n_stems * K;
-    TO* stems_out = p.stems_out ? reinterpret_cast<TO*>(p.stems_out) + bt * p.n_stems * p.n_channels * n : nullptr;
-    const int n_stems = (int)p.n_stems;
-    const bool zero_mask = p.zero_mask != 0;
-
     for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
-        const long long i0 = v * V;
-        // gain index of sample i0: k0 = min(i0 / coef, K-1), without a 64-bit integer division (double
-        // reciprocal estimate, exact to within one for i0 < 2^52, then an exact correction).  `cross` is
-        // how many of this thread's V samples still belong to gain k0 (V when no boundary is crossed).
+        Vec<TO, V> o;
+        gain_mix_vector<TS, TC, TO, V>(p, q, v, o, loc_peak, loc_sq);
+    }
+    if (p.peak) {
+        const double m = block_max(loc_peak, s_red);
+        if (threadIdx.x == 0) atomic_max_nonneg(p.peak + bt * p.n_channels + c, m);
+    }
+    if (p.sumsq) {
+        const double m = block_sum(loc_sq, s_red);
+        if (threadIdx.x == 0) atomicAdd(p.sumsq + bt * p.n_channels + c, m);
+    }
+}
+
+// K2 + pass A of K4 in one kernel (dam_gain_mix_kweight): the mix is about to be measured by the BS.1770 meter, whose
+// first pass over it computes, for every 256-sample chunk, the end state of the two K-weighting biquads from a zero
+// start state -- a dot product of the chunk with a response table.  Here a WARP owns a chunk (lane l holds samples
+// 4 l .. 4 l + 3 and 128 + 4 l .. 128 + 4 l + 3), multiplies its 8 mix samples with its 8 x 4 table entries (shared
+// memory, lane-major: conflict-free 16-byte loads) and the 32 x 2 group sums are added in the order of
+// kweight_common.cuh by a transposed butterfly: a lane sends half of what it holds and keeps the other half, so the
+// 8 values per lane cost 20 shuffles instead of 80.  The meter then starts at its scan; the mix is read once less.
+struct KwFuseParams {
+    double G[kKwChunk * 4];
+    KwStateLayout lay;
+    long long n_chunks;
+    unsigned cpp_inv, super_inv;   // floor(2^32 / cpp), floor(2^32 / super) (0xffffffff for a divisor of 1)
+};
+
+// x / d for x < 2^32 with inv = floor(2^32 / d): the estimate is at most one short
+__device__ __forceinline__ unsigned div_u32(unsigned x, unsigned d, unsigned inv) {
+    unsigned qt = __umulhi(x, inv);
+    if (x - qt * d >= d) ++qt;
+    return qt;
+}
+
+// kw_state_ptr without its two 64-bit divisions (a chunk index fits 32 bits: they were ~100 of the instructions a warp
+// spends per chunk)
+__device__ __forceinline__ double* kw_state_ptr_fast(const KwFuseParams& kw, long long row, unsigned chunk) {
+    const unsigned cpp = (unsigned)kw.lay.cpp, super = (unsigned)kw.lay.super;
+    const unsigned part = div_u32(chunk, cpp, kw.cpp_inv);
+    const unsigned cl = chunk - part * cpp;
+    const unsigned u = div_u32(cl, super, kw.super_inv);
+    const unsigned k = cl - u * super;
+    return kw.lay.states + ((row * kw.lay.parts + part) * kw.lay.cpp + (long long)k * kKwScanBlock + u) * 4;
+}
+
+#ifndef DAM_K2KW_CTAS
+#define DAM_K2KW_CTAS 2
+#endif
+template <typename TS, typename TC, typename TO>
+__global__ void __launch_bounds__(kBlock, DAM_K2KW_CTAS) gain_mix_kweight_kernel(const GainMixParams p, const KwFuseParams kw) {
+    constexpr int V = 4;
+    __shared__ double s_red[kBlock / 32];
+    // [half][2 j + (slot >> 1)][lane] = G[(half * 32 + lane) * 4 + j][slot ^ (lane & 3)] for slot = 2 (k & 1), + 1: a lane
+    // keeps its four sums in SLOTS ordered by when they leave it in the butterfly (slot 0 = the component the lane
+    // ends up with, lane & 3; slots 1 and 3 go to lane ^ 1, slot 2 to lane ^ 2), so no step has to select
+    __shared__ double2 s_G[2][8][32];
+    const long long c = blockIdx.y;
+    const long long bt = blockIdx.z;
+    const GainMixPlane<TS, TO> q = gain_mix_plane<TS, TO>(p, c, bt);
+    const long long nvec = q.n / V;            // the launcher guarantees n % V == 0
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < 2 * 8 * 32; e += kBlock) {
+        const int l = e & 31, k = (e >> 5) & 7, h = e >> 8;
+        const int base = ((h * 32 + l) * 4 + (k >> 1)) * 4, slot = (k & 1) * 2, cs = l & 3;
+        s_G[h][k][l] = make_double2(kw.G[base + (slot ^ cs)], kw.G[base + ((slot + 1) ^ cs)]);
+    }
+    __syncthreads();
+    double loc_peak = 0.0, loc_sq = 0.0;
+    const long long row = bt * p.n_channels + c;
+    const long long K = q.K, coef = q.coef, n = q.n;
+    for (long long ch = (long long)blockIdx.x * (kBlock / 32) + warp; ch < kw.n_chunks; ch += (long long)gridDim.x * (kBlock / 32)) {
+        Vec<TO, V> o[2];
+        // warp-uniform: is the chunk whole and under ONE gain per stem?  Then the loads of both of a lane's vectors
+        // (2 x 4 stems) are in flight together and the gain index is worked out once per chunk, not per vector.
+        const long long i0c = ch * kKwChunk;
         int k0 = (int)K - 1;
-        int cross = V;
+        bool one_gain = true;
         if (coef > 0) {
-            long long kk = (long long)((double)i0 * inv_coef);
-            if (kk * coef > i0) --kk;
-            else if ((kk + 1) * coef <= i0) ++kk;
+            long long kk = (long long)((double)i0c * q.inv_coef);
+            if (kk * coef > i0c) --kk;
+            else if ((kk + 1) * coef <= i0c) ++kk;
             if (kk < K - 1) {
                 k0 = (int)kk;
-                const long long left = (kk + 1) * coef - i0;      // samples until gain k0+1 starts
-                cross = left < V ? (int)left : V;
+                one_gain = (kk + 1) * coef - i0c >= kKwChunk;
             }
         }
-        TC acc[V];
-#pragma unroll
-        for (int j = 0; j < V; ++j) acc[j] = TC(0);
-        constexpr int SU = sizeof(TS) == 4 ? 4 : 2;    // stems whose loads are in flight together
-        const TS* src = base + i0;
-        const double* grow = gains + k0;
-        TO* sout = stems_out ? stems_out + c * n + i0 : nullptr;
-        if (cross == V) {
-            // common case, no gain boundary inside the vector: one gain per stem, no per-sample index work
-            // (this loop was 535 instructions per vector with the per-sample boundary checks inlined)
-            for (int s0 = 0; s0 < n_stems; s0 += SU) {
-                Vec<TS, V> x[SU];
+        if (one_gain && i0c + kKwChunk <= n) {
+            constexpr int SU = sizeof(TS) == 4 ? 4 : 2;
+            const TS* src = q.base + i0c + lane * V;
+            const double* grow = q.gains + k0;
+            TO* sout = q.stems_out ? q.stems_out + i0c + lane * V : nullptr;
+            TC acc[2][V];
+            for (int s0 = 0; s0 < q.n_stems; s0 += SU) {
+                Vec<TS, V> x[2][SU];
                 TC g[SU];
 #pragma unroll
                 for (int u = 0; u < SU; ++u) {
-                    if (s0 + u < n_stems) {
-                        x[u] = load_vec<TS, V>(src + (long long)(s0 + u) * p.stem_stride);
-                        g[u] = zero_mask ? TC(0) : (TC)__ldg(grow + (long long)(s0 + u) * K);
+                    if (s0 + u < q.n_stems) {
+                        x[0][u] = load_vec<TS, V>(src + (long long)(s0 + u) * p.stem_stride);
+                        x[1][u] = load_vec<TS, V>(src + (long long)(s0 + u) * p.stem_stride + kKwChunk / 2);
+                        g[u] = q.zero_mask ? TC(0) : (TC)__ldg(grow + (long long)(s0 + u) * K);
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < SU; ++u) {
-                    if (s0 + u < n_stems) {
-                        Vec<TO, V> y;
+                    if (s0 + u < q.n_stems) {
 #pragma unroll
-                        for (int j = 0; j < V; ++j) {
-                            const TC prod = mul_rn((TC)x[u].v[j], g[u]);
-                            acc[j] = (s0 + u) == 0 ? prod : add_rn(acc[j], prod);
-                            y.v[j] = (TO)prod;
+                        for (int h = 0; h < 2; ++h) {
+                            Vec<TO, V> y;
+#pragma unroll
+                            for (int j = 0; j < V; ++j) {
+                                const TC prod = mul_rn((TC)x[h][u].v[j], g[u]);
+                                acc[h][j] = (s0 + u) == 0 ? prod : add_rn(acc[h][j], prod);
+                                y.v[j] = (TO)prod;
+                            }
+                            if (sout) store_vec<TO, V>(sout + (long long)(s0 + u) * p.n_channels * n + h * (kKwChunk / 2), y);
                         }
-                        if (sout) store_vec<TO, V>(sout + (long long)(s0 + u) * p.n_channels * n, y);
                     }
                 }
             }
-        } else {
-            // a gain boundary falls inside this vector (once per interp_coef samples)
-            for (int s = 0; s < n_stems; ++s) {
-                const Vec<TS, V> x = load_vec<TS, V>(src + (long long)s * p.stem_stride);
-                const double g0 = __ldg(grow + (long long)s * K);
-                Vec<TO, V> y;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
-                    double gd = g0;
-                    if (j >= cross) {
-                        long long k = (i0 + j) / coef;
-                        if (k > K - 1) k = K - 1;
-                        gd = __ldg(gains + (long long)s * K + k);
-                    }
-                    const TC g = zero_mask ? TC(0) : (TC)gd;
-                    const TC prod = mul_rn((TC)x.v[j], g);
-                    acc[j] = s == 0 ? prod : add_rn(acc[j], prod);
-                    y.v[j] = (TO)prod;
+                    o[h].v[j] = (TO)acc[h][j];
+                    const double a = fabs((double)acc[h][j]);
+                    loc_peak = fmax(loc_peak, a);
+                    loc_sq += a * a;
                 }
-                if (sout) store_vec<TO, V>(sout + (long long)s * p.n_channels * n, y);
+                if (q.mix) store_vec<TO, V>(q.mix + i0c + h * (kKwChunk / 2) + lane * V, o[h]);
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const long long v = ch * (kKwChunk / V) + h * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < V; ++j) o[h].v[j] = TO(0);
+                if (v < nvec) gain_mix_vector<TS, TC, TO, V>(p, q, v, o[h], loc_peak, loc_sq);
             }
         }
-        Vec<TO, V> o;
+        double val[8];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            o.v[j] = (TO)acc[j];
-            const double a = fabs((double)acc[j]);
-            loc_peak = fmax(loc_peak, a);
-            loc_sq += a * a;
+        for (int h = 0; h < 2; ++h) {
+            double g[16];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const double2 t = s_G[h][k][lane];
+                g[(k >> 1) * 4 + (k & 1) * 2] = t.x;
+                g[(k >> 1) * 4 + (k & 1) * 2 + 1] = t.y;
+            }
+            kw_group_sum(g, (double)o[h].v[0], (double)o[h].v[1], (double)o[h].v[2], (double)o[h].v[3], val + h * 4);
         }
-        if (mix) store_vec<TO, V>(mix + i0, o);
+        // val[0..3]: group `lane` (first half A of the chunk), val[4..7]: group 32 + lane (second half B); slot s of
+        // either holds component s ^ (lane & 3).  Transposed butterfly: a lane hands over half of what it holds.
+        const unsigned full = 0xffffffffu;
+        const double w0 = __dadd_rn(val[0], __shfl_xor_sync(full, val[1], 1));
+        const double w1 = __dadd_rn(val[2], __shfl_xor_sync(full, val[3], 1));
+        const double w2 = __dadd_rn(val[4], __shfl_xor_sync(full, val[5], 1));
+        const double w3 = __dadd_rn(val[6], __shfl_xor_sync(full, val[7], 1));
+        const double u0 = __dadd_rn(w0, __shfl_xor_sync(full, w1, 2));       // A, component lane & 3, over 4 lanes
+        const double u1 = __dadd_rn(w2, __shfl_xor_sync(full, w3, 2));       // B
+        const bool upper = (lane & 4) != 0;                                  // lanes with bit 2 set carry B from here on
+        double t = __dadd_rn(upper ? u1 : u0, __shfl_xor_sync(full, upper ? u0 : u1, 4));
+        t = __dadd_rn(t, __shfl_xor_sync(full, t, 8));
+        t = __dadd_rn(t, __shfl_xor_sync(full, t, 16));
+        t = __dadd_rn(t, __shfl_xor_sync(full, t, 4));                       // A + B
+        if (lane < 4) {
+            // the last chunk of a row (possibly partial) has no successor: its end state is never used
+            kw_state_ptr_fast(kw, row, (unsigned)ch)[lane] = ch == kw.n_chunks - 1 ? 0.0 : t;
+        }
     }
     if (p.peak) {
         const double m = block_max(loc_peak, s_red);
@@ -238,6 +439,22 @@ int launch_gain_mix(const GainMixParams& p, bool vec_ok, cudaStream_t st) {
         dim3 grid(grid_for(p.n_samples, 8), (unsigned)p.n_channels, (unsigned)p.n_batch);
         { gain_mix_kernel<TS, TC, TO, 1><<<grid, kBlock, 0, st>>>(p); dam_note_launch(); }
     }
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
+
+template <typename TS, typename TC, typename TO>
+int launch_gain_mix_kweight(const GainMixParams& p, const KwFuseParams& kw, cudaStream_t st) {
+    const long long planes = p.n_channels * p.n_batch;
+    // DAM_K2KW_CTAS resident CTAs per SM (two: with both of a lane's vectors in flight and the butterfly the kernel
+    // needs ~100 registers; at 80 or 64 it spills and is 35-60 % slower, measured), about two waves of them over all
+    // planes; a warp takes whole chunks
+    long long per_plane = (2LL * DAM_K2KW_CTAS * dam_sm_count()) / (planes > 0 ? planes : 1);
+    const long long max_blocks = (kw.n_chunks + kBlock / 32 - 1) / (kBlock / 32);
+    if (per_plane < 1) per_plane = 1;
+    if (per_plane > max_blocks) per_plane = max_blocks;
+    dim3 grid((unsigned)per_plane, (unsigned)p.n_channels, (unsigned)p.n_batch);
+    { gain_mix_kweight_kernel<TS, TC, TO><<<grid, kBlock, 0, st>>>(p, kw); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }
@@ -553,12 +770,14 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 }  // namespace
 
 // ==========================================================================================
-extern "C" int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_batch, int64_t batch_stride,
-                            int64_t n_stems, int64_t n_channels,
-                            int64_t n_samples, int64_t stem_stride, int64_t chan_stride,
-                            const double* gains, int64_t n_gains, int64_t interp_coef, int hold_single,
-                            int compute_dtype, void* mix_out, void* stems_out, int out_dtype,
-                            double* peak, double* sumsq, void* stream) {
+// Shared body of dam_gain_mix and dam_gain_mix_kweight (kw_coeffs_host == nullptr: plain mixdown).
+static int gain_mix_entry(const void* stems, int stems_dtype, int64_t n_batch, int64_t batch_stride,
+                          int64_t n_stems, int64_t n_channels,
+                          int64_t n_samples, int64_t stem_stride, int64_t chan_stride,
+                          const double* gains, int64_t n_gains, int64_t interp_coef, int hold_single,
+                          int compute_dtype, void* mix_out, void* stems_out, int out_dtype,
+                          double* peak, double* sumsq,
+                          const double* kw_coeffs_host, void* kw_workspace, size_t kw_workspace_bytes, void* stream) {
     dam_clear_error();
     DAM_CHECK_ARG(stems && gains, "null pointer argument");
     DAM_CHECK_ARG(mix_out || stems_out || peak || sumsq, "no output requested");
@@ -568,6 +787,14 @@ extern "C" int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_batch,
     DAM_CHECK_ARG(!(stems_dtype == DAM_F64 && compute_dtype == DAM_F32), "F64 stems need F64 compute");
     DAM_CHECK_ARG(n_stems >= 1 && n_channels >= 1 && n_channels <= 65535 && n_samples >= 0, "bad sizes");
     DAM_CHECK_ARG(n_batch >= 0 && n_batch <= 65535, "n_batch must be in [0, 65535]");
+    const bool want_kw = kw_coeffs_host != nullptr;
+    if (want_kw) {
+        DAM_CHECK_ARG(mix_out && kw_workspace, "the K-weighting states need mix_out and a workspace");
+        DAM_CHECK_ARG(n_batch >= 1 && n_samples >= 1 && n_batch * n_channels <= 65535, "bad sizes for the K-weighting states");
+        DAM_CHECK_ARG(kw_workspace_bytes >= dam_kweight_workspace_bytes(n_batch * n_channels, n_samples),
+                      "workspace too small: need %zu bytes", dam_kweight_workspace_bytes(n_batch * n_channels, n_samples));
+        DAM_CHECK_ARG((reinterpret_cast<uintptr_t>(kw_workspace) & 15u) == 0, "workspace must be 16-byte aligned");
+    }
     if (n_batch == 0) return DAM_OK;
     DAM_CHECK_ARG(n_gains >= 1, "need at least one gain per stem");
     DAM_CHECK_ARG(n_gains <= n_samples || n_samples == 0, "Target mask should be longer than the initial one");
@@ -587,15 +814,74 @@ extern "C" int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_batch,
                   (!stems_out || (reinterpret_cast<uintptr_t>(stems_out) % 32) == 0);
     if (stems_dtype == DAM_F64) vec_ok = vec_ok && (reinterpret_cast<uintptr_t>(stems) % 32 == 0);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (want_kw && vec_ok) {
+        KwFuseParams kw;
+        const double* G = nullptr;
+        const int rc = dam_kw_response_table(kw_coeffs_host, &G);
+        if (rc != DAM_OK) return rc;
+        memcpy(kw.G, G, sizeof(kw.G));
+        kw.n_chunks = (n_samples + kKwChunk - 1) / kKwChunk;
+        int parts;
+        int64_t super;
+        dam_kw_scan_partition(kw.n_chunks, &parts, &super);
+        kw.lay.states = reinterpret_cast<double*>(kw_workspace);
+        kw.lay.parts = parts; kw.lay.super = super; kw.lay.cpp = super * kKwScanBlock;
+        DAM_CHECK_ARG(kw.n_chunks < (1LL << 31), "n_samples too large");
+        kw.cpp_inv = kw.lay.cpp == 1 ? 0xffffffffu : (unsigned)((1ULL << 32) / (unsigned long long)kw.lay.cpp);
+        kw.super_inv = kw.lay.super == 1 ? 0xffffffffu : (unsigned)((1ULL << 32) / (unsigned long long)kw.lay.super);
+        if (stems_dtype == DAM_F32) {
+            if (compute_dtype == DAM_F64)
+                return out_dtype == DAM_F64 ? launch_gain_mix_kweight<float, double, double>(p, kw, st)
+                                            : launch_gain_mix_kweight<float, double, float>(p, kw, st);
+            return out_dtype == DAM_F64 ? launch_gain_mix_kweight<float, float, double>(p, kw, st)
+                                        : launch_gain_mix_kweight<float, float, float>(p, kw, st);
+        }
+        return out_dtype == DAM_F64 ? launch_gain_mix_kweight<double, double, double>(p, kw, st)
+                                    : launch_gain_mix_kweight<double, double, float>(p, kw, st);
+    }
+    int rc;
     if (stems_dtype == DAM_F32) {
         if (compute_dtype == DAM_F64)
-            return out_dtype == DAM_F64 ? launch_gain_mix<float, double, double>(p, vec_ok, st)
-                                        : launch_gain_mix<float, double, float>(p, vec_ok, st);
-        return out_dtype == DAM_F64 ? launch_gain_mix<float, float, double>(p, vec_ok, st)
-                                    : launch_gain_mix<float, float, float>(p, vec_ok, st);
+            rc = out_dtype == DAM_F64 ? launch_gain_mix<float, double, double>(p, vec_ok, st)
+                                      : launch_gain_mix<float, double, float>(p, vec_ok, st);
+        else
+            rc = out_dtype == DAM_F64 ? launch_gain_mix<float, float, double>(p, vec_ok, st)
+                                      : launch_gain_mix<float, float, float>(p, vec_ok, st);
+    } else {
+        rc = out_dtype == DAM_F64 ? launch_gain_mix<double, double, double>(p, vec_ok, st)
+                                  : launch_gain_mix<double, double, float>(p, vec_ok, st);
     }
-    return out_dtype == DAM_F64 ? launch_gain_mix<double, double, double>(p, vec_ok, st)
-                                : launch_gain_mix<double, double, float>(p, vec_ok, st);
+    if (rc != DAM_OK || !want_kw) return rc;
+    // a layout the fused kernel does not take (unaligned or n % 4 != 0): the states come from the stand-alone pass
+    // over the mix that was just written -- the same bits, one more read
+    return dam_kw_chunk_states(mix_out, out_dtype, n_batch * n_channels, n_samples, n_samples, kw_coeffs_host,
+                               kw_workspace, kw_workspace_bytes, stream);
+}
+
+extern "C" int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_batch, int64_t batch_stride,
+                            int64_t n_stems, int64_t n_channels,
+                            int64_t n_samples, int64_t stem_stride, int64_t chan_stride,
+                            const double* gains, int64_t n_gains, int64_t interp_coef, int hold_single,
+                            int compute_dtype, void* mix_out, void* stems_out, int out_dtype,
+                            double* peak, double* sumsq, void* stream) {
+    return gain_mix_entry(stems, stems_dtype, n_batch, batch_stride, n_stems, n_channels, n_samples, stem_stride, chan_stride,
+                          gains, n_gains, interp_coef, hold_single, compute_dtype, mix_out, stems_out, out_dtype, peak, sumsq,
+                          nullptr, nullptr, 0, stream);
+}
+
+extern "C" int dam_gain_mix_kweight(const void* stems, int stems_dtype, int64_t n_batch, int64_t batch_stride,
+                                    int64_t n_stems, int64_t n_channels,
+                                    int64_t n_samples, int64_t stem_stride, int64_t chan_stride,
+                                    const double* gains, int64_t n_gains, int64_t interp_coef, int hold_single,
+                                    int compute_dtype, void* mix_out, void* stems_out, int out_dtype,
+                                    double* peak, double* sumsq,
+                                    const double* kw_coeffs_host, void* kw_workspace, size_t kw_workspace_bytes,
+                                    void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(kw_coeffs_host != nullptr, "null pointer argument");
+    return gain_mix_entry(stems, stems_dtype, n_batch, batch_stride, n_stems, n_channels, n_samples, stem_stride, chan_stride,
+                          gains, n_gains, interp_coef, hold_single, compute_dtype, mix_out, stems_out, out_dtype, peak, sumsq,
+                          kw_coeffs_host, kw_workspace, kw_workspace_bytes, stream);
 }
 
 extern "C" int dam_bus_sum(const void* stems, int dtype, int64_t n_batch, int64_t batch_stride,

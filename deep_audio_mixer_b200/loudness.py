@@ -120,37 +120,54 @@ class Meter:
             self._ws_cache[key] = hit
         return hit
 
-    def _segment_sums(self, rows: torch.Tensor):
+    def workspace_for(self, R, n, dev):
+        """(segment sums, filter-state workspace, its size in bytes) of one call over R rows of n samples: cached per
+        shape and stream, or fresh from the graph's private pool inside a CUDA-graph capture."""
+        if n < self.block_size * self.rate:
+            raise ValueError('Audio must have length greater than the block size.')
+        n_seg = self._geometry(n, dev)[1]
+        if torch.cuda.is_current_stream_capturing():
+            ws_bytes = _lib.lib().dam_kweight_workspace_bytes(R, n)
+            return (torch.empty((R, n_seg), dtype=torch.float64, device=dev),
+                    torch.empty(ws_bytes // 8 + 2, dtype=torch.float64, device=dev), ws_bytes)
+        return self._workspace(R, n, n_seg, dev)
+
+    def _segment_sums(self, rows: torch.Tensor, kw_workspace=None):
+        """kw_workspace: what mixing.gain_mix(..., meter=self) returned -- the chunk states of ``rows`` are already
+        in it, so the call resumes at the scan (dam_kweight_segments_resume) and reads ``rows`` once."""
         R, n = rows.shape
         dev = rows.device
         bounds, n_seg, first, last, num_blocks = self._geometry(n, dev)[:5]
         lib = _lib.lib()
-        if torch.cuda.is_current_stream_capturing():
-            # inside a CUDA-graph capture the scratch must belong to the graph's private pool
-            ws_bytes = lib.dam_kweight_workspace_bytes(R, n)
-            seg = torch.empty((R, n_seg), dtype=torch.float64, device=dev)
-            ws = torch.empty(ws_bytes // 8 + 2, dtype=torch.float64, device=dev)
+        resume = kw_workspace is not None
+        if resume:
+            seg, ws, ws_bytes, ws_rows, ws_n, ws_ptr = kw_workspace
+            if (ws_rows, ws_n, ws_ptr) != (R, n, rows.data_ptr()) or rows.stride(1) != 1 or rows.stride(0) != n:
+                raise ValueError('kw_workspace belongs to another mix (gain_mix(..., meter=) returns the pair)')
         else:
-            seg, ws, ws_bytes = self._workspace(R, n, n_seg, dev)
+            seg, ws, ws_bytes = self.workspace_for(R, n, dev)
         seg.zero_()
         coeffs = (ctypes.c_double * 10)(*self._coeffs)
+        entry = lib.dam_kweight_segments_resume if resume else lib.dam_kweight_segments
         with torch.cuda.device(dev):
-            rc = lib.dam_kweight_segments(_lib.ptr(rows), _lib.dtype_code(rows.dtype), R, n,
-                                          rows.stride(0), rows.stride(1), coeffs, _lib.ptr(bounds), n_seg,
-                                          _lib.ptr(seg), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+            rc = entry(_lib.ptr(rows), _lib.dtype_code(rows.dtype), R, n,
+                       rows.stride(0), rows.stride(1), coeffs, _lib.ptr(bounds), n_seg,
+                       _lib.ptr(seg), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
         _lib.check(rc, 'dam_kweight_segments')
         return seg, first, last
 
-    def integrated_loudness_device(self, signals: torch.Tensor) -> torch.Tensor:
+    def integrated_loudness_device(self, signals: torch.Tensor, kw_workspace=None) -> torch.Tensor:
         """signals [R, C, N] CUDA -> float64 CUDA tensor [R] of LUFS values; K-weighting, block sums
-        and gating all run on the device with no host synchronisation."""
+        and gating all run on the device with no host synchronisation.  ``kw_workspace``: see _segment_sums."""
         R, C, n = signals.shape
         if n < self.block_size * self.rate:
             raise ValueError('Audio must have length greater than the block size.')
         rows = signals.reshape(R * C, n)
         if rows.stride(1) != 1:
+            if kw_workspace is not None:
+                raise ValueError('kw_workspace needs the contiguous mix gain_mix returned')
             rows = rows.contiguous()
-        seg, _, _ = self._segment_sums(rows)
+        seg, _, _ = self._segment_sums(rows, kw_workspace)
         geo = self._geometry(n, rows.device)
         out = torch.empty(R, dtype=torch.float64, device=rows.device)
         with torch.cuda.device(rows.device):

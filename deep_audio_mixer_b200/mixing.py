@@ -14,7 +14,7 @@ def _check_cuda(t, name):
 
 def gain_mix(stems: torch.Tensor, gains, interp_coef: int = None, hold_single: bool = False,
              compute_dtype: torch.dtype = torch.float64, out_dtype: torch.dtype = None,
-             want_mix: bool = True, want_stems: bool = False, want_stats: bool = False):
+             want_mix: bool = True, want_stems: bool = False, want_stats: bool = False, meter=None):
     """Zero-order-hold gain masks x stems, summed over stems (kernel K2).
 
     stems [S, C, N] (or a batch [B, S, C, N]) CUDA float32/float64 planar audio; gains [S, K]
@@ -24,6 +24,11 @@ def gain_mix(stems: torch.Tensor, gains, interp_coef: int = None, hold_single: b
     Returns dict(mix=[C, N], stems=[S, C, N], peak=[C], sumsq=[C]) for the requested outputs.  Runs on torch's
     current stream.  Device gains are used in place (no copy, no synchronisation); host gains go through a small
     ring of pinned staging buffers and an asynchronous copy.
+
+    ``meter`` (a loudness.Meter): the mix is about to be measured -- the kernel also leaves the meter's first pass
+    over the mix (K-weighting chunk states) in a workspace, returned as ``kw_workspace``; hand it to
+    ``meter.integrated_loudness_device(mix, kw_workspace=...)``, which then reads the mix once instead of twice
+    (same bits as measuring the mix from scratch).
     """
     _check_cuda(stems, 'stems')
     batched = stems.dim() == 4
@@ -50,17 +55,28 @@ def gain_mix(stems: torch.Tensor, gains, interp_coef: int = None, hold_single: b
     st_out = torch.empty((B, S, C, N), dtype=out_dtype, device=dev) if want_stems else None
     peak = torch.zeros((B, C), dtype=torch.float64, device=dev) if want_stats else None
     sumsq = torch.zeros((B, C), dtype=torch.float64, device=dev) if want_stats else None
+    common = (_lib.ptr(stems), _lib.dtype_code(stems.dtype), B, stems.stride(0) if B > 1 else 0,
+              S, C, N, stems.stride(1), stems.stride(2),
+              _lib.ptr(g), K, int(interp_coef), int(bool(hold_single)), _lib.dtype_code(compute_dtype),
+              _lib.ptr(mix), _lib.ptr(st_out), _lib.dtype_code(out_dtype),
+              _lib.ptr(peak), _lib.ptr(sumsq))
+    kw_workspace = None
     with torch.cuda.device(dev):
-        rc = _lib.lib().dam_gain_mix(
-            _lib.ptr(stems), _lib.dtype_code(stems.dtype), B, stems.stride(0) if B > 1 else 0,
-            S, C, N, stems.stride(1), stems.stride(2),
-            _lib.ptr(g), K, int(interp_coef), int(bool(hold_single)), _lib.dtype_code(compute_dtype),
-            _lib.ptr(mix), _lib.ptr(st_out), _lib.dtype_code(out_dtype),
-            _lib.ptr(peak), _lib.ptr(sumsq), _lib.stream_ptr())
+        if meter is not None:
+            if mix is None:
+                raise ValueError('gain_mix: meter needs want_mix=True')
+            kw_workspace = meter.workspace_for(B * C, N, dev)
+            coeffs = (ctypes.c_double * 10)(*meter._coeffs)
+            rc = _lib.lib().dam_gain_mix_kweight(*common, coeffs, _lib.ptr(kw_workspace[1]), kw_workspace[2],
+                                                 _lib.stream_ptr())
+        else:
+            rc = _lib.lib().dam_gain_mix(*common, _lib.stream_ptr())
     _lib.check(rc, 'dam_gain_mix')
     if not batched:
         mix, st_out, peak, sumsq = [None if t is None else t[0] for t in (mix, st_out, peak, sumsq)]
-    return dict(mix=mix, stems=st_out, peak=peak, sumsq=sumsq)
+    if kw_workspace is not None:
+        kw_workspace = tuple(kw_workspace) + (B * C, N, mix.data_ptr())          # what the states belong to
+    return dict(mix=mix, stems=st_out, peak=peak, sumsq=sumsq, kw_workspace=kw_workspace)
 
 
 def stem_sum(stems: torch.Tensor, out_dtype=None) -> torch.Tensor:

@@ -96,15 +96,18 @@ class SegmentBatchPipeline:
         reference (data/dataset_utils.py:46-50), widened to float64 for the mask."""
         return torch.pow(10.0, 0.5 * m.float()).double().reshape(B, nc, 4).permute(0, 2, 1).contiguous()
 
-    def stage_mix(self, buses: torch.Tensor, gains: torch.Tensor):
-        """zero-order-hold masks, per-bus products, stem sum, peak and sum of squares (kernel K2)."""
+    def stage_mix(self, buses: torch.Tensor, gains: torch.Tensor, for_meter: bool = True):
+        """zero-order-hold masks, per-bus products, stem sum, peak and sum of squares (kernel K2).  With
+        ``for_meter`` the kernel also leaves the meter's first pass over the mix (the K-weighting chunk states) in
+        ``kw_workspace`` for ``stage_loudness``."""
         N = buses.shape[-1]
         return mixing.gain_mix(buses, gains, interp_coef=int(N / gains.shape[-1]), compute_dtype=torch.float64,
-                               want_mix=True, want_stats=True)
+                               want_mix=True, want_stats=True, meter=self.meter if for_meter else None)
 
-    def stage_loudness(self, mix: torch.Tensor) -> torch.Tensor:
-        """BS.1770 integrated loudness of every mix, on the device (kernel K4 + gating)."""
-        return self.meter.integrated_loudness_device(mix)
+    def stage_loudness(self, mix: torch.Tensor, kw_workspace=None) -> torch.Tensor:
+        """BS.1770 integrated loudness of every mix, on the device (kernel K4 + gating); with the ``kw_workspace``
+        of ``stage_mix`` it reads the mix once."""
+        return self.meter.integrated_loudness_device(mix, kw_workspace)
 
     def stage_normalise(self, mix: torch.Tensor, lufs: torch.Tensor) -> torch.Tensor:
         """x * 10**((target - L)/20) (kernel K5; the factors never leave the device)."""
@@ -131,7 +134,7 @@ class SegmentBatchPipeline:
         self._ev('gain0')
         res = self.stage_mix(buses, gains)
         self._ev('mix1')
-        lufs = self.stage_loudness(res['mix'])                                      # [B] on the device
+        lufs = self.stage_loudness(res['mix'], res['kw_workspace'])                 # [B] on the device
         self._ev('loud1')
         norm = self.stage_normalise(res['mix'], lufs)
         self._ev('scale1')
@@ -227,8 +230,8 @@ class SongBatchMixdown:
         the target, lufs [B] before normalisation, peak, sumsq)."""
         B, S, C, N = stems.shape
         feats = self.features(stems, feats_out) if want_features else None
-        res = mixing.gain_mix(stems, gains, compute_dtype=torch.float64, want_mix=True, want_stats=True)
-        lufs = self.meter.integrated_loudness_device(res['mix'])
+        res = mixing.gain_mix(stems, gains, compute_dtype=torch.float64, want_mix=True, want_stats=True, meter=self.meter)
+        lufs = self.meter.integrated_loudness_device(res['mix'], res['kw_workspace'])
         factor = torch.pow(10.0, (self.target - lufs) / 20.0)
         norm = mixing.scale_rows(res['mix'].reshape(B, C * N), factor).reshape(B, C, N)
         return dict(features=feats, mix=norm, lufs=lufs, peak=res['peak'], sumsq=res['sumsq'])

@@ -138,6 +138,29 @@ int dam_gain_mix(const void* stems, int stems_dtype, int64_t n_batch, int64_t ba
                  double* peak, double* sumsq, void* stream);
 
 /*
+ * K2 followed by the meter (evaluation.py:59-64: the stem sum is measured with pyloudnorm right after it is
+ * formed): dam_gain_mix that ALSO leaves, in the workspace of the K4 call that follows, the zero-state end state of
+ * the K-weighting filters over every 256-sample chunk of mix_out -- K4's first pass over the signal, computed here
+ * while the mix is still in registers.  Rows of the later K4 call = the [n_batch * n_channels] rows of mix_out, in
+ * that order.  Follow it with dam_kweight_segments_resume on mix_out and the same workspace; the segment sums are
+ * bit-identical to dam_gain_mix + dam_kweight_segments.
+ *   mix_out        required.
+ *   kw_coeffs_host HOST double[10] as for dam_kweight_segments.
+ *   kw_workspace   DEVICE scratch of dam_kweight_workspace_bytes(n_batch * n_channels, n_samples) bytes,
+ *                  16-byte aligned.
+ * Layouts the fused kernel does not take (n_samples % 4 != 0, unaligned planes) run the plain mixdown and K4's
+ * own first pass -- same results, one more read of the mix.
+ */
+int dam_gain_mix_kweight(const void* stems, int stems_dtype, int64_t n_batch, int64_t batch_stride,
+                         int64_t n_stems, int64_t n_channels,
+                         int64_t n_samples, int64_t stem_stride, int64_t chan_stride,
+                         const double* gains, int64_t n_gains, int64_t interp_coef, int hold_single,
+                         int compute_dtype, void* mix_out, void* stems_out, int out_dtype,
+                         double* peak, double* sumsq,
+                         const double* kw_coeffs_host, void* kw_workspace, size_t kw_workspace_bytes,
+                         void* stream);
+
+/*
  * N2: S raw stems -> n_bus bus sums (summed_track += track in stem order, in the audio dtype).
  * Replaces  sum_stems  data/medleydb_data_surgery.ipynb:305-332.
  *   stems: n_batch songs of [n_stems, n_elems] (stems stem_stride apart, songs batch_stride apart),
@@ -223,6 +246,12 @@ int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, int64_t n_sam
                          int64_t row_stride, int64_t samp_stride,
                          const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,
                          double* seg_sumsq, void* workspace, size_t workspace_bytes, void* stream);
+/* Same, for a signal whose chunk end states dam_gain_mix_kweight already left in `workspace` (x = its mix_out,
+ * unit sample stride, row_stride = n_samples): starts at the scan, reads x once instead of twice. */
+int dam_kweight_segments_resume(const void* x, int dtype, int64_t n_rows, int64_t n_samples,
+                                int64_t row_stride, int64_t samp_stride,
+                                const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,
+                                double* seg_sumsq, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * K-weighting + mean square of every 400 ms gating block in ONE call: z_out[r, j] of

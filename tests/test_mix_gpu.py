@@ -185,3 +185,40 @@ def test_scale_scalar_entry_point(cuda_device):
         assert got.dtype == torch.float64 and torch.equal(got, x.double() * -2.5)
     y = mixing.normalize_loudness(torch.ones(2, 1000, device='cuda', dtype=torch.float64), -23.0, -20.0)
     assert torch.allclose(y, torch.full_like(y, 10 ** (3 / 20)), rtol=0, atol=1e-15)
+
+
+@pytest.mark.parametrize('B,S,C,N,K,st_dtype,out_dtype', [
+    (3, 4, 2, 100000, 5, torch.float32, torch.float64),      # last chunk partial (100000 = 390 * 256 + 160)
+    (2, 4, 2, 65536, 7, torch.float32, torch.float64),       # whole chunks only
+    (2, 3, 1, 88201, 3, torch.float32, torch.float64),       # n % 4 != 0: plain mixdown + the meter's own first pass
+    (2, 4, 2, 88200, 4, torch.float32, torch.float32),       # float32 mix: the states follow the STORED values
+    (1, 2, 2, 44100, 1, torch.float64, torch.float64),       # float64 stems, one held gain
+    (1, 2, 2, 2400000, 9, torch.float32, torch.float64),     # 9 375 chunks per row: scanned by a cluster of two CTAs
+    (64, 4, 2, 441000, 5, torch.float32, torch.float64),     # the bench batch
+])
+def test_gain_mix_with_meter_states_is_bit_identical_to_mixing_then_measuring(cuda_device, B, S, C, N, K, st_dtype, out_dtype):
+    """dam_gain_mix_kweight + dam_kweight_segments_resume (the mix read once by the meter) against dam_gain_mix +
+    dam_kweight_segments (read twice): same mix, same segment sums, same loudness, to the bit."""
+    from deep_audio_mixer_b200.loudness import Meter
+    gen = torch.Generator(device='cuda').manual_seed(B * 7 + N)
+    stems = (torch.rand((B, S, C, N), generator=gen, device='cuda', dtype=torch.float32) - 0.5).to(st_dtype)
+    stems[:, :, :, N // 3:N // 3 + 30000] *= 1e-5                            # a stretch the gate drops
+    gains = torch.rand((B, S, K), generator=gen, device='cuda', dtype=torch.float64) + 0.5
+    meter = Meter(44100)
+    hold = K == 1
+    plain = mixing.gain_mix(stems, gains, hold_single=hold, out_dtype=out_dtype, want_stats=True)
+    seg_plain = meter._segment_sums(plain['mix'].reshape(B * C, N))[0].clone()
+    lufs_plain = meter.integrated_loudness_device(plain['mix']).clone()
+    fused = mixing.gain_mix(stems, gains, hold_single=hold, out_dtype=out_dtype, want_stats=True, meter=meter)
+    assert plain['kw_workspace'] is None and fused['kw_workspace'] is not None
+    assert torch.equal(fused['mix'], plain['mix'])
+    assert torch.equal(fused['peak'], plain['peak'])
+    assert torch.allclose(fused['sumsq'], plain['sumsq'], rtol=1e-12, atol=0)
+    seg_fused = meter._segment_sums(fused['mix'].reshape(B * C, N), fused['kw_workspace'])[0].clone()
+    assert torch.equal(seg_fused, seg_plain)
+    fused = mixing.gain_mix(stems, gains, hold_single=hold, out_dtype=out_dtype, meter=meter)
+    lufs_fused = meter.integrated_loudness_device(fused['mix'], fused['kw_workspace'])
+    assert torch.equal(lufs_fused, lufs_plain)
+    assert torch.isfinite(lufs_plain).all()
+    with pytest.raises(ValueError):
+        meter.integrated_loudness_device(fused['mix'][:, :, :N - 4], fused['kw_workspace'])
