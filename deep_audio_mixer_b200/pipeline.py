@@ -30,6 +30,7 @@ class SegmentBatchPipeline:
         self.meter = Meter(sr)
         self.timings = None          # optional dict of CUDA event pairs per stage
         self.mono_features = True    # K1 reads the bus-sum kernel's mono down-mix instead of averaging channels
+        self.fuse_meter = True       # K2 also computes the meter's first pass over the mix it writes (dam_gain_mix_kweight)
         self.feature_compute_dtype = None     # None: follows the audio like the reference (float32); torch.float64
                                               # meets 1e-4 dB on every bin (the reference's training-path dtype)
 
@@ -132,7 +133,7 @@ class SegmentBatchPipeline:
             m = torch.cat([v.reshape(-1, 1) for v in ms], dim=1)
         gains = self.stage_gains(m, B, nc)
         self._ev('gain0')
-        res = self.stage_mix(buses, gains)
+        res = self.stage_mix(buses, gains, for_meter=self.fuse_meter)
         self._ev('mix1')
         lufs = self.stage_loudness(res['mix'], res['kw_workspace'])                 # [B] on the device
         self._ev('loud1')

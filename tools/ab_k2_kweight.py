@@ -57,6 +57,39 @@ def main():
     t_both, l1 = timed(fused)
     res['fused'] = {'gain_mix_ms': t_mix, 'loudness_ms': t_loud, 'both_ms': t_both}
     res['identical_lufs'] = bool(torch.equal(l0, l1))
+    # the whole bench step, both ways, interleaved
+    raw = torch.rand((B, 8, 2, n), device='cuda') - 0.5
+    m = torch.rand((B * 5, 4), device='cuda') - 0.5
+    feats = pipe.feature_buffer(B * 5)
+    del buses
+    graphs = {}
+    for name, flag in (('separate', False), ('fused', True)):
+        pipe.fuse_meter = flag
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            pipe.run(raw, m, feats_out=feats)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = pipe.run(raw, m, feats_out=feats)
+        graphs[name] = (g, out)
+    step = {'separate': [], 'fused': []}
+    for rnd in range(6):
+        for name in ('separate', 'fused'):
+            g = graphs[name][0]
+            for _ in range(3):
+                g.replay()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20):
+                g.replay()
+            b.record()
+            torch.cuda.synchronize()
+            step[name].append(round(a.elapsed_time(b) / 20, 4))
+    res['step_ms'] = step
+    res['step_identical_mix'] = bool(torch.equal(graphs['separate'][1]['mix'], graphs['fused'][1]['mix']))
     res['segments'] = B
     print(json.dumps(res))
 
