@@ -49,8 +49,8 @@ class LoudnessEvaluator:
         """evaluation.py:59-64: stem sum -> integrated loudness -> scale to `target` LUFS.
         Returns (normalised mix [C, N] on the device, loudness of the raw sum)."""
         stems, _ = stack_tracks(track_dict, list(track_dict.keys()))
-        track_sum = mixing.stem_sum(stems)
-        loudness = self.meter.integrated_loudness(track_sum.t())
+        track_sum, kw = mixing.stem_sum(stems, meter=self.meter)      # the sum kernel also runs the meter's first pass
+        loudness = self.meter.integrated_loudness(track_sum.t(), kw)
         return mixing.normalize_loudness(track_sum, loudness, target), loudness
 
     def _sum_and_evaluate_tracks(self, track_dict, reference_dict, song_name, identifier, write_to_disk=True):
@@ -136,6 +136,6 @@ def produce_mixture(track_dict: dict, meter: Meter = None, sr=44100, target=-20.
     -20 LUFS.  Returns the [C, N] device tensor."""
     meter = meter or Meter(sr)
     stems, _ = stack_tracks(track_dict, list(track_dict.keys()))
-    track_sum = mixing.stem_sum(stems)
-    loudness = meter.integrated_loudness(track_sum.t())
+    track_sum, kw = mixing.stem_sum(stems, meter=meter)
+    loudness = meter.integrated_loudness(track_sum.t(), kw)
     return mixing.normalize_loudness(track_sum, loudness, target)

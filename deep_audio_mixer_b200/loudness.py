@@ -70,16 +70,16 @@ class Meter:
         self._bounds_cache[key] = geo
         return geo
 
-    def block_energies(self, rows: torch.Tensor) -> np.ndarray:
+    def block_energies(self, rows: torch.Tensor, kw_workspace=None) -> np.ndarray:
         """rows [R, N] CUDA (float32/float64) -> z [R, num_blocks] float64 (host): mean square of the
-        K-weighted signal over each 400 ms gating block."""
+        K-weighted signal over each 400 ms gating block.  ``kw_workspace``: see _segment_sums."""
         if not rows.is_cuda:
             raise ValueError('block_energies needs a CUDA tensor')
         R, n = rows.shape
         if n < self.block_size * self.rate:
             raise ValueError('Audio must have length greater than the block size.')
         dev = rows.device
-        seg, first, last = self._segment_sums(rows)
+        seg, first, last = self._segment_sums(rows, kw_workspace)
         csum = np.concatenate([np.zeros((R, 1)), np.cumsum(seg.cpu().numpy(), axis=1)], axis=1)
         return (csum[:, last] - csum[:, first]) / (self.block_size * self.rate)
 
@@ -207,9 +207,10 @@ class Meter:
             rows = rows.contiguous()
         return rows
 
-    def integrated_loudness(self, data) -> float:
-        """pyln.Meter.integrated_loudness(data) for data [N, C] or [N]."""
-        return self.gated_loudness(self.block_energies(self._rows(data)))
+    def integrated_loudness(self, data, kw_workspace=None) -> float:
+        """pyln.Meter.integrated_loudness(data) for data [N, C] or [N].  ``kw_workspace``: ``data`` is the transpose of
+        a mix that mixing.gain_mix / stem_sum produced with ``meter=self`` (its first pass is already done)."""
+        return self.gated_loudness(self.block_energies(self._rows(data), kw_workspace))
 
     def integrated_loudness_batch(self, signals: torch.Tensor):
         """signals [R, C, N] CUDA -> list of R loudness values, one kernel pass for all of them."""

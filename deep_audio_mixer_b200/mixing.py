@@ -79,11 +79,12 @@ def gain_mix(stems: torch.Tensor, gains, interp_coef: int = None, hold_single: b
     return dict(mix=mix, stems=st_out, peak=peak, sumsq=sumsq, kw_workspace=kw_workspace)
 
 
-def stem_sum(stems: torch.Tensor, out_dtype=None) -> torch.Tensor:
-    """np.sum(np.array(list(d.values())), axis=0) (evaluation.py:59-60) for stems [S, C, N]."""
+def stem_sum(stems: torch.Tensor, out_dtype=None, meter=None):
+    """np.sum(np.array(list(d.values())), axis=0) (evaluation.py:59-60) for stems [S, C, N].  With ``meter`` (the sum is
+    measured next, evaluation.py:63) returns (sum, kw_workspace) for ``meter.integrated_loudness(sum.t(), kw_workspace)``."""
     ones = torch.ones(tuple(stems.shape[:-2]) + (1,), dtype=torch.float64, device=stems.device)
-    return gain_mix(stems, ones, hold_single=True, compute_dtype=stems.dtype,
-                    out_dtype=out_dtype or stems.dtype)['mix']
+    res = gain_mix(stems, ones, hold_single=True, compute_dtype=stems.dtype, out_dtype=out_dtype or stems.dtype, meter=meter)
+    return res['mix'] if meter is None else (res['mix'], res['kw_workspace'])
 
 
 def bus_sum(stems: torch.Tensor, group, n_bus: int = 4, batch_dims: int = 0,

@@ -222,3 +222,8 @@ def test_gain_mix_with_meter_states_is_bit_identical_to_mixing_then_measuring(cu
     assert torch.isfinite(lufs_plain).all()
     with pytest.raises(ValueError):
         meter.integrated_loudness_device(fused['mix'][:, :, :N - 4], fused['kw_workspace'])
+    # evaluation.py:59-63 as evaluation.sum_and_normalize runs it: stem sum in the audio dtype, host-side gating
+    song = stems[0]
+    total, kw = mixing.stem_sum(song, meter=meter)
+    assert torch.equal(total, mixing.stem_sum(song))
+    assert meter.integrated_loudness(total.t(), kw) == meter.integrated_loudness(mixing.stem_sum(song).t())
