@@ -7,6 +7,7 @@
 
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -117,10 +118,10 @@ template <typename TS, typename TO>
 struct GainMixPlane {
     const TS* base;
     TO* mix;
-    TO* stems_out;                 // plane of stem 0 (stems n_channels * n apart), or null
+    TO* stems_out;                 // plane of stem 0 (stems out_stem_stride apart), or null
     const double* gains;
     long long n, K, coef;
-    double inv_coef;
+    long long stem_stride, out_stem_stride;
     int n_stems;
     bool zero_mask;
 };
@@ -133,94 +134,127 @@ __device__ __forceinline__ GainMixPlane<TS, TO> gain_mix_plane(const GainMixPara
     q.mix = p.mix_out ? reinterpret_cast<TO*>(p.mix_out) + (bt * p.n_channels + c) * q.n : nullptr;
     q.K = p.n_gains;
     q.coef = p.interp_coef;
-    q.inv_coef = q.coef > 0 ? 1.0 / (double)q.coef : 0.0;
     q.gains = p.gains + bt * p.n_stems * q.K;
     q.stems_out = p.stems_out ? reinterpret_cast<TO*>(p.stems_out) + bt * p.n_stems * p.n_channels * q.n + c * q.n : nullptr;
+    q.stem_stride = p.stem_stride;
+    q.out_stem_stride = p.n_channels * q.n;
     q.n_stems = (int)p.n_stems;
     q.zero_mask = p.zero_mask != 0;
     return q;
 }
 
-// Samples [v * V, (v + 1) * V) of one plane: masked stems (optionally stored), their sum in stem order `o` (stored to
-// the mix), running peak and sum of squares.
-template <typename TS, typename TC, typename TO, int V>
-__device__ __forceinline__ void gain_mix_vector(const GainMixParams& p, const GainMixPlane<TS, TO>& q, long long v,
-                                                Vec<TO, V>& o, double& loc_peak, double& loc_sq) {
-    const long long K = q.K, coef = q.coef, n = q.n;
+// The run of samples that share the gain of sample i0: k0 = min(i0 / coef, K-1) and the first sample of the next
+// gain (LLONG_MAX on the last one).  A thread walks its samples in ascending order, so this (with its 64-bit
+// division) runs once per gain run, not once per vector.
+struct GainRun { int k0; long long end; };
+
+template <typename TS, typename TO>
+__device__ __forceinline__ GainRun gain_run(const GainMixPlane<TS, TO>& q, long long i0) {
+    GainRun r;
+    r.k0 = (int)q.K - 1;
+    r.end = 0x7fffffffffffffffLL;
+    if (q.coef > 0) {
+        const long long kk = i0 / q.coef;
+        if (kk < q.K - 1) { r.k0 = (int)kk; r.end = (kk + 1) * q.coef; }
+    }
+    return r;
+}
+
+// One stem of NV vectors (vgap samples apart) that lie inside one gain run: product rounded, added to the running
+// sum in stem order (numpy: `track * mask` is a rounded array, np.sum starts from the first one), optionally stored.
+template <typename TS, typename TC, typename TO, int V, int NV, bool kFirst>
+__device__ __forceinline__ void mix_stem(const Vec<TS, V> (&x)[NV], TC g, TC (&acc)[NV][V], TO* po, long long vgap) {
+#pragma unroll
+    for (int h = 0; h < NV; ++h) {
+        Vec<TO, V> y;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const TC prod = mul_rn((TC)x[h].v[j], g);
+            acc[h][j] = kFirst ? prod : add_rn(acc[h][j], prod);
+            y.v[j] = (TO)prod;
+        }
+        if (po) store_vec<TO, V>(po + h * vgap, y);
+    }
+}
+
+// All stems of NV vectors inside one gain run.  Stems are taken SU at a time (their loads are in flight together);
+// source, gain and output pointers advance by additions -- the 64-bit multiplies and the per-stem `s < n_stems`
+// predicates of the first version were most of its 343 instructions per vector (ncu: 96 IMAD, 32 LDC, 27 ISETP,
+// 20 BRA against 45 floating-point instructions).
+template <typename TS, typename TC, typename TO, int V, int NV>
+__device__ __forceinline__ void mix_stems(const GainMixPlane<TS, TO>& q, const TS* ps, const double* pg, TO* po,
+                                          long long vgap, TC (&acc)[NV][V]) {
+    constexpr int SU = sizeof(TS) == 4 ? (NV == 1 ? 4 : 4) : 2;
+    const long long ss = q.stem_stride, os = q.out_stem_stride, K = q.K;
     const int n_stems = q.n_stems;
-    const bool zero_mask = q.zero_mask;
-    const long long i0 = v * V;
-    // gain index of sample i0: k0 = min(i0 / coef, K-1), without a 64-bit integer division (double
-    // reciprocal estimate, exact to within one for i0 < 2^52, then an exact correction).  `cross` is
-    // how many of this thread's V samples still belong to gain k0 (V when no boundary is crossed).
-    int k0 = (int)K - 1;
-    int cross = V;
-    if (coef > 0) {
-        long long kk = (long long)((double)i0 * q.inv_coef);
-        if (kk * coef > i0) --kk;
-        else if ((kk + 1) * coef <= i0) ++kk;
-        if (kk < K - 1) {
-            k0 = (int)kk;
-            const long long left = (kk + 1) * coef - i0;      // samples until gain k0+1 starts
-            cross = left < V ? (int)left : V;
+    const bool zero = q.zero_mask;
+    int s = 0;
+    if (n_stems >= SU) {
+        Vec<TS, V> x[SU][NV];
+        TC g[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+#pragma unroll
+            for (int h = 0; h < NV; ++h) x[u][h] = load_vec<TS, V>(ps + u * ss + h * vgap);
+            g[u] = zero ? TC(0) : (TC)__ldg(pg + u * K);
+        }
+        mix_stem<TS, TC, TO, V, NV, true>(x[0], g[0], acc, po, vgap);
+#pragma unroll
+        for (int u = 1; u < SU; ++u) mix_stem<TS, TC, TO, V, NV, false>(x[u], g[u], acc, po ? po + u * os : nullptr, vgap);
+        s = SU; ps += SU * ss; pg += SU * K; if (po) po += SU * os;
+        for (; s + SU <= n_stems; s += SU) {
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+#pragma unroll
+                for (int h = 0; h < NV; ++h) x[u][h] = load_vec<TS, V>(ps + u * ss + h * vgap);
+                g[u] = zero ? TC(0) : (TC)__ldg(pg + u * K);
+            }
+#pragma unroll
+            for (int u = 0; u < SU; ++u) mix_stem<TS, TC, TO, V, NV, false>(x[u], g[u], acc, po ? po + u * os : nullptr, vgap);
+            ps += SU * ss; pg += SU * K; if (po) po += SU * os;
         }
     }
-    TC acc[V];
+    for (; s < n_stems; ++s) {
+        Vec<TS, V> x[NV];
 #pragma unroll
-    for (int j = 0; j < V; ++j) acc[j] = TC(0);
-    constexpr int SU = sizeof(TS) == 4 ? 4 : 2;    // stems whose loads are in flight together
+        for (int h = 0; h < NV; ++h) x[h] = load_vec<TS, V>(ps + h * vgap);
+        const TC g = zero ? TC(0) : (TC)__ldg(pg);
+        if (s == 0) mix_stem<TS, TC, TO, V, NV, true>(x, g, acc, po, vgap);
+        else mix_stem<TS, TC, TO, V, NV, false>(x, g, acc, po, vgap);
+        ps += ss; pg += K; if (po) po += os;
+    }
+}
+
+// A vector with a gain boundary inside it (once per interp_coef samples): per-sample gain look-up.
+template <typename TS, typename TC, typename TO, int V>
+__device__ __forceinline__ void mix_boundary_vector(const GainMixPlane<TS, TO>& q, long long i0, const GainRun& run, TC (&acc)[V]) {
+    const int cross = (int)(run.end - i0);                 // samples of this vector that still belong to gain k0
     const TS* src = q.base + i0;
-    const double* grow = q.gains + k0;
     TO* sout = q.stems_out ? q.stems_out + i0 : nullptr;
-    if (cross == V) {
-        // common case, no gain boundary inside the vector: one gain per stem, no per-sample index work
-        // (this loop was 535 instructions per vector with the per-sample boundary checks inlined)
-        for (int s0 = 0; s0 < n_stems; s0 += SU) {
-            Vec<TS, V> x[SU];
-            TC g[SU];
+    for (int s = 0; s < q.n_stems; ++s) {
+        const Vec<TS, V> x = load_vec<TS, V>(src + (long long)s * q.stem_stride);
+        const double g0 = __ldg(q.gains + (long long)s * q.K + run.k0);
+        Vec<TO, V> y;
 #pragma unroll
-            for (int u = 0; u < SU; ++u) {
-                if (s0 + u < n_stems) {
-                    x[u] = load_vec<TS, V>(src + (long long)(s0 + u) * p.stem_stride);
-                    g[u] = zero_mask ? TC(0) : (TC)__ldg(grow + (long long)(s0 + u) * K);
-                }
+        for (int j = 0; j < V; ++j) {
+            double gd = g0;
+            if (j >= cross) {
+                long long k = (i0 + j) / q.coef;
+                if (k > q.K - 1) k = q.K - 1;
+                gd = __ldg(q.gains + (long long)s * q.K + k);
             }
-#pragma unroll
-            for (int u = 0; u < SU; ++u) {
-                if (s0 + u < n_stems) {
-                    Vec<TO, V> y;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        const TC prod = mul_rn((TC)x[u].v[j], g[u]);
-                        acc[j] = (s0 + u) == 0 ? prod : add_rn(acc[j], prod);
-                        y.v[j] = (TO)prod;
-                    }
-                    if (sout) store_vec<TO, V>(sout + (long long)(s0 + u) * p.n_channels * n, y);
-                }
-            }
+            const TC g = q.zero_mask ? TC(0) : (TC)gd;
+            const TC prod = mul_rn((TC)x.v[j], g);
+            acc[j] = s == 0 ? prod : add_rn(acc[j], prod);
+            y.v[j] = (TO)prod;
         }
-    } else {
-        // a gain boundary falls inside this vector (once per interp_coef samples)
-        for (int s = 0; s < n_stems; ++s) {
-            const Vec<TS, V> x = load_vec<TS, V>(src + (long long)s * p.stem_stride);
-            const double g0 = __ldg(grow + (long long)s * K);
-            Vec<TO, V> y;
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-                double gd = g0;
-                if (j >= cross) {
-                    long long k = (i0 + j) / coef;
-                    if (k > K - 1) k = K - 1;
-                    gd = __ldg(q.gains + (long long)s * K + k);
-                }
-                const TC g = zero_mask ? TC(0) : (TC)gd;
-                const TC prod = mul_rn((TC)x.v[j], g);
-                acc[j] = s == 0 ? prod : add_rn(acc[j], prod);
-                y.v[j] = (TO)prod;
-            }
-            if (sout) store_vec<TO, V>(sout + (long long)s * p.n_channels * n, y);
-        }
+        if (sout) store_vec<TO, V>(sout + (long long)s * q.out_stem_stride, y);
     }
+}
+
+// the mix in its output dtype, running peak and sum of squares, optional store
+template <typename TC, typename TO, int V>
+__device__ __forceinline__ void finish_vector(const TC (&acc)[V], Vec<TO, V>& o, TO* mix_at, double& loc_peak, double& loc_sq) {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         o.v[j] = (TO)acc[j];
@@ -228,7 +262,23 @@ __device__ __forceinline__ void gain_mix_vector(const GainMixParams& p, const Ga
         loc_peak = fmax(loc_peak, a);
         loc_sq += a * a;
     }
-    if (q.mix) store_vec<TO, V>(q.mix + i0, o);
+    if (mix_at) store_vec<TO, V>(mix_at, o);
+}
+
+// Samples [v * V, (v + 1) * V) of one plane (the general entry: locates the gain run itself).
+template <typename TS, typename TC, typename TO, int V>
+__device__ __forceinline__ void gain_mix_vector(const GainMixPlane<TS, TO>& q, long long v, GainRun& run,
+                                                Vec<TO, V>& o, double& loc_peak, double& loc_sq) {
+    const long long i0 = v * V;
+    if (i0 >= run.end || run.k0 < 0) run = gain_run(q, i0);
+    TC acc[1][V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[0][j] = TC(0);
+    if (i0 + V <= run.end)
+        mix_stems<TS, TC, TO, V, 1>(q, q.base + i0, q.gains + run.k0, q.stems_out ? q.stems_out + i0 : nullptr, 0, acc);
+    else
+        mix_boundary_vector<TS, TC, TO, V>(q, i0, run, acc[0]);
+    finish_vector<TC, TO, V>(acc[0], o, q.mix ? q.mix + i0 : nullptr, loc_peak, loc_sq);
 }
 
 template <typename TS, typename TC, typename TO, int V>
@@ -239,9 +289,11 @@ __global__ void __launch_bounds__(kBlock, 4) gain_mix_kernel(const GainMixParams
     const GainMixPlane<TS, TO> q = gain_mix_plane<TS, TO>(p, c, bt);
     const long long nvec = (q.n + V - 1) / V;
     double loc_peak = 0.0, loc_sq = 0.0;
+    GainRun run;
+    run.k0 = -1; run.end = 0;
     for (long long v = (long long)blockIdx.x * kBlock + threadIdx.x; v < nvec; v += (long long)gridDim.x * kBlock) {
         Vec<TO, V> o;
-        gain_mix_vector<TS, TC, TO, V>(p, q, v, o, loc_peak, loc_sq);
+        gain_mix_vector<TS, TC, TO, V>(q, v, run, o, loc_peak, loc_sq);
     }
     if (p.peak) {
         const double m = block_max(loc_peak, s_red);
@@ -260,11 +312,13 @@ __global__ void __launch_bounds__(kBlock, 4) gain_mix_kernel(const GainMixParams
 // memory, lane-major: conflict-free 16-byte loads) and the 32 x 2 group sums are added in the order of
 // kweight_common.cuh by a transposed butterfly: a lane sends half of what it holds and keeps the other half, so the
 // 8 values per lane cost 20 shuffles instead of 80.  The meter then starts at its scan; the mix is read once less.
-struct KwFuseParams {
-    double G[kKwChunk * 4];
+struct KwFuseLite {                // what the chunk kernel needs without its meter part
     KwStateLayout lay;
     long long n_chunks;
     unsigned cpp_inv, super_inv;   // floor(2^32 / cpp), floor(2^32 / super) (0xffffffff for a divisor of 1)
+};
+struct KwFuseParams : KwFuseLite {
+    double G[kKwChunk * 4];        // response table, in the kernel parameters like K4's own
 };
 
 // x / d for x < 2^32 with inv = floor(2^32 / d): the estimate is at most one short
@@ -276,7 +330,7 @@ __device__ __forceinline__ unsigned div_u32(unsigned x, unsigned d, unsigned inv
 
 // kw_state_ptr without its two 64-bit divisions (a chunk index fits 32 bits: they were ~100 of the instructions a warp
 // spends per chunk)
-__device__ __forceinline__ double* kw_state_ptr_fast(const KwFuseParams& kw, long long row, unsigned chunk) {
+__device__ __forceinline__ double* kw_state_ptr_fast(const KwFuseLite& kw, long long row, unsigned chunk) {
     const unsigned cpp = (unsigned)kw.lay.cpp, super = (unsigned)kw.lay.super;
     const unsigned part = div_u32(chunk, cpp, kw.cpp_inv);
     const unsigned cl = chunk - part * cpp;
@@ -288,173 +342,150 @@ __device__ __forceinline__ double* kw_state_ptr_fast(const KwFuseParams& kw, lon
 #ifndef DAM_K2KW_CTAS
 #define DAM_K2KW_CTAS 2
 #endif
-template <typename TS, typename TC, typename TO>
-__global__ void __launch_bounds__(kBlock, DAM_K2KW_CTAS) gain_mix_kweight_kernel(const GainMixParams p, const KwFuseParams kw) {
+template <typename TS, typename TC, typename TO, bool kKw>
+__global__ void __launch_bounds__(kBlock, DAM_K2KW_CTAS)
+gain_mix_chunks_kernel(const GainMixParams p, const typename std::conditional<kKw, KwFuseParams, KwFuseLite>::type kw) {
     constexpr int V = 4;
-    __shared__ double s_red[kBlock / 32];
     // [half][2 j + (slot >> 1)][lane] = G[(half * 32 + lane) * 4 + j][slot ^ (lane & 3)] for slot = 2 (k & 1), + 1: a lane
     // keeps its four sums in SLOTS ordered by when they leave it in the butterfly (slot 0 = the component the lane
     // ends up with, lane & 3; slots 1 and 3 go to lane ^ 1, slot 2 to lane ^ 2), so no step has to select
-    __shared__ double2 s_G[2][8][32];
-    const long long c = blockIdx.y;
-    const long long bt = blockIdx.z;
-    const GainMixPlane<TS, TO> q = gain_mix_plane<TS, TO>(p, c, bt);
-    const long long nvec = q.n / V;            // the launcher guarantees n % V == 0
+    __shared__ double2 s_G[kKw ? 2 : 1][kKw ? 8 : 1][kKw ? 32 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int e = threadIdx.x; e < 2 * 8 * 32; e += kBlock) {
-        const int l = e & 31, k = (e >> 5) & 7, h = e >> 8;
-        const int base = ((h * 32 + l) * 4 + (k >> 1)) * 4, slot = (k & 1) * 2, cs = l & 3;
-        s_G[h][k][l] = make_double2(kw.G[base + (slot ^ cs)], kw.G[base + ((slot + 1) ^ cs)]);
+    if constexpr (kKw) {
+        for (int e = threadIdx.x; e < 2 * 8 * 32; e += kBlock) {
+            const int l = e & 31, k = (e >> 5) & 7, h = e >> 8;
+            const int base = ((h * 32 + l) * 4 + (k >> 1)) * 4, slot = (k & 1) * 2, cs = l & 3;
+            s_G[h][k][l] = make_double2(kw.G[base + (slot ^ cs)], kw.G[base + ((slot + 1) ^ cs)]);
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    // PERSISTENT grid, one contiguous range of (plane, chunk) items per WARP (planes = (song, channel) in row order):
+    // with one CTA per slice of a plane the ~5 us a CTA spends on this table, its launch and its block reduction came
+    // to 20 us per bench step and the grid had to be sized around whole waves of CTAs.  A warp's range touches one or
+    // two planes; it leaves its peak / sum of squares at every plane change (shuffle reduction + two atomics).
+    const long long n = p.n_samples;
+    const long long nvec = n / V;              // the launcher guarantees n % V == 0
+    const long long planes = p.n_batch * p.n_channels;
+    const long long total = planes * kw.n_chunks;
+    const long long wid = (long long)blockIdx.x * (kBlock / 32) + warp, nw = (long long)gridDim.x * (kBlock / 32);
+    const long long t0 = total / nw * wid + (total % nw) * wid / nw;             // = floor(total * wid / nw) without overflow
+    const long long t1 = total / nw * (wid + 1) + (total % nw) * (wid + 1) / nw;
+    long long row = t0 / kw.n_chunks;
+    long long ch = t0 - row * kw.n_chunks;
+    GainMixPlane<TS, TO> q = gain_mix_plane<TS, TO>(p, row % p.n_channels, row / p.n_channels);
     double loc_peak = 0.0, loc_sq = 0.0;
-    const long long row = bt * p.n_channels + c;
-    const long long K = q.K, coef = q.coef, n = q.n;
-    for (long long ch = (long long)blockIdx.x * (kBlock / 32) + warp; ch < kw.n_chunks; ch += (long long)gridDim.x * (kBlock / 32)) {
+    GainRun run;
+    run.k0 = -1; run.end = 0;
+    for (long long item = t0; item < t1; ++item, ++ch) {
+        if (ch == kw.n_chunks) {               // next plane
+            const double m = dam_warp_max(loc_peak), sq = dam_warp_sum(loc_sq);
+            if (lane == 0 && p.peak) atomic_max_nonneg(p.peak + row, m);
+            if (lane == 0 && p.sumsq) atomicAdd(p.sumsq + row, sq);
+            loc_peak = 0.0; loc_sq = 0.0;
+            ++row; ch = 0;
+            q = gain_mix_plane<TS, TO>(p, row % p.n_channels, row / p.n_channels);
+            run.k0 = -1; run.end = 0;
+        }
         Vec<TO, V> o[2];
         // warp-uniform: is the chunk whole and under ONE gain per stem?  Then the loads of both of a lane's vectors
-        // (2 x 4 stems) are in flight together and the gain index is worked out once per chunk, not per vector.
+        // (2 x SU stems) are in flight together.
         const long long i0c = ch * kKwChunk;
-        int k0 = (int)K - 1;
-        bool one_gain = true;
-        if (coef > 0) {
-            long long kk = (long long)((double)i0c * q.inv_coef);
-            if (kk * coef > i0c) --kk;
-            else if ((kk + 1) * coef <= i0c) ++kk;
-            if (kk < K - 1) {
-                k0 = (int)kk;
-                one_gain = (kk + 1) * coef - i0c >= kKwChunk;
-            }
-        }
-        if (one_gain && i0c + kKwChunk <= n) {
-            constexpr int SU = sizeof(TS) == 4 ? 4 : 2;
-            const TS* src = q.base + i0c + lane * V;
-            const double* grow = q.gains + k0;
-            TO* sout = q.stems_out ? q.stems_out + i0c + lane * V : nullptr;
+        if (i0c >= run.end || run.k0 < 0) run = gain_run(q, i0c);
+        if (i0c + kKwChunk <= run.end && i0c + kKwChunk <= n) {
             TC acc[2][V];
-            for (int s0 = 0; s0 < q.n_stems; s0 += SU) {
-                Vec<TS, V> x[2][SU];
-                TC g[SU];
 #pragma unroll
-                for (int u = 0; u < SU; ++u) {
-                    if (s0 + u < q.n_stems) {
-                        x[0][u] = load_vec<TS, V>(src + (long long)(s0 + u) * p.stem_stride);
-                        x[1][u] = load_vec<TS, V>(src + (long long)(s0 + u) * p.stem_stride + kKwChunk / 2);
-                        g[u] = q.zero_mask ? TC(0) : (TC)__ldg(grow + (long long)(s0 + u) * K);
-                    }
-                }
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int u = 0; u < SU; ++u) {
-                    if (s0 + u < q.n_stems) {
+                for (int j = 0; j < V; ++j) acc[h][j] = TC(0);
+            const long long at = i0c + lane * V;
+            mix_stems<TS, TC, TO, V, 2>(q, q.base + at, q.gains + run.k0, q.stems_out ? q.stems_out + at : nullptr,
+                                        kKwChunk / 2, acc);
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            Vec<TO, V> y;
-#pragma unroll
-                            for (int j = 0; j < V; ++j) {
-                                const TC prod = mul_rn((TC)x[h][u].v[j], g[u]);
-                                acc[h][j] = (s0 + u) == 0 ? prod : add_rn(acc[h][j], prod);
-                                y.v[j] = (TO)prod;
-                            }
-                            if (sout) store_vec<TO, V>(sout + (long long)(s0 + u) * p.n_channels * n + h * (kKwChunk / 2), y);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    o[h].v[j] = (TO)acc[h][j];
-                    const double a = fabs((double)acc[h][j]);
-                    loc_peak = fmax(loc_peak, a);
-                    loc_sq += a * a;
-                }
-                if (q.mix) store_vec<TO, V>(q.mix + i0c + h * (kKwChunk / 2) + lane * V, o[h]);
-            }
+            for (int h = 0; h < 2; ++h)
+                finish_vector<TC, TO, V>(acc[h], o[h], q.mix ? q.mix + at + h * (kKwChunk / 2) : nullptr, loc_peak, loc_sq);
         } else {
+            GainRun r2 = run;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const long long v = ch * (kKwChunk / V) + h * 32 + lane;
 #pragma unroll
                 for (int j = 0; j < V; ++j) o[h].v[j] = TO(0);
-                if (v < nvec) gain_mix_vector<TS, TC, TO, V>(p, q, v, o[h], loc_peak, loc_sq);
+                if (v < nvec) gain_mix_vector<TS, TC, TO, V>(q, v, r2, o[h], loc_peak, loc_sq);
             }
         }
-        double val[8];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            double g[16];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const double2 t = s_G[h][k][lane];
-                g[(k >> 1) * 4 + (k & 1) * 2] = t.x;
-                g[(k >> 1) * 4 + (k & 1) * 2 + 1] = t.y;
+        if constexpr (kKw) {
+            double val[8];
+    #pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                double g[16];
+    #pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const double2 t = s_G[h][k][lane];
+                    g[(k >> 1) * 4 + (k & 1) * 2] = t.x;
+                    g[(k >> 1) * 4 + (k & 1) * 2 + 1] = t.y;
+                }
+                kw_group_sum(g, (double)o[h].v[0], (double)o[h].v[1], (double)o[h].v[2], (double)o[h].v[3], val + h * 4);
             }
-            kw_group_sum(g, (double)o[h].v[0], (double)o[h].v[1], (double)o[h].v[2], (double)o[h].v[3], val + h * 4);
-        }
-        // val[0..3]: group `lane` (first half A of the chunk), val[4..7]: group 32 + lane (second half B); slot s of
-        // either holds component s ^ (lane & 3).  Transposed butterfly: a lane hands over half of what it holds.
-        const unsigned full = 0xffffffffu;
-        const double w0 = __dadd_rn(val[0], __shfl_xor_sync(full, val[1], 1));
-        const double w1 = __dadd_rn(val[2], __shfl_xor_sync(full, val[3], 1));
-        const double w2 = __dadd_rn(val[4], __shfl_xor_sync(full, val[5], 1));
-        const double w3 = __dadd_rn(val[6], __shfl_xor_sync(full, val[7], 1));
-        const double u0 = __dadd_rn(w0, __shfl_xor_sync(full, w1, 2));       // A, component lane & 3, over 4 lanes
-        const double u1 = __dadd_rn(w2, __shfl_xor_sync(full, w3, 2));       // B
-        const bool upper = (lane & 4) != 0;                                  // lanes with bit 2 set carry B from here on
-        double t = __dadd_rn(upper ? u1 : u0, __shfl_xor_sync(full, upper ? u0 : u1, 4));
-        t = __dadd_rn(t, __shfl_xor_sync(full, t, 8));
-        t = __dadd_rn(t, __shfl_xor_sync(full, t, 16));
-        t = __dadd_rn(t, __shfl_xor_sync(full, t, 4));                       // A + B
-        if (lane < 4) {
-            // the last chunk of a row (possibly partial) has no successor: its end state is never used
-            kw_state_ptr_fast(kw, row, (unsigned)ch)[lane] = ch == kw.n_chunks - 1 ? 0.0 : t;
+            // val[0..3]: group `lane` (first half A of the chunk), val[4..7]: group 32 + lane (second half B); slot s of
+            // either holds component s ^ (lane & 3).  Transposed butterfly: a lane hands over half of what it holds.
+            const unsigned full = 0xffffffffu;
+            const double w0 = __dadd_rn(val[0], __shfl_xor_sync(full, val[1], 1));
+            const double w1 = __dadd_rn(val[2], __shfl_xor_sync(full, val[3], 1));
+            const double w2 = __dadd_rn(val[4], __shfl_xor_sync(full, val[5], 1));
+            const double w3 = __dadd_rn(val[6], __shfl_xor_sync(full, val[7], 1));
+            const double u0 = __dadd_rn(w0, __shfl_xor_sync(full, w1, 2));       // A, component lane & 3, over 4 lanes
+            const double u1 = __dadd_rn(w2, __shfl_xor_sync(full, w3, 2));       // B
+            const bool upper = (lane & 4) != 0;                                  // lanes with bit 2 set carry B from here on
+            double t = __dadd_rn(upper ? u1 : u0, __shfl_xor_sync(full, upper ? u0 : u1, 4));
+            t = __dadd_rn(t, __shfl_xor_sync(full, t, 8));
+            t = __dadd_rn(t, __shfl_xor_sync(full, t, 16));
+            t = __dadd_rn(t, __shfl_xor_sync(full, t, 4));                       // A + B
+            if (lane < 4) {
+                // the last chunk of a row (possibly partial) has no successor: its end state is never used
+                kw_state_ptr_fast(kw, row, (unsigned)ch)[lane] = ch == kw.n_chunks - 1 ? 0.0 : t;
+            }
         }
     }
-    if (p.peak) {
-        const double m = block_max(loc_peak, s_red);
-        if (threadIdx.x == 0) atomic_max_nonneg(p.peak + bt * p.n_channels + c, m);
-    }
-    if (p.sumsq) {
-        const double m = block_sum(loc_sq, s_red);
-        if (threadIdx.x == 0) atomicAdd(p.sumsq + bt * p.n_channels + c, m);
+    if (t1 > t0) {
+        const double m = dam_warp_max(loc_peak), sq = dam_warp_sum(loc_sq);
+        if (lane == 0 && p.peak) atomic_max_nonneg(p.peak + row, m);
+        if (lane == 0 && p.sumsq) atomicAdd(p.sumsq + row, sq);
     }
 }
 
 template <typename TS, typename TC, typename TO>
+int launch_gain_mix_kweight(const GainMixParams& p, const KwFuseParams& kw, cudaStream_t st);
+
+template <typename TS, typename TC, typename TO>
 int launch_gain_mix(const GainMixParams& p, bool vec_ok, cudaStream_t st) {
-    constexpr int V = 4;
     if (vec_ok) {
-        const long long nvec = (p.n_samples + V - 1) / V;
-        const long long planes = p.n_channels * p.n_batch;
-        // about two waves of resident CTAs (4 per SM) over all planes: the per-CTA prologue (index set-up) and
-        // epilogue (block reduction + two atomics) are then amortised over tens of vectors per thread
-        long long per_plane = (2LL * 4 * dam_sm_count()) / (planes > 0 ? planes : 1);
-        const long long max_blocks = (nvec + kBlock - 1) / kBlock;
-        if (per_plane < 1) per_plane = 1;
-        if (per_plane > max_blocks) per_plane = max_blocks;
-        dim3 grid((unsigned)per_plane, (unsigned)p.n_channels, (unsigned)p.n_batch);
-        { gain_mix_kernel<TS, TC, TO, V><<<grid, kBlock, 0, st>>>(p); dam_note_launch(); }
-    } else {
-        dim3 grid(grid_for(p.n_samples, 8), (unsigned)p.n_channels, (unsigned)p.n_batch);
-        { gain_mix_kernel<TS, TC, TO, 1><<<grid, kBlock, 0, st>>>(p); dam_note_launch(); }
+        // the persistent chunk kernel without its meter part (states == nullptr): 6 % faster than one CTA per slice
+        // of a plane (no wave quantisation, no per-CTA block reduction, two vectors per lane in flight)
+        KwFuseParams kw;
+        kw.lay.states = nullptr;
+        kw.n_chunks = (p.n_samples + kKwChunk - 1) / kKwChunk;
+        return launch_gain_mix_kweight<TS, TC, TO>(p, kw, st);
     }
+    // unaligned planes or n % 4 != 0: one sample per thread
+    dim3 grid(grid_for(p.n_samples, 8), (unsigned)p.n_channels, (unsigned)p.n_batch);
+    { gain_mix_kernel<TS, TC, TO, 1><<<grid, kBlock, 0, st>>>(p); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }
 
 template <typename TS, typename TC, typename TO>
 int launch_gain_mix_kweight(const GainMixParams& p, const KwFuseParams& kw, cudaStream_t st) {
-    const long long planes = p.n_channels * p.n_batch;
-    // DAM_K2KW_CTAS resident CTAs per SM (two: with both of a lane's vectors in flight and the butterfly the kernel
-    // needs ~100 registers; at 80 or 64 it spills and is 35-60 % slower, measured), about two waves of them over all
-    // planes; a warp takes whole chunks
-    long long per_plane = (2LL * DAM_K2KW_CTAS * dam_sm_count()) / (planes > 0 ? planes : 1);
-    const long long max_blocks = (kw.n_chunks + kBlock / 32 - 1) / (kBlock / 32);
-    if (per_plane < 1) per_plane = 1;
-    if (per_plane > max_blocks) per_plane = max_blocks;
-    dim3 grid((unsigned)per_plane, (unsigned)p.n_channels, (unsigned)p.n_batch);
-    { gain_mix_kweight_kernel<TS, TC, TO><<<grid, kBlock, 0, st>>>(p, kw); dam_note_launch(); }
+    // persistent: DAM_K2KW_CTAS resident CTAs per SM (two: with both of a lane's vectors in flight and the butterfly the
+    // kernel needs ~100 registers; at 80 or 64 it spills and is 35-60 % slower, measured); a warp takes a contiguous
+    // range of whole chunks
+    const long long total = p.n_channels * p.n_batch * kw.n_chunks;
+    long long blocks = (long long)DAM_K2KW_CTAS * dam_sm_count();
+    const long long max_blocks = (total + kBlock / 32 - 1) / (kBlock / 32);
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    dim3 grid((unsigned)blocks);
+    if (kw.lay.states) { gain_mix_chunks_kernel<TS, TC, TO, true><<<grid, kBlock, 0, st>>>(p, kw); dam_note_launch(); }
+    else { gain_mix_chunks_kernel<TS, TC, TO, false><<<grid, kBlock, 0, st>>>(p, static_cast<const KwFuseLite&>(kw)); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
 }
