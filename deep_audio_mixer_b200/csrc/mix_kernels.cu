@@ -181,36 +181,42 @@ __device__ __forceinline__ void mix_stem(const Vec<TS, V> (&x)[NV], TC g, TC (&a
 // source, gain and output pointers advance by additions -- the 64-bit multiplies and the per-stem `s < n_stems`
 // predicates of the first version were most of its 343 instructions per vector (ncu: 96 IMAD, 32 LDC, 27 ISETP,
 // 20 BRA against 45 floating-point instructions).
-template <typename TS, typename TC, typename TO, int V, int NV>
-__device__ __forceinline__ void mix_stems(const GainMixPlane<TS, TO>& q, const TS* ps, const double* pg, TO* po,
-                                          long long vgap, TC (&acc)[NV][V]) {
-    constexpr int SU = sizeof(TS) == 4 ? (NV == 1 ? 4 : 4) : 2;
-    const long long ss = q.stem_stride, os = q.out_stem_stride, K = q.K;
-    const int n_stems = q.n_stems;
-    const bool zero = q.zero_mask;
-    int s = 0;
-    if (n_stems >= SU) {
-        Vec<TS, V> x[SU][NV];
-        TC g[SU];
+template <typename TS> struct StemsInFlight { static constexpr int v = sizeof(TS) == 4 ? 4 : 2; };
+
+// SU stems of NV vectors with their gains: what a thread keeps in flight
+template <typename TS, typename TC, int V, int NV>
+struct StemGroup {
+    static constexpr int SU = StemsInFlight<TS>::v;
+    Vec<TS, V> x[SU][NV];
+    TC g[SU];
+    template <typename TO>
+    __device__ __forceinline__ void load(const GainMixPlane<TS, TO>& q, const TS* ps, const double* pg, long long vgap) {
 #pragma unroll
         for (int u = 0; u < SU; ++u) {
 #pragma unroll
-            for (int h = 0; h < NV; ++h) x[u][h] = load_vec<TS, V>(ps + u * ss + h * vgap);
-            g[u] = zero ? TC(0) : (TC)__ldg(pg + u * K);
+            for (int h = 0; h < NV; ++h) x[u][h] = load_vec<TS, V>(ps + u * q.stem_stride + h * vgap);
+            g[u] = q.zero_mask ? TC(0) : (TC)__ldg(pg + u * q.K);
         }
-        mix_stem<TS, TC, TO, V, NV, true>(x[0], g[0], acc, po, vgap);
+    }
+};
+
+template <typename TS, typename TC, typename TO, int V, int NV>
+__device__ __forceinline__ void mix_stems(const GainMixPlane<TS, TO>& q, const TS* ps, const double* pg, TO* po,
+                                          long long vgap, TC (&acc)[NV][V], StemGroup<TS, TC, V, NV>& grp, bool loaded) {
+    constexpr int SU = StemsInFlight<TS>::v;
+    const long long ss = q.stem_stride, os = q.out_stem_stride, K = q.K;
+    const int n_stems = q.n_stems;
+    int s = 0;
+    if (n_stems >= SU) {
+        if (!loaded) grp.load(q, ps, pg, vgap);            // `loaded`: the caller prefetched the first SU stems
+        mix_stem<TS, TC, TO, V, NV, true>(grp.x[0], grp.g[0], acc, po, vgap);
 #pragma unroll
-        for (int u = 1; u < SU; ++u) mix_stem<TS, TC, TO, V, NV, false>(x[u], g[u], acc, po ? po + u * os : nullptr, vgap);
+        for (int u = 1; u < SU; ++u) mix_stem<TS, TC, TO, V, NV, false>(grp.x[u], grp.g[u], acc, po ? po + u * os : nullptr, vgap);
         s = SU; ps += SU * ss; pg += SU * K; if (po) po += SU * os;
         for (; s + SU <= n_stems; s += SU) {
+            grp.load(q, ps, pg, vgap);
 #pragma unroll
-            for (int u = 0; u < SU; ++u) {
-#pragma unroll
-                for (int h = 0; h < NV; ++h) x[u][h] = load_vec<TS, V>(ps + u * ss + h * vgap);
-                g[u] = zero ? TC(0) : (TC)__ldg(pg + u * K);
-            }
-#pragma unroll
-            for (int u = 0; u < SU; ++u) mix_stem<TS, TC, TO, V, NV, false>(x[u], g[u], acc, po ? po + u * os : nullptr, vgap);
+            for (int u = 0; u < SU; ++u) mix_stem<TS, TC, TO, V, NV, false>(grp.x[u], grp.g[u], acc, po ? po + u * os : nullptr, vgap);
             ps += SU * ss; pg += SU * K; if (po) po += SU * os;
         }
     }
@@ -218,7 +224,7 @@ __device__ __forceinline__ void mix_stems(const GainMixPlane<TS, TO>& q, const T
         Vec<TS, V> x[NV];
 #pragma unroll
         for (int h = 0; h < NV; ++h) x[h] = load_vec<TS, V>(ps + h * vgap);
-        const TC g = zero ? TC(0) : (TC)__ldg(pg);
+        const TC g = q.zero_mask ? TC(0) : (TC)__ldg(pg);
         if (s == 0) mix_stem<TS, TC, TO, V, NV, true>(x, g, acc, po, vgap);
         else mix_stem<TS, TC, TO, V, NV, false>(x, g, acc, po, vgap);
         ps += ss; pg += K; if (po) po += os;
@@ -274,9 +280,10 @@ __device__ __forceinline__ void gain_mix_vector(const GainMixPlane<TS, TO>& q, l
     TC acc[1][V];
 #pragma unroll
     for (int j = 0; j < V; ++j) acc[0][j] = TC(0);
-    if (i0 + V <= run.end)
-        mix_stems<TS, TC, TO, V, 1>(q, q.base + i0, q.gains + run.k0, q.stems_out ? q.stems_out + i0 : nullptr, 0, acc);
-    else
+    if (i0 + V <= run.end) {
+        StemGroup<TS, TC, V, 1> grp;
+        mix_stems<TS, TC, TO, V, 1>(q, q.base + i0, q.gains + run.k0, q.stems_out ? q.stems_out + i0 : nullptr, 0, acc, grp, false);
+    } else
         mix_boundary_vector<TS, TC, TO, V>(q, i0, run, acc[0]);
     finish_vector<TC, TO, V>(acc[0], o, q.mix ? q.mix + i0 : nullptr, loc_peak, loc_sq);
 }
@@ -376,12 +383,17 @@ gain_mix_chunks_kernel(const GainMixParams p, const typename std::conditional<kK
     double loc_peak = 0.0, loc_sq = 0.0;
     GainRun run;
     run.k0 = -1; run.end = 0;
+    // The first SU stems of the NEXT chunk are requested before the epilogue of this one (rounding, statistics,
+    // store and, with the meter part, ~130 instructions of table products and butterfly that touch no global memory).
+    StemGroup<TS, TC, V, 2> grp;
+    bool prefetched = false;                   // warp-uniform: grp holds the first stems of chunk `ch` of this plane
     for (long long item = t0; item < t1; ++item, ++ch) {
         if (ch == kw.n_chunks) {               // next plane
             const double m = dam_warp_max(loc_peak), sq = dam_warp_sum(loc_sq);
             if (lane == 0 && p.peak) atomic_max_nonneg(p.peak + row, m);
             if (lane == 0 && p.sumsq) atomicAdd(p.sumsq + row, sq);
             loc_peak = 0.0; loc_sq = 0.0;
+            prefetched = false;
             ++row; ch = 0;
             q = gain_mix_plane<TS, TO>(p, row % p.n_channels, row / p.n_channels);
             run.k0 = -1; run.end = 0;
@@ -399,11 +411,22 @@ gain_mix_chunks_kernel(const GainMixParams p, const typename std::conditional<kK
                 for (int j = 0; j < V; ++j) acc[h][j] = TC(0);
             const long long at = i0c + lane * V;
             mix_stems<TS, TC, TO, V, 2>(q, q.base + at, q.gains + run.k0, q.stems_out ? q.stems_out + at : nullptr,
-                                        kKwChunk / 2, acc);
+                                        kKwChunk / 2, acc, grp, prefetched);
+            // the first stems of the NEXT chunk are requested now: they fly while this chunk is rounded, stored,
+            // measured (peak, sum of squares) and, with the meter part, run through the butterfly
+            prefetched = false;
+            {
+                const long long nxt = i0c + 2 * kKwChunk;      // end of the next chunk
+                if (q.n_stems >= StemsInFlight<TS>::v && item + 1 < t1 && ch + 1 < kw.n_chunks && nxt <= run.end && nxt <= n) {
+                    grp.load(q, q.base + at + kKwChunk, q.gains + run.k0, kKwChunk / 2);
+                    prefetched = true;
+                }
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h)
                 finish_vector<TC, TO, V>(acc[h], o[h], q.mix ? q.mix + at + h * (kKwChunk / 2) : nullptr, loc_peak, loc_sq);
         } else {
+            prefetched = false;
             GainRun r2 = run;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {

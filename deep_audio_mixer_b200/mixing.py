@@ -53,8 +53,9 @@ def gain_mix(stems: torch.Tensor, gains, interp_coef: int = None, hold_single: b
         out_dtype = compute_dtype
     mix = torch.empty((B, C, N), dtype=out_dtype, device=dev) if want_mix else None
     st_out = torch.empty((B, S, C, N), dtype=out_dtype, device=dev) if want_stems else None
-    peak = torch.zeros((B, C), dtype=torch.float64, device=dev) if want_stats else None
-    sumsq = torch.zeros((B, C), dtype=torch.float64, device=dev) if want_stats else None
+    stats = torch.zeros((2, B, C), dtype=torch.float64, device=dev) if want_stats else None     # one fill for both
+    peak = stats[0] if want_stats else None
+    sumsq = stats[1] if want_stats else None
     common = (_lib.ptr(stems), _lib.dtype_code(stems.dtype), B, stems.stride(0) if B > 1 else 0,
               S, C, N, stems.stride(1), stems.stride(2),
               _lib.ptr(g), K, int(interp_coef), int(bool(hold_single)), _lib.dtype_code(compute_dtype),

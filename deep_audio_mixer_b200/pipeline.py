@@ -95,7 +95,10 @@ class SegmentBatchPipeline:
     def stage_gains(self, m: torch.Tensor, B: int, nc: int) -> torch.Tensor:
         """head outputs m [B*nc, 4] -> amplitude gains [B, 4, nc]: 10**(0.5 m) in float32 like the
         reference (data/dataset_utils.py:46-50), widened to float64 for the mask."""
-        return torch.pow(10.0, 0.5 * m.float()).double().reshape(B, nc, 4).permute(0, 2, 1).contiguous()
+        g32 = torch.pow(10.0, 0.5 * m.float())
+        out = torch.empty((B, 4, nc), dtype=torch.float64, device=m.device)
+        out.copy_(g32.reshape(B, nc, 4).permute(0, 2, 1))           # widening and transposition in one kernel
+        return out
 
     def stage_mix(self, buses: torch.Tensor, gains: torch.Tensor, for_meter: bool = True):
         """zero-order-hold masks, per-bus products, stem sum, peak and sum of squares (kernel K2).  With
