@@ -366,8 +366,9 @@ def run_ours(args):
     stages['stft_db'], _ = time_graph(lambda: pipe.features(mono, feats_buf))
     gains = pipe.stage_gains(m, N_SEG, nc)
     stages['gain_mix'], mixres = time_graph(lambda: pipe.stage_mix(buses, gains))
-    stages['loudness'], lufs = time_graph(lambda: pipe.stage_loudness(mixres['mix'], mixres['kw_workspace']))
-    stages['scale'], _ = time_graph(lambda: pipe.stage_normalise(mixres['mix'], lufs))
+    stages['loudness'], (lufs, factor) = time_graph(lambda: pipe.stage_loudness(mixres['mix'], mixres['kw_workspace'],
+                                                                                with_gain=True))
+    stages['scale'], _ = time_graph(lambda: pipe.stage_normalise(mixres['mix'], lufs, factor))
     mono_keep = mono
     del buses, mono, mixres
     stem_s_per_step = N_SEG * N_STEMS * SECONDS

@@ -37,6 +37,8 @@ SIGNATURES = {
     'dam_row_reduce': (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp, _vp]),
     'dam_kweight_workspace_bytes': (_c.c_size_t, [_i64, _i64]),
     'dam_gated_loudness': (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i64, _d, _vp, _vp]),
+    'dam_gated_loudness_gain': (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i64, _d, _d, _vp, _vp, _vp]),
+    'dam_head_gains': (_i, [_vp, _i64, _i64, _i64, _vp, _vp]),
     'dam_kweight_segments': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _c.POINTER(_d), _vp, _i64, _vp, _vp,
                                   _c.c_size_t, _vp]),
     'dam_kweight_segments_resume': (_i, [_vp, _i, _i64, _i64, _i64, _i64, _c.POINTER(_d), _vp, _i64, _vp, _vp,

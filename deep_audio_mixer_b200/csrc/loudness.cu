@@ -124,6 +124,7 @@ struct KwParams {
     double* seg_sumsq;             // [n_rows][n_seg]
     double* states;                // workspace [n_rows][parts * cpp][4] (transposed per part, see state_ptr)
     double* partials;              // workspace [n_rows * n_chunks][2]: pass C's per-chunk sums for the (at most two) segments it touches
+    int zero_seg;                  // the scan clears seg_sumsq first (dam_kweight_segments_resume OVERWRITES its output)
 };
 
 // Filter state of chunk c of a row (layout: kweight_common.cuh).
@@ -314,6 +315,8 @@ __global__ void __launch_bounds__(kScanBlock) kw_scan_kernel(const KwParams p) {
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned part = p.parts > 1 ? cluster.block_rank() : 0;
     const long long row = blockIdx.x / p.parts;
+    if (p.zero_seg && part == 0)
+        for (long long k = threadIdx.x; k < p.n_seg; k += kScanBlock) p.seg_sumsq[row * p.n_seg + k] = 0.0;
     double* st = p.states + ((row * p.parts + part) * p.cpp + threadIdx.x) * 4;   // slot of step k: st + k * kScanBlock * 4
     const long long u = threadIdx.x;
     const long long c0 = (long long)part * p.cpp + u * p.super;
@@ -516,6 +519,8 @@ struct GateParams {
     const long long* last;         // [n_blocks] one past the last segment
     double inv_len;                // 1 / (block_size * rate)
     double* out;                   // [n_signals]
+    double target;                 // gain_out[sig] = 10^((target - L) / 20) (evaluation.py:64), when gain_out is set
+    double* gain_out;              // [n_signals] or null
 };
 
 __device__ __forceinline__ double gate_block_sum(double v, double* s_buf) {
@@ -563,7 +568,11 @@ __global__ void __launch_bounds__(kGateBlock) gated_loudness_kernel(const GatePa
             w += G[c] * zavg[c];
         }
         if (pass == 0) gamma = -0.691 + 10.0 * log10(w) - 10.0;      // NaN if nothing passed: pass 2 keeps nothing
-        else if (threadIdx.x == 0) p.out[sig] = -0.691 + 10.0 * log10(w);
+        else if (threadIdx.x == 0) {
+            const double L = -0.691 + 10.0 * log10(w);
+            p.out[sig] = L;
+            if (p.gain_out) p.gain_out[sig] = pow(10.0, (p.target - L) / 20.0);
+        }
     }
 }
 
@@ -664,6 +673,7 @@ static int kweight_segments(const void* x, int dtype, int64_t n_rows, int64_t n_
     }
     p.seg_bounds = reinterpret_cast<const long long*>(seg_bounds); p.n_seg = n_seg;
     p.seg_sumsq = seg_sumsq; p.states = reinterpret_cast<double*>(workspace);
+    p.zero_seg = mode == KW_RESUME ? 1 : 0;
     p.partials = p.states + (size_t)n_rows * (size_t)p.parts * (size_t)p.cpp * 4;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     static std::mutex mu;
@@ -742,9 +752,9 @@ int dam_kw_chunk_states(const void* x, int dtype, int64_t n_rows, int64_t n_samp
                             workspace_bytes, stream, KW_STATES_ONLY);
 }
 
-extern "C" int dam_gated_loudness(const double* seg_sumsq, int64_t n_signals, int n_channels, int64_t n_seg,
-                                  const int64_t* block_first, const int64_t* block_last, int64_t n_blocks,
-                                  double inv_block_len, double* lufs_out, void* stream) {
+static int gated_loudness(const double* seg_sumsq, int64_t n_signals, int n_channels, int64_t n_seg,
+                          const int64_t* block_first, const int64_t* block_last, int64_t n_blocks,
+                          double inv_block_len, double target_lufs, double* lufs_out, double* gain_out, void* stream) {
     dam_clear_error();
     DAM_CHECK_ARG(seg_sumsq && block_first && block_last && lufs_out, "null pointer argument");
     DAM_CHECK_ARG(n_channels >= 1 && n_channels <= kMaxCh, "n_channels must be in [1, 5]");
@@ -755,9 +765,27 @@ extern "C" int dam_gated_loudness(const double* seg_sumsq, int64_t n_signals, in
     p.first = reinterpret_cast<const long long*>(block_first);
     p.last = reinterpret_cast<const long long*>(block_last);
     p.inv_len = inv_block_len; p.out = lufs_out;
+    p.target = target_lufs; p.gain_out = gain_out;
     { gated_loudness_kernel<<<(unsigned)n_signals, kGateBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p); dam_note_launch(); }
     DAM_CHECK_CUDA(cudaGetLastError());
     return DAM_OK;
+}
+
+extern "C" int dam_gated_loudness(const double* seg_sumsq, int64_t n_signals, int n_channels, int64_t n_seg,
+                                  const int64_t* block_first, const int64_t* block_last, int64_t n_blocks,
+                                  double inv_block_len, double* lufs_out, void* stream) {
+    return gated_loudness(seg_sumsq, n_signals, n_channels, n_seg, block_first, block_last, n_blocks, inv_block_len, 0.0,
+                          lufs_out, nullptr, stream);
+}
+
+extern "C" int dam_gated_loudness_gain(const double* seg_sumsq, int64_t n_signals, int n_channels, int64_t n_seg,
+                                       const int64_t* block_first, const int64_t* block_last, int64_t n_blocks,
+                                       double inv_block_len, double target_lufs, double* lufs_out, double* gain_out,
+                                       void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(gain_out != nullptr, "null pointer argument");
+    return gated_loudness(seg_sumsq, n_signals, n_channels, n_seg, block_first, block_last, n_blocks, inv_block_len,
+                          target_lufs, lufs_out, gain_out, stream);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -938,6 +938,32 @@ extern "C" int dam_gain_mix_kweight(const void* stems, int stems_dtype, int64_t 
                           kw_coeffs_host, kw_workspace, kw_workspace_bytes, stream);
 }
 
+// N3: head outputs of one batch of chunks -> per-chunk amplitude gains in the layout K2 reads.
+//   gains[b][s][c] = (double) powf(10, 0.5 * m[(b * n_chunks + c) * n_stems + s])
+// i.e. data/dataset_utils.py:46-50 (10 ** (0.5 m) in float32) widened for the float64 mask -- what three elementwise
+// launches (scale, power, widening transposition) did before.
+__global__ void __launch_bounds__(kBlock) head_gains_kernel(const float* __restrict__ m, long long n_batch, long long n_chunks,
+                                                            long long n_stems, double* __restrict__ out) {
+    const long long total = n_batch * n_stems * n_chunks;
+    for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < total; i += (long long)gridDim.x * kBlock) {
+        const long long c = i % n_chunks, bs = i / n_chunks;
+        const long long s = bs % n_stems, b = bs / n_stems;
+        out[i] = (double)powf(10.0f, __fmul_rn(0.5f, m[(b * n_chunks + c) * n_stems + s]));
+    }
+}
+
+extern "C" int dam_head_gains(const float* m, int64_t n_batch, int64_t n_chunks, int64_t n_stems, double* gains_out,
+                              void* stream) {
+    dam_clear_error();
+    DAM_CHECK_ARG(m && gains_out, "null pointer argument");
+    DAM_CHECK_ARG(n_batch >= 0 && n_chunks >= 1 && n_stems >= 1, "bad sizes");
+    if (n_batch == 0) return DAM_OK;
+    { head_gains_kernel<<<grid_for(n_batch * n_chunks * n_stems, 4), kBlock, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+          m, n_batch, n_chunks, n_stems, gains_out); dam_note_launch(); }
+    DAM_CHECK_CUDA(cudaGetLastError());
+    return DAM_OK;
+}
+
 extern "C" int dam_bus_sum(const void* stems, int dtype, int64_t n_batch, int64_t batch_stride,
                            int64_t n_stems, int64_t n_elems, int64_t stem_stride,
                            const int32_t* group_host, int n_bus, double input_scale, void* out, void* mono_out,

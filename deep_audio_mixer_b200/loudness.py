@@ -146,7 +146,7 @@ class Meter:
                 raise ValueError('kw_workspace belongs to another mix (gain_mix(..., meter=) returns the pair)')
         else:
             seg, ws, ws_bytes = self.workspace_for(R, n, dev)
-        seg.zero_()
+            seg.zero_()                      # dam_kweight_segments ADDS; the resumed form clears its output itself
         coeffs = (ctypes.c_double * 10)(*self._coeffs)
         entry = lib.dam_kweight_segments_resume if resume else lib.dam_kweight_segments
         with torch.cuda.device(dev):
@@ -156,9 +156,11 @@ class Meter:
         _lib.check(rc, 'dam_kweight_segments')
         return seg, first, last
 
-    def integrated_loudness_device(self, signals: torch.Tensor, kw_workspace=None) -> torch.Tensor:
+    def integrated_loudness_device(self, signals: torch.Tensor, kw_workspace=None, gain_target: float = None):
         """signals [R, C, N] CUDA -> float64 CUDA tensor [R] of LUFS values; K-weighting, block sums
-        and gating all run on the device with no host synchronisation.  ``kw_workspace``: see _segment_sums."""
+        and gating all run on the device with no host synchronisation.  ``kw_workspace``: see _segment_sums.
+        With ``gain_target`` (LUFS) returns (lufs, gain): gain = 10**((gain_target - lufs) / 20), the factor of
+        pyln.normalize.loudness / evaluation.py:64, from the same launch."""
         R, C, n = signals.shape
         if n < self.block_size * self.rate:
             raise ValueError('Audio must have length greater than the block size.')
@@ -169,13 +171,18 @@ class Meter:
             rows = rows.contiguous()
         seg, _, _ = self._segment_sums(rows, kw_workspace)
         geo = self._geometry(n, rows.device)
-        out = torch.empty(R, dtype=torch.float64, device=rows.device)
+        out = torch.empty((2, R) if gain_target is not None else (R,), dtype=torch.float64, device=rows.device)
+        lib = _lib.lib()
         with torch.cuda.device(rows.device):
-            rc = _lib.lib().dam_gated_loudness(_lib.ptr(seg), R, C, geo[1], _lib.ptr(geo[5]), _lib.ptr(geo[6]),
-                                               geo[4], 1.0 / (self.block_size * self.rate), _lib.ptr(out),
-                                               _lib.stream_ptr())
+            if gain_target is None:
+                rc = lib.dam_gated_loudness(_lib.ptr(seg), R, C, geo[1], _lib.ptr(geo[5]), _lib.ptr(geo[6]),
+                                            geo[4], 1.0 / (self.block_size * self.rate), _lib.ptr(out), _lib.stream_ptr())
+            else:
+                rc = lib.dam_gated_loudness_gain(_lib.ptr(seg), R, C, geo[1], _lib.ptr(geo[5]), _lib.ptr(geo[6]),
+                                                 geo[4], 1.0 / (self.block_size * self.rate), float(gain_target),
+                                                 _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.stream_ptr())
         _lib.check(rc, 'dam_gated_loudness')
-        return out
+        return out if gain_target is None else (out[0], out[1])
 
     @staticmethod
     def gated_loudness(z: np.ndarray) -> float:

@@ -80,6 +80,22 @@ def gain_mix(stems: torch.Tensor, gains, interp_coef: int = None, hold_single: b
     return dict(mix=mix, stems=st_out, peak=peak, sumsq=sumsq, kw_workspace=kw_workspace)
 
 
+def head_gains(m: torch.Tensor, n_batch: int, n_chunks: int) -> torch.Tensor:
+    """CNN head outputs m [n_batch * n_chunks, S] float32 (row = chunk c of song b) -> amplitude gains
+    [n_batch, S, n_chunks] float64 for ``gain_mix``: 10 ** (0.5 m) in float32 (data/dataset_utils.py:46-50), widened.
+    One launch (dam_head_gains); the same bits as torch.pow(10.0, 0.5 * m).double() transposed."""
+    _check_cuda(m, 'm')
+    if m.dim() != 2 or m.shape[0] != n_batch * n_chunks:
+        raise ValueError('m must be [n_batch * n_chunks, S]')
+    m = m.float().contiguous()
+    S = m.shape[1]
+    out = torch.empty((n_batch, S, n_chunks), dtype=torch.float64, device=m.device)
+    with torch.cuda.device(m.device):
+        rc = _lib.lib().dam_head_gains(_lib.ptr(m), n_batch, n_chunks, S, _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, 'dam_head_gains')
+    return out
+
+
 def stem_sum(stems: torch.Tensor, out_dtype=None, meter=None):
     """np.sum(np.array(list(d.values())), axis=0) (evaluation.py:59-60) for stems [S, C, N].  With ``meter`` (the sum is
     measured next, evaluation.py:63) returns (sum, kw_workspace) for ``meter.integrated_loudness(sum.t(), kw_workspace)``."""

@@ -94,11 +94,8 @@ class SegmentBatchPipeline:
 
     def stage_gains(self, m: torch.Tensor, B: int, nc: int) -> torch.Tensor:
         """head outputs m [B*nc, 4] -> amplitude gains [B, 4, nc]: 10**(0.5 m) in float32 like the
-        reference (data/dataset_utils.py:46-50), widened to float64 for the mask."""
-        g32 = torch.pow(10.0, 0.5 * m.float())
-        out = torch.empty((B, 4, nc), dtype=torch.float64, device=m.device)
-        out.copy_(g32.reshape(B, nc, 4).permute(0, 2, 1))           # widening and transposition in one kernel
-        return out
+        reference (data/dataset_utils.py:46-50), widened to float64 for the mask (one launch, dam_head_gains)."""
+        return mixing.head_gains(m, B, nc)
 
     def stage_mix(self, buses: torch.Tensor, gains: torch.Tensor, for_meter: bool = True):
         """zero-order-hold masks, per-bus products, stem sum, peak and sum of squares (kernel K2).  With
@@ -108,15 +105,17 @@ class SegmentBatchPipeline:
         return mixing.gain_mix(buses, gains, interp_coef=int(N / gains.shape[-1]), compute_dtype=torch.float64,
                                want_mix=True, want_stats=True, meter=self.meter if for_meter else None)
 
-    def stage_loudness(self, mix: torch.Tensor, kw_workspace=None) -> torch.Tensor:
+    def stage_loudness(self, mix: torch.Tensor, kw_workspace=None, with_gain: bool = False):
         """BS.1770 integrated loudness of every mix, on the device (kernel K4 + gating); with the ``kw_workspace``
-        of ``stage_mix`` it reads the mix once."""
-        return self.meter.integrated_loudness_device(mix, kw_workspace)
+        of ``stage_mix`` it reads the mix once.  ``with_gain``: returns (lufs, factor) with the normalisation factor
+        10**((target - L)/20) from the gating launch."""
+        return self.meter.integrated_loudness_device(mix, kw_workspace, gain_target=self.target if with_gain else None)
 
-    def stage_normalise(self, mix: torch.Tensor, lufs: torch.Tensor) -> torch.Tensor:
+    def stage_normalise(self, mix: torch.Tensor, lufs: torch.Tensor, factor: torch.Tensor = None) -> torch.Tensor:
         """x * 10**((target - L)/20) (kernel K5; the factors never leave the device)."""
         B, C, N = mix.shape
-        factor = torch.pow(10.0, (self.target - lufs) / 20.0)
+        if factor is None:
+            factor = torch.pow(10.0, (self.target - lufs) / 20.0)
         return mixing.scale_rows(mix.reshape(B, C * N), factor).reshape(B, C, N)
 
     def run(self, raw: torch.Tensor, m: torch.Tensor = None, model=None, feats_out: torch.Tensor = None):
@@ -138,9 +137,9 @@ class SegmentBatchPipeline:
         self._ev('gain0')
         res = self.stage_mix(buses, gains, for_meter=self.fuse_meter)
         self._ev('mix1')
-        lufs = self.stage_loudness(res['mix'], res['kw_workspace'])                 # [B] on the device
+        lufs, factor = self.stage_loudness(res['mix'], res['kw_workspace'], with_gain=True)    # [B] on the device
         self._ev('loud1')
-        norm = self.stage_normalise(res['mix'], lufs)
+        norm = self.stage_normalise(res['mix'], lufs, factor)
         self._ev('scale1')
         return dict(mix=norm, lufs=lufs, peak=res['peak'], sumsq=res['sumsq'], features=feats, m=m)
 
@@ -235,8 +234,7 @@ class SongBatchMixdown:
         B, S, C, N = stems.shape
         feats = self.features(stems, feats_out) if want_features else None
         res = mixing.gain_mix(stems, gains, compute_dtype=torch.float64, want_mix=True, want_stats=True, meter=self.meter)
-        lufs = self.meter.integrated_loudness_device(res['mix'], res['kw_workspace'])
-        factor = torch.pow(10.0, (self.target - lufs) / 20.0)
+        lufs, factor = self.meter.integrated_loudness_device(res['mix'], res['kw_workspace'], gain_target=self.target)
         norm = mixing.scale_rows(res['mix'].reshape(B, C * N), factor).reshape(B, C, N)
         return dict(features=feats, mix=norm, lufs=lufs, peak=res['peak'], sumsq=res['sumsq'])
 

@@ -161,6 +161,15 @@ int dam_gain_mix_kweight(const void* stems, int stems_dtype, int64_t n_batch, in
                          void* stream);
 
 /*
+ * N3: CNN head outputs -> per-chunk amplitude gains in the layout dam_gain_mix reads.
+ * Replaces  scalar_dB_to_amplitude on every head output    data/dataset_utils.py:46-50, inference_utils.py:125-131
+ *   m          DEVICE float32 [n_batch * n_chunks, n_stems] (row = chunk c of song b, the model's batch order)
+ *   gains_out  DEVICE float64 [n_batch, n_stems, n_chunks]: (double) powf(10, 0.5 * m), the float32 power the reference
+ *              computes, widened for the float64 mask.
+ */
+int dam_head_gains(const float* m, int64_t n_batch, int64_t n_chunks, int64_t n_stems, double* gains_out, void* stream);
+
+/*
  * N2: S raw stems -> n_bus bus sums (summed_track += track in stem order, in the audio dtype).
  * Replaces  sum_stems  data/medleydb_data_surgery.ipynb:305-332.
  *   stems: n_batch songs of [n_stems, n_elems] (stems stem_stride apart, songs batch_stride apart),
@@ -247,7 +256,8 @@ int dam_kweight_segments(const void* x, int dtype, int64_t n_rows, int64_t n_sam
                          const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,
                          double* seg_sumsq, void* workspace, size_t workspace_bytes, void* stream);
 /* Same, for a signal whose chunk end states dam_gain_mix_kweight already left in `workspace` (x = its mix_out,
- * unit sample stride, row_stride = n_samples): starts at the scan, reads x once instead of twice. */
+ * unit sample stride, row_stride = n_samples): starts at the scan, reads x once instead of twice.  Unlike
+ * dam_kweight_segments it OVERWRITES seg_sumsq (the scan clears it), so the caller need not zero it. */
 int dam_kweight_segments_resume(const void* x, int dtype, int64_t n_rows, int64_t n_samples,
                                 int64_t row_stride, int64_t samp_stride,
                                 const double* coeffs_host, const int64_t* seg_bounds, int64_t n_seg,
@@ -283,6 +293,13 @@ int dam_kweight_blocks(const void* x, int dtype, int64_t n_rows, int64_t n_sampl
 int dam_gated_loudness(const double* seg_sumsq, int64_t n_signals, int n_channels, int64_t n_seg,
                        const int64_t* block_first, const int64_t* block_last, int64_t n_blocks,
                        double inv_block_len, double* lufs_out, void* stream);
+/* Same, plus the normalisation gain of evaluation.py:64 / pyln.normalize.loudness: gain_out[i] =
+ * 10^((target_lufs - L_i) / 20), DEVICE double[n_signals] -- what dam_scale_rows multiplies by. */
+int dam_gated_loudness_gain(const double* seg_sumsq, int64_t n_signals, int n_channels, int64_t n_seg,
+                            const int64_t* block_first, const int64_t* block_last, int64_t n_blocks,
+                            double inv_block_len, double target_lufs, double* lufs_out, double* gain_out,
+                            void* stream);
+
 
 /* Number of frames dam_stft_db produces for n_samples (1 + n_samples / hop). */
 int64_t dam_stft_num_frames(int64_t n_samples, int hop);

@@ -89,3 +89,16 @@ def test_long_rows_scan_over_a_cluster_of_ctas(cuda_device, n):
     z = meter.block_energies(torch.from_numpy(np.ascontiguousarray(x.T)).cuda())
     z_ref = OL.block_energies(x, 44100)
     assert np.max(np.abs(z - z_ref) / (np.abs(z_ref) + 1e-300)) < 1e-9
+
+
+def test_gating_launch_also_returns_the_normalisation_gain(cuda_device):
+    """dam_gated_loudness_gain: the factor of evaluation.py:64 from the gating launch equals 10 ** ((target - L) / 20)
+    evaluated by torch on the loudness the same launch returned."""
+    gen = torch.Generator(device='cuda').manual_seed(11)
+    x = (torch.rand((5, 2, 3 * 44100), generator=gen, device='cuda', dtype=torch.float64) - 0.5)
+    x *= torch.tensor([1.0, 0.3, 0.05, 2.0, 1e-3], device='cuda', dtype=torch.float64)[:, None, None]
+    meter = Meter(44100)
+    lufs = meter.integrated_loudness_device(x).clone()
+    lufs2, gain = meter.integrated_loudness_device(x, gain_target=-20.0)
+    assert torch.equal(lufs2, lufs)
+    assert torch.equal(gain, torch.pow(10.0, (-20.0 - lufs) / 20.0))

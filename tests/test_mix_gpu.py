@@ -227,3 +227,23 @@ def test_gain_mix_with_meter_states_is_bit_identical_to_mixing_then_measuring(cu
     total, kw = mixing.stem_sum(song, meter=meter)
     assert torch.equal(total, mixing.stem_sum(song))
     assert meter.integrated_loudness(total.t(), kw) == meter.integrated_loudness(mixing.stem_sum(song).t())
+
+
+def test_head_gains_kernel_equals_the_torch_expression_it_replaces(cuda_device):
+    """dam_head_gains against torch.pow(10.0, 0.5 * m).double() transposed (what the pipeline ran before): same bits,
+    on random head outputs, on a dense sweep of float32 values and on the edge values of the power function."""
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    B, nc, S = 7, 13, 4
+    m = torch.randn((B * nc, S), generator=gen, device='cuda') * 2.0
+    ref = torch.pow(10.0, 0.5 * m.float()).double().reshape(B, nc, S).permute(0, 2, 1).contiguous()
+    assert torch.equal(mixing.head_gains(m, B, nc), ref)
+    sweep = torch.linspace(-12.0, 12.0, 4_000_000, device='cuda').reshape(-1, 4)
+    edge = torch.tensor([0.0, -0.0, 1.0, -1.0, 2.0, 80.0, -80.0, 200.0, -200.0, float('inf'), -float('inf'), 1e-30],
+                        device='cuda').reshape(-1, 4)
+    for mm in (sweep, edge):
+        n = mm.shape[0]
+        got = mixing.head_gains(mm, n, 1)
+        want = torch.pow(10.0, 0.5 * mm).double().reshape(n, 1, 4).permute(0, 2, 1).contiguous()
+        assert torch.equal(got, want)
+    nan = mixing.head_gains(torch.full((1, 4), float('nan'), device='cuda'), 1, 1)
+    assert torch.isnan(nan).all()
